@@ -1,0 +1,247 @@
+// Shared definitions of the fused sm_100a AAE train step (device side).
+//
+// Reference semantics: /root/reference/sc/clustering/trainer.py:103-304 (loop body + eval block),
+// model.py:330-378 (FCEncoder), 518-570 (FCDecoder), 631-663 (DiscriminatorFC), functions.py:37-219.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rankaae_b200.h"
+
+namespace raae {
+
+constexpr int kH = RAAE_HIDDEN;   // hidden width
+constexpr int kTM = 128;          // batch rows per tile
+constexpr int kLD = 68;           // smem leading dimension of a [rows][64] tile (16 B aligned, conflict-free)
+constexpr int kLDW = 260;         // smem leading dimension of a [rows][256] tile
+constexpr int kThreads = 256;
+constexpr int kZ = RAAE_ZPAD;     // padded latent width
+constexpr int kMaxDim = 256;      // max dim_in / dim_out
+constexpr float kBnEps = 1e-5f;
+constexpr float kBnMomentum = 0.1f;
+constexpr float kAdamEps = 1e-8f;
+
+enum Phase { kAdv = 0, kCorr = 1, kRecon = 2, kMI = 3, kSmooth = 4 };
+enum NetId { kE = 0, kD = 1, kS = 2 };
+
+// scratch block sub-buffers (offsets in floats from the trial's scratch base)
+struct ScratchLayout {
+  int xn;                       // [rows][xld]   noised spectra of the batch (trainer.py:112)
+  int aux;                      // [rows][kZ]    descriptors of the batch
+  int uE[RAAE_MAX_LAYERS];      // [rows][64]    pre-activation of encoder hidden layer l
+  int zE;                       // [rows][kZ]    pre-BN output of the last encoder Linear
+  int dz;                       // [rows][kZ]    gradient w.r.t. the encoder output
+  int uD[RAAE_MAX_LAYERS];      // [rows][64]    pre-activation of decoder hidden layer l
+  int v;                        // [rows][vld]   pre-activation of the decoder output (MI phase) / its gradient
+  int g[2];                     // [rows][64]    gradient w.r.t. a hidden block's BN output (ping-pong)
+  int zs;                       // [rows][kZ]    z_sample (MI phase)
+  int rank;                     // [kZ][rows]    validation: per-style ranks (Spearman)
+  int xld, vld;                 // padded row strides
+  int total;
+};
+
+struct KParams {
+  raae_layout lay;
+  raae_config cfg;
+  ScratchLayout sl;
+  float* state;
+  float* scratch;
+  const double* hp;
+  const float* spec_train;
+  const float* aux_train;
+  int n_train;
+  const float* spec_val;
+  const float* aux_val;
+  int n_val;
+  const float* shapiro_w;
+};
+
+struct RunArgs {
+  int trial0;                   // first trial handled by blockIdx.x == 0
+  int epoch;
+  int n_steps;                  // batches in this launch (production) — ignored in debug mode
+  int debug;                    // 1 = teacher-forced single step driven by `dbg`
+  const int32_t* perm;          // [n_trials][n_train] shuffled row order of this epoch (production)
+  float* out_losses;            // [n_trials][12] (production, may be null)
+  float* out_metrics;           // [n_trials][6]
+  raae_debug_io dbg;
+  raae_val_io val;
+};
+
+// ------------------------------------------------------------------------------------------
+// counter-based RNG (production mode).  Parity tests inject every draw explicitly, so the generator
+// only has to be statistically sound: two rounds of a 32-bit avalanche mixer keyed per stream.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t hash2(uint32_t key, uint32_t idx) { return mix32(mix32(idx ^ key) + key * 0x9e3779b9U); }
+
+enum StreamKind { kStreamXNoise = 1, kStreamEncMask = 16, kStreamDecMask = 80, kStreamDisMask = 120,
+                  kStreamZReal = 140, kStreamDisEpsReal = 141, kStreamDisEpsFake = 142, kStreamZSample = 143,
+                  kStreamValZSample = 150, kStreamValZReal = 151 };
+
+__device__ __forceinline__ uint32_t stream_key(uint32_t seed, uint32_t step_id, uint32_t kind) {
+  return mix32(seed ^ mix32(step_id * 256u + kind));
+}
+
+// standard normal for element idx of a stream (Box-Muller on two hashed uniforms per pair)
+__device__ __forceinline__ float normal_at(uint32_t key, uint32_t idx) {
+  uint32_t pair = idx >> 1;
+  uint32_t h1 = hash2(key, 2u * pair), h2 = hash2(key, 2u * pair + 1u);
+  float u1 = ((h1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  float u2 = ((h2 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.28318530717958647692f * u2, &s, &c);
+  return (idx & 1u) ? r * s : r * c;
+}
+
+struct MaskSrc {
+  const uint8_t* ptr;   // explicit keep-mask [rows][64] or null
+  uint32_t key;
+  uint32_t thresh;      // drop when the 16-bit draw < thresh; 0 = keep everything
+  float scale;          // 1 / (1 - p)
+};
+
+__device__ __forceinline__ bool mask_keep(const MaskSrc& m, int row, int c) {
+  if (m.ptr) return m.ptr[row * kH + c] != 0;
+  if (m.thresh == 0u) return true;
+  uint32_t idx = (uint32_t)(row * kH + c);
+  uint32_t h = hash2(m.key, idx >> 1);
+  uint32_t d = (idx & 1u) ? (h >> 16) : (h & 0xffffu);
+  return d >= m.thresh;
+}
+
+// four consecutive channels c..c+3 (c % 4 == 0): returns keep bits
+__device__ __forceinline__ uint32_t mask_keep4(const MaskSrc& m, int row, int c) {
+  if (m.ptr) {
+    uint32_t w = *reinterpret_cast<const uint32_t*>(m.ptr + row * kH + c);
+    return ((w & 0xffu) ? 1u : 0u) | ((w & 0xff00u) ? 2u : 0u) | ((w & 0xff0000u) ? 4u : 0u) | ((w & 0xff000000u) ? 8u : 0u);
+  }
+  if (m.thresh == 0u) return 0xfu;
+  uint32_t idx = (uint32_t)(row * kH + c);
+  uint32_t h0 = hash2(m.key, idx >> 1), h1 = hash2(m.key, (idx >> 1) + 1u);
+  return ((h0 & 0xffffu) >= m.thresh ? 1u : 0u) | ((h0 >> 16) >= m.thresh ? 2u : 0u) |
+         ((h1 & 0xffffu) >= m.thresh ? 4u : 0u) | ((h1 >> 16) >= m.thresh ? 8u : 0u);
+}
+
+// ------------------------------------------------------------------------------------------
+// scalar math restated from SURVEY.md Appendix A
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float prelu_f(float u, float a) { return u > 0.f ? u : a * u; }
+
+// nn.Softplus(beta=2, threshold=20): model.py:535
+__device__ __forceinline__ float softplus2_f(float v) {
+  float bv = 2.f * v;
+  return bv > 20.f ? v : 0.5f * log1pf(expf(bv));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float softplus2_grad_f(float v) {
+  float bv = 2.f * v;
+  return bv > 20.f ? 1.f : sigmoid_f(bv);
+}
+
+// 17-tap Gaussian (sigma 3) exactly as torch builds it in float32 (model.py:186-206)
+__device__ __constant__ float kGauss17[17] = {
+    0.0038155282381922007f, 0.008779441937804222f, 0.018076900392770767f, 0.03330628201365471f,
+    0.05491277202963829f,   0.08101504296064377f,  0.10695548355579376f,  0.1263529658317566f,
+    0.13357123732566833f,   0.1263529658317566f,   0.10695548355579376f,  0.08101504296064377f,
+    0.05491277202963829f,   0.03330628201365471f,  0.018076900392770767f, 0.008779441937804222f,
+    0.0038155282381922007f};
+
+// ------------------------------------------------------------------------------------------
+// register-tile SIMT contractions on smem tiles (FP32 FMA: the parity mode)
+// ------------------------------------------------------------------------------------------
+// C[m][n] += sum_k A[m*lda + k] * B[n*ldb + k]     m = ty + 16 i (i < 8), n = tx + 16 j (j < 4)
+template <int K>
+__device__ __forceinline__ void mma_nt(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                       float (&acc)[8][4], int ty, int tx) {
+#pragma unroll 2
+  for (int k = 0; k < K; k += 4) {
+    float4 a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(A + (ty + 16 * i) * lda + k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(B + (tx + 16 * j) * ldb + k);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+        acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+        acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+        acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+      }
+  }
+}
+
+// C[m][n] += sum_k A[m*lda + k] * B[k*ldb + n]     m = ty + 16 i (i < 8), n = 4 tx + j (j < 4)
+template <int K>
+__device__ __forceinline__ void mma_nn(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                       float (&acc)[8][4], int ty, int tx) {
+#pragma unroll 2
+  for (int k = 0; k < K; k += 4) {
+    float4 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(A + (ty + 16 * i) * lda + k);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      float4 b = *reinterpret_cast<const float4*>(B + (k + kk) * ldb + 4 * tx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+        acc[i][0] = fmaf(av, b.x, acc[i][0]);
+        acc[i][1] = fmaf(av, b.y, acc[i][1]);
+        acc[i][2] = fmaf(av, b.z, acc[i][2]);
+        acc[i][3] = fmaf(av, b.w, acc[i][3]);
+      }
+    }
+  }
+}
+
+// C[m0+i][n0+j] += sum_{r in [r0, r1)} A[r*lda + m0 + i] * B[r*ldb + n0 + j]      i, j < 8
+__device__ __forceinline__ void mma_tn8(const float* __restrict__ A, int lda, int m0, const float* __restrict__ B,
+                                        int ldb, int n0, int r0, int r1, float (&acc)[8][8]) {
+#pragma unroll 2
+  for (int r = r0; r < r1; ++r) {
+    float4 a0 = *reinterpret_cast<const float4*>(A + r * lda + m0);
+    float4 a1 = *reinterpret_cast<const float4*>(A + r * lda + m0 + 4);
+    float4 b0 = *reinterpret_cast<const float4*>(B + r * ldb + n0);
+    float4 b1 = *reinterpret_cast<const float4*>(B + r * ldb + n0 + 4);
+    float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+}
+
+// block-wide sum, result broadcast to every thread; `red` holds >= 8 floats of smem.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) s += red[w];
+  return s;
+}
+
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) s += red[w];
+  return s;
+}
+
+}  // namespace raae

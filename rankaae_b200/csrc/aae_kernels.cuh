@@ -1,0 +1,417 @@
+// Kernels: the persistent per-trial train kernel (all batches of an epoch), the validation/metrics
+// kernel (eval block + Shapiro-Wilk + Spearman + ReduceLROnPlateau), and the small state-init kernel.
+#pragma once
+#include "aae_stages.cuh"
+
+namespace raae {
+
+// functions.py:214-219, float64 like the reference's numpy scalar
+__device__ inline float alpha_schedule(const Ctx& c) {
+  double pct = (double)c.epoch / c.hp[RAAE_HP_MAX_EPOCH];
+  double a = (2.0 / (1.0 + exp(-1.0e4 / c.hp[RAAE_HP_ALPHA_FLAT_STEP] * pct)) - 1.0) * c.hp[RAAE_HP_ALPHA_LIMIT];
+  return (float)a;
+}
+
+// spec_in += randn_like(spec_in) * spec_noise (trainer.py:112) for the rows idx[0..B) of the training
+// split; descriptors of the same rows; z_sample of the MI phase.
+__device__ __noinline__ void build_batch(const Ctx& c, const int32_t* __restrict__ idx) {
+  const KParams& p = *c.p;
+  const int tid = threadIdx.x, dim = p.cfg.dim_in, xld = p.sl.xld, K = p.cfg.n_aux, ns = p.cfg.nstyle;
+  float* xn = c.sc + p.sl.xn;
+  float* aux = c.sc + p.sl.aux;
+  float* zs = c.sc + p.sl.zs;
+  __syncthreads();
+  if (c.a->debug) {
+    const raae_debug_io& d = c.a->dbg;
+    for (int i = tid; i < c.B * (dim >> 2); i += kThreads) {
+      int r = i / (dim >> 2), c4 = (i - r * (dim >> 2)) * 4;
+      *reinterpret_cast<float4*>(xn + (size_t)r * xld + c4) = *reinterpret_cast<const float4*>(d.x_noisy + (size_t)r * dim + c4);
+    }
+    for (int i = tid; i < c.B * kZ; i += kThreads) {
+      int r = i >> 3, k = i & 7;
+      aux[i] = k < K ? d.aux[(size_t)r * K + k] : 0.f;
+    }
+  } else {
+    const float sigma = (float)c.hp[RAAE_HP_SPEC_NOISE];
+    const uint32_t key = stream_key(c.seed, c.step_id, kStreamXNoise);
+    for (int i = tid; i < c.B * (dim >> 2); i += kThreads) {
+      int r = i / (dim >> 2), c4 = (i - r * (dim >> 2)) * 4;
+      float4 v = *reinterpret_cast<const float4*>(p.spec_train + (size_t)idx[r] * dim + c4);
+      if (sigma != 0.f) {
+        uint32_t e = (uint32_t)(r * kMaxDim + c4);
+        v.x += sigma * normal_at(key, e); v.y += sigma * normal_at(key, e + 1);
+        v.z += sigma * normal_at(key, e + 2); v.w += sigma * normal_at(key, e + 3);
+      }
+      *reinterpret_cast<float4*>(xn + (size_t)r * xld + c4) = v;
+    }
+    for (int i = tid; i < c.B * kZ; i += kThreads) {
+      int r = i >> 3, k = i & 7;
+      aux[i] = k < K ? p.aux_train[(size_t)idx[r] * K + k] : 0.f;
+    }
+  }
+  const float* zsp = c.a->debug ? c.a->dbg.z_sample : nullptr;
+  const uint32_t kz = stream_key(c.seed, c.step_id, kStreamZSample);
+  for (int i = tid; i < c.B * kZ; i += kThreads) {
+    int r = i >> 3, k = i & 7;
+    zs[i] = k < ns ? (zsp ? zsp[(size_t)r * ns + k] : normal_at(kz, (uint32_t)i)) : 0.f;
+  }
+  __syncthreads();
+}
+
+// One iteration of the batch loop body, trainer.py:112-204 (gradient-reversal branch).
+__device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
+  const KParams& p = *c.p;
+  SmemFixed* sm = c.sm;
+  const int tid = threadIdx.x, ns = p.cfg.nstyle;
+  const int LE = p.lay.net[kE].n_linear;
+  c.train = 1;
+  if (tid == 0) {
+    sm->alpha = alpha_schedule(c);
+    for (int i = 0; i < 8; ++i) sm->loss_acc[i] = 0.0;
+  }
+  __syncthreads();
+  const LayerIn x = wide_in(c.sc + p.sl.xn, p.sl.xld, p.cfg.dim_in, 0);
+  const float* zE = c.sc + p.sl.zE;
+  const float* meanZ = sm->mean[kE][LE - 1];
+  const float* invZ = sm->inv[kE][LE - 1];
+  float* dz = c.sc + p.sl.dz;
+  const int act = p.cfg.decoder_softplus ? 1 : 2;
+
+  // P0 (trainer.py:113-114): styles = E(x); spec_out = D(styles) is unused, but the decoder's BatchNorm
+  // buffers advance, so its hidden blocks run (the output Linear has no side effect and is skipped).
+  encoder_forward(c, x, 0);
+  if (c.a->debug && c.a->dbg.styles) {
+    for (int i = tid; i < c.B * ns; i += kThreads) {
+      int r = i / ns, k = i - r * ns;
+      c.a->dbg.styles[i] = (zE[(size_t)r * kZ + k] - meanZ[k]) * invZ[k];
+    }
+  }
+  decoder_forward_hidden(c, latent_in(zE, ns, meanZ, invZ), 0);
+
+  // P1 adversarial (trainer.py:118-127)
+  if (phase_mask & (1 << kAdv)) {
+    if (tid == 0) adam_prepare(c, kAdv);
+    __syncthreads();
+    dis_stage(c, 1, kAdv, c.a->debug ? c.a->dbg.z_real : nullptr, stream_key(c.seed, c.step_id, kStreamZReal));
+    encoder_backward(c, x, 0, kAdv, nullptr);
+    if (tid == 0) adam_finish(c, kAdv);
+    __syncthreads();
+  }
+  // P2 Kendall constraint (trainer.py:153-161)
+  if (phase_mask & (1 << kCorr)) {
+    encoder_forward(c, x, 1);
+    kendall_stage(c, c.sc + p.sl.aux, 1);
+    if (tid == 0) adam_prepare(c, kCorr);
+    __syncthreads();
+    encoder_backward(c, x, 1, kCorr, nullptr);
+    if (tid == 0) adam_finish(c, kCorr);
+    __syncthreads();
+  }
+  // P3 reconstruction (trainer.py:164-172)
+  if (phase_mask & (1 << kRecon)) {
+    encoder_forward(c, x, 2);
+    const LayerIn z = latent_in(zE, ns, meanZ, invZ);
+    decoder_forward_hidden(c, z, 1);
+    if (tid == 0) adam_prepare(c, kRecon);
+    __syncthreads();
+    dec_last(c, kLastRecon, 1, kRecon);
+    decoder_backward_hidden(c, z, 1, kRecon, dz);
+    encoder_backward(c, x, 2, kRecon, nullptr);
+    if (tid == 0) adam_finish(c, kRecon);
+    __syncthreads();
+  }
+  // P4 mutual information (trainer.py:175-186)
+  if (phase_mask & (1 << kMI)) {
+    encoder_forward(c, x, 3);                       // trainer.py:176: result unused, BN buffers advance
+    const LayerIn zs = latent_in(c.sc + p.sl.zs, ns, nullptr, nullptr);
+    decoder_forward_hidden(c, zs, 2);
+    dec_last(c, kLastStoreV, 2, kMI);
+    const LayerIn y = wide_in(c.sc + p.sl.v, p.sl.vld, p.cfg.dim_out, act);
+    encoder_forward(c, y, 4);
+    mi_mse_stage(c, 1);
+    if (tid == 0) adam_prepare(c, kMI);
+    __syncthreads();
+    encoder_backward(c, y, 4, kMI, c.sc + p.sl.v);
+    dec_last(c, kLastFromDv, 2, kMI);
+    decoder_backward_hidden(c, zs, 2, kMI, nullptr);
+    if (tid == 0) adam_finish(c, kMI);
+    __syncthreads();
+  }
+  // P5 smoothness (trainer.py:189-200): only the decoder is stepped, so the encoder backward is skipped
+  if ((phase_mask & (1 << kSmooth)) && (double)c.epoch < c.hp[RAAE_HP_EPOCH_STOP_SMOOTH]) {
+    encoder_forward(c, x, 5);
+    const LayerIn z = latent_in(zE, ns, meanZ, invZ);
+    decoder_forward_hidden(c, z, 3);
+    if (tid == 0) adam_prepare(c, kSmooth);
+    __syncthreads();
+    dec_last(c, kLastSmooth, 3, kSmooth);
+    decoder_backward_hidden(c, z, 3, kSmooth, nullptr);
+    if (tid == 0) adam_finish(c, kSmooth);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    float* misc = c.st + p.lay.misc_off;
+    for (int i = 0; i < RAAE_NUM_PHASES; ++i) misc[i] = (float)sm->loss_acc[i];
+    misc[5] += (float)sm->loss_acc[kMI];
+    misc[6] += 1.f;
+    if (c.a->debug && c.a->dbg.losses)
+      for (int i = 0; i < RAAE_NUM_PHASES; ++i) c.a->dbg.losses[i] = (float)sm->loss_acc[i];
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void init_ctx(Ctx& c, const KParams& p, const RunArgs& a, unsigned char* smem_raw, int trial) {
+  c.p = &p;
+  c.a = &a;
+  c.st = p.state + (size_t)trial * p.lay.state_floats;
+  c.sc = p.scratch + (size_t)trial * p.lay.scratch_floats;
+  c.hp = p.hp + (size_t)trial * RAAE_HP_COUNT;
+  c.sm = reinterpret_cast<SmemFixed*>(smem_raw);
+  c.arena = reinterpret_cast<float*>(smem_raw + ((sizeof(SmemFixed) + 15) / 16) * 16);
+  c.Breal = p.cfg.batch_size;
+  c.seed = mix32((uint32_t)(long long)c.hp[RAAE_HP_SEED] * 0x9e3779b9U + (uint32_t)trial * 0x85ebca6bU + 1u);
+  c.epoch = a.epoch;
+  c.apply = 1;
+  c.train = 1;
+  c.x = c.sc + p.sl.xn;
+  c.xld = p.sl.xld;
+}
+
+constexpr size_t kSmemBytes = ((sizeof(SmemFixed) + 15) / 16) * 16 + (size_t)kArenaFloats * sizeof(float);
+
+__global__ void __launch_bounds__(kThreads, 1)
+raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int trial = a.trial0 + blockIdx.x;
+  Ctx c;
+  init_ctx(c, p, a, smem_raw, trial);
+  if (a.debug) {
+    c.B = a.dbg.rows;
+    c.epoch = a.dbg.epoch;
+    c.apply = a.dbg.apply_updates;
+    c.step_id = 0;
+    build_batch(c, nullptr);
+    train_step(c, a.dbg.phase_mask);
+    return;
+  }
+  const int bs = p.cfg.batch_size;
+  const int32_t* perm = a.perm + (size_t)trial * p.n_train;
+  if (threadIdx.x == 0) { c.st[p.lay.misc_off + 5] = 0.f; c.st[p.lay.misc_off + 6] = 0.f; }
+  for (int s = 0; s < a.n_steps; ++s) {
+    c.B = min(bs, p.n_train - s * bs);
+    c.step_id = (uint32_t)(a.epoch * a.n_steps + s);
+    build_batch(c, perm + s * bs);
+    train_step(c, 0x1f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// validation block (trainer.py:207-304)
+// ------------------------------------------------------------------------------------------
+// in-place bitonic sort of (key, idx) pairs in shared memory, npad a power of two
+__device__ __forceinline__ void bitonic_sort(float* key, int* idx, int npad) {
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < npad; i += kThreads) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          bool up = (i & k) == 0;
+          float a = key[i], b = key[ixj];
+          if ((a > b) == up) {
+            key[i] = b; key[ixj] = a;
+            int t = idx[i]; idx[i] = idx[ixj]; idx[ixj] = t;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// scipy.stats.shapiro(z_k).statistic per style (Royston weights supplied by the host)
+// and max |Spearman| over style pairs (trainer.py:286-293).  Results: sm->zs[2][0] = min W, zs[2][1] = coupling.
+__device__ __noinline__ void latent_metrics(const Ctx& c) {
+  SmemFixed* sm = c.sm;
+  const KParams& p = *c.p;
+  const int n = c.B, ns = p.cfg.nstyle, tid = threadIdx.x;
+  const int lE = p.lay.net[kE].n_linear - 1;
+  const float* zE = c.sc + p.sl.zE;
+  float* ranks = c.sc + p.sl.rank;             // [kZ][max_rows]
+  const int rstride = p.cfg.max_rows;
+  int npad = 1;
+  while (npad < n) npad <<= 1;
+  float* key = c.arena;
+  int* idx = reinterpret_cast<int*>(c.arena + npad);
+  float wmin = 1e30f;
+  for (int k = 0; k < ns; ++k) {
+    __syncthreads();
+    const float mu = sm->mean[kE][lE][k], is = sm->inv[kE][lE][k];
+    for (int i = tid; i < npad; i += kThreads) {
+      key[i] = i < n ? (zE[(size_t)i * kZ + k] - mu) * is : __int_as_float(0x7f800000);
+      idx[i] = i;
+    }
+    bitonic_sort(key, idx, npad);
+    double sw = 0.0, sx = 0.0;
+    for (int i = tid; i < n; i += kThreads) { sw += (double)p.shapiro_w[i] * (double)key[i]; sx += (double)key[i]; }
+    sw = block_sum_d(sw, sm->redd);
+    sx = block_sum_d(sx, sm->redd);
+    const double xm = sx / (double)n;
+    double ss = 0.0;
+    for (int i = tid; i < n; i += kThreads) { double d = (double)key[i] - xm; ss += d * d; }
+    ss = block_sum_d(ss, sm->redd);
+    float W = (float)(sw * sw / ss);
+    wmin = fminf(wmin, W);
+    // average ranks (scipy.stats.rankdata 'average')
+    for (int i = tid; i < n; i += kThreads) {
+      int lo = i, hi = i;
+      const float v = key[i];
+      while (lo > 0 && key[lo - 1] == v) --lo;
+      while (hi + 1 < n && key[hi + 1] == v) ++hi;
+      ranks[(size_t)k * rstride + idx[i]] = 0.5f * (float)(lo + hi) + 1.f;
+    }
+  }
+  __syncthreads();
+  // Pearson correlation of the rank columns
+  const double rm = 0.5 * ((double)n + 1.0);
+  float cmax = 0.f;
+  double var[kZ];
+  for (int a = 0; a < ns; ++a) {
+    double s = 0.0;
+    for (int i = tid; i < n; i += kThreads) { double d = (double)ranks[(size_t)a * rstride + i] - rm; s += d * d; }
+    var[a] = block_sum_d(s, sm->redd);
+  }
+  for (int a = 0; a < ns; ++a)
+    for (int b = a + 1; b < ns; ++b) {
+      double s = 0.0;
+      for (int i = tid; i < n; i += kThreads)
+        s += ((double)ranks[(size_t)a * rstride + i] - rm) * ((double)ranks[(size_t)b * rstride + i] - rm);
+      s = block_sum_d(s, sm->redd);
+      float r = (float)(s / sqrt(var[a] * var[b]));
+      cmax = fmaxf(cmax, fabsf(r));
+    }
+  if (tid == 0) { sm->zs[2][0] = wmin; sm->zs[2][1] = cmax; }
+  __syncthreads();
+}
+
+// torch ReduceLROnPlateau(mode="min", threshold_mode="rel", threshold=0.01, cooldown=0, min_lr=0, eps=1e-8)
+// on every stepped optimizer with the same metric (trainer.py:303-304, 400-408); thread 0 only.
+__device__ inline void plateau_step(const Ctx& c, double metric) {
+  const double factor = c.hp[RAAE_HP_SCH_FACTOR], patience = c.hp[RAAE_HP_SCH_PATIENCE];
+  for (int o = 0; o < RAAE_NUM_PHASES; ++o) {
+    float* s = c.st + c.p->lay.opt[o].scalar_off;
+    double lr = (double)s[0], best = (double)s[2], bad = (double)s[3];
+    if (metric < best * (1.0 - 0.01)) { best = metric; bad = 0.0; }
+    else bad += 1.0;
+    if (bad > patience) {
+      double nl = lr * factor;
+      if (lr - nl > 1e-8) lr = nl;
+      bad = 0.0;
+    }
+    s[0] = (float)lr; s[2] = (float)best; s[3] = (float)bad;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int trial = a.trial0 + blockIdx.x;
+  Ctx c;
+  init_ctx(c, p, a, smem_raw, trial);
+  SmemFixed* sm = c.sm;
+  const int tid = threadIdx.x, ns = p.cfg.nstyle, K = p.cfg.n_aux;
+  const int LE = p.lay.net[kE].n_linear;
+  c.train = 0;
+  c.apply = 0;
+  c.B = p.n_val;
+  c.x = p.spec_val;
+  c.xld = p.cfg.dim_in;
+  c.step_id = 0x40000000u + (uint32_t)a.epoch;
+  const raae_val_io& io = a.val;
+  if (tid == 0) {
+    sm->alpha = alpha_schedule(c);
+    for (int i = 0; i < 8; ++i) sm->loss_acc[i] = 0.0;
+  }
+  // descriptors of the validation rows, z_sample
+  float* aux = c.sc + p.sl.aux;
+  float* zs = c.sc + p.sl.zs;
+  const uint32_t kz = stream_key(c.seed, c.step_id, kStreamValZSample);
+  for (int i = tid; i < c.B * kZ; i += kThreads) {
+    int r = i >> 3, k = i & 7;
+    aux[i] = k < K ? p.aux_val[(size_t)r * K + k] : 0.f;
+    zs[i] = k < ns ? (io.z_sample ? io.z_sample[(size_t)r * ns + k] : normal_at(kz, (uint32_t)i)) : 0.f;
+  }
+  __syncthreads();
+  const float* zE = c.sc + p.sl.zE;
+  const float* meanZ = sm->mean[kE][LE - 1];
+  const float* invZ = sm->inv[kE][LE - 1];
+  const int act = p.cfg.decoder_softplus ? 1 : 2;
+  // z = E(x_val); spec_out = D(z)   (trainer.py:213-214)
+  encoder_forward(c, wide_in(p.spec_val, p.cfg.dim_in, p.cfg.dim_in, 0), 0);
+  if (io.z)
+    for (int i = tid; i < c.B * ns; i += kThreads) {
+      int r = i / ns, k = i - r * ns;
+      io.z[i] = (zE[(size_t)r * kZ + k] - meanZ[k]) * invZ[k];
+    }
+  latent_metrics(c);
+  const float wmin = sm->zs[2][0], coupling = sm->zs[2][1];
+  kendall_stage(c, aux, 0);
+  dis_stage(c, 0, kAdv, io.z_real, stream_key(c.seed, c.step_id, kStreamValZReal));
+  decoder_forward_hidden(c, latent_in(zE, ns, meanZ, invZ), 0);
+  dec_last(c, kLastEval, 0, kRecon);
+  // mutual information on z_sample (trainer.py:240-246)
+  decoder_forward_hidden(c, latent_in(zs, ns, nullptr, nullptr), 0);
+  dec_last(c, kLastStoreV, 0, kMI);
+  encoder_forward(c, wide_in(c.sc + p.sl.v, p.sl.vld, p.cfg.dim_out, act), 0);
+  mi_mse_stage(c, 0);
+  if (tid == 0) {
+    float* misc = c.st + p.lay.misc_off;
+    float avg_mi = io.avg_mutual_info > -1e30f ? io.avg_mutual_info : (misc[6] > 0.f ? misc[5] / misc[6] : 0.f);
+    double m[5] = {(double)wmin, sm->loss_acc[kRecon], (double)avg_mi, (double)coupling, sm->loss_acc[kCorr]};
+    // combined_metric = -sum(metric_weights * metrics), metric_weights = [1, -1, -0.01, -1, -1]  (trainer.py:35, 297)
+    double combined = -(1.0 * m[0] - 1.0 * m[1] - 0.01 * m[2] - 1.0 * m[3] - 1.0 * m[4]);
+    if (io.losses)
+      for (int i = 0; i < RAAE_NUM_PHASES; ++i) io.losses[i] = (float)sm->loss_acc[i];
+    if (io.metrics) {
+      for (int i = 0; i < 5; ++i) io.metrics[i] = (float)m[i];
+      io.metrics[5] = (float)combined;
+    }
+    if (!a.debug) {
+      // production: losses.csv columns (trainer.py:84-87, 270-279) and the scheduler step
+      if (a.out_losses) {
+        float* o = a.out_losses + (size_t)trial * 12;
+        o[0] = misc[kAdv];    o[1] = (float)sm->loss_acc[kAdv];
+        o[2] = 0.f;           o[3] = 0.f;
+        o[4] = misc[kCorr];   o[5] = (float)sm->loss_acc[kCorr];
+        o[6] = misc[kRecon];  o[7] = (float)sm->loss_acc[kRecon];
+        o[8] = (double)a.epoch < c.hp[RAAE_HP_EPOCH_STOP_SMOOTH] ? misc[kSmooth] : 0.f;
+        o[9] = (float)sm->loss_acc[kSmooth];
+        o[10] = misc[kMI];    o[11] = (float)sm->loss_acc[kMI];
+      }
+      if (a.out_metrics) {
+        float* o = a.out_metrics + (size_t)trial * 6;
+        for (int i = 0; i < 5; ++i) o[i] = (float)m[i];
+        o[5] = (float)combined;
+      }
+      plateau_step(c, combined);
+    }
+  }
+}
+
+// lr <- hp, t <- 0, best <- +inf, bad <- 0; misc zeroed
+__global__ void raae_reset_opt_kernel(const __grid_constant__ KParams p, int n_trials) {
+  int trial = blockIdx.x * blockDim.x + threadIdx.x;
+  if (trial >= n_trials) return;
+  float* st = p.state + (size_t)trial * p.lay.state_floats;
+  const double* hp = p.hp + (size_t)trial * RAAE_HP_COUNT;
+  for (int o = 0; o < RAAE_NUM_PHASES; ++o) {
+    float* s = st + p.lay.opt[o].scalar_off;
+    s[0] = (float)hp[RAAE_HP_LR0 + o];
+    s[1] = 0.f;
+    s[2] = __int_as_float(0x7f800000);
+    s[3] = 0.f;
+  }
+  for (int i = 0; i < 16; ++i) st[p.lay.misc_off + i] = 0.f;
+}
+
+}  // namespace raae

@@ -1,0 +1,672 @@
+// Loss-side stages of the fused AAE step: decoder output layer (+ reconstruction / smoothness losses),
+// style discriminator (+ BCE through the gradient-reversal layer), Kendall rank constraint, latent MSE.
+#pragma once
+#include "aae_step.cuh"
+
+namespace raae {
+
+enum LastMode { kLastRecon = 0, kLastSmooth = 1, kLastStoreV = 2, kLastFromDv = 3, kLastEval = 4 };
+
+// ------------------------------------------------------------------------------------------
+// Decoder output layer  v = a @ W^T + b,  y = act(v)   (model.py:558-561), fused per 128-row tile with
+//   kLastRecon : recon_loss(scale = use_flex_spec_target)  functions.py:81-107, dL/dv, dW, db, g -> sc.g[0]
+//   kLastSmooth: smoothness_loss                            functions.py:194-212, likewise
+//   kLastStoreV: v -> sc.v                                  (MI phase forward)
+//   kLastFromDv: dL/dv read from sc.v                       (MI phase backward)
+//   kLastEval  : plain-MSE reconstruction and smoothness losses only (validation, trainer.py:223-239)
+// Losses land in sm->loss_acc[kRecon] / [kSmooth].
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
+  SmemFixed* sm = c.sm;
+  const raae_net_layout& nl = NL(c, kD);
+  const int L = nl.n_linear, l = L - 1, N = nl.out_dim[l];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, lane = tid & 31, warp = tid >> 5;
+  const float* Wg = netp(c, kD) + nl.w_off[l];
+  const int act = c.p->cfg.decoder_softplus ? 1 : 2;
+  float* Y = c.arena;                       // [kTM][kLDW]
+  float* At = Y + kWideTile;                // [kTM][kLD]
+  float* Wc = At + kTile;                   // [64][kLD]
+  float* rowbuf = Wc + kWTile + warp * 576; // per warp: ypad[272] | ezp[288]
+  float* vpanel = c.sc + c.p->sl.v;
+  const int vld = c.p->sl.vld;
+  const LayerIn in = hidden_out(c, kD, L - 2, inst);
+  const bool want_bwd = mode == kLastRecon || mode == kLastSmooth || mode == kLastFromDv;
+  const bool flex = c.p->cfg.use_flex_spec_target != 0;
+  __syncthreads();
+  sm->bias[tid] = tid < N ? netp(c, kD)[nl.b_off[l] + tid] : 0.f;
+  __syncthreads();
+  float accW[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accW[i][j] = 0.f;
+  float dbp = 0.f;
+  float sg4[4] = {0.f, 0.f, 0.f, 0.f}, sgx4[4] = {0.f, 0.f, 0.f, 0.f};
+  double loss_a = 0.0, loss_b = 0.0;        // a: reconstruction, b: smoothness
+  const float nB = (float)c.B, nN = (float)N;
+  const int ntiles = (c.B + kTM - 1) / kTM;
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    build_act_tile(At, in.src, row0, nv, in.mean, in.inv, in.slope, in.mask);
+    if (mode != kLastFromDv) {
+      for (int n0 = 0; n0 < N; n0 += kH) {
+        __syncthreads();
+        load_w_rows(Wc, kLD, Wg, kH, n0, N);
+        __syncthreads();
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        mma_nt<kH>(At, kLD, Wc, kLD, acc, ty, tx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            Y[(ty + 16 * i) * kLDW + n0 + tx + 16 * j] = acc[i][j] + sm->bias[n0 + tx + 16 * j];
+      }
+    } else {
+      build_wide_tile(Y, vpanel, vld, N, row0, nv, 0);
+    }
+    __syncthreads();
+    if (mode == kLastStoreV) {
+      const int cc = (tid & 63) * 4;
+      for (int r = tid >> 6; r < nv; r += 4)
+        if (cc < N) *reinterpret_cast<float4*>(vpanel + (size_t)(row0 + r) * vld + cc) = *reinterpret_cast<const float4*>(Y + r * kLDW + cc);
+      __syncthreads();
+      continue;
+    }
+    if (mode != kLastFromDv) {
+      // ---- per-row losses and dL/dv; one warp per row, lane owns 8 consecutive columns ----
+      float* ypad = rowbuf;
+      float* ezp = rowbuf + 272;
+      for (int r = warp; r < kTM; r += kThreads / 32) {
+        float* yrow = Y + r * kLDW;
+        const int col0 = lane * 8;
+        if (r >= nv) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) yrow[col0 + e] = 0.f;
+          continue;
+        }
+        float v[8], y[8], dy[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v[e] = yrow[col0 + e];
+          y[e] = (col0 + e < N) ? (act == 1 ? softplus2_f(v[e]) : fmaxf(v[e], 0.f)) : 0.f;
+          dy[e] = 0.f;
+        }
+        if (mode == kLastRecon || mode == kLastEval) {
+          float x[8];
+          const float* xrow = c.x + (size_t)(row0 + r) * c.xld;
+          float sy = 0.f, sx = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            x[e] = (col0 + e < N) ? xrow[col0 + e] : 0.f;
+            sy += y[e]; sx += x[e];
+          }
+          float cc = 1.f, dr = 0.f;
+          if (mode == kLastRecon && flex) {
+#pragma unroll
+            for (int of = 16; of > 0; of >>= 1) { sy += __shfl_xor_sync(0xffffffffu, sy, of); sx += __shfl_xor_sync(0xffffffffu, sx, of); }
+            float m_out = sy / nN, m_in = sx / nN;
+            float rr = fabsf(m_out) / fabsf(m_in);
+            cc = fminf(fmaxf(rr, 0.7f), 1.3f);
+            float sgn = m_out > 0.f ? 1.f : (m_out < 0.f ? -1.f : 0.f);
+            dr = (0.2f / nB) * (rr - 1.f) * sgn / (fabsf(m_in) * nN);
+            if (lane == 0) loss_a += 0.1 * (double)((rr - 1.f) * (rr - 1.f)) / (double)nB;
+          }
+          float sq = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (col0 + e < N) {
+              float d = y[e] - x[e] * cc;
+              sq = fmaf(d, d, sq);
+              dy[e] = dr + (2.f / (nB * nN)) * d;
+            }
+          }
+          loss_a += (double)sq / ((double)nB * (double)nN);
+        }
+        if (mode == kLastSmooth || mode == kLastEval) {
+          // replicate-padded copy of the row
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (col0 + e < N) ypad[8 + col0 + e] = y[e];
+          __syncwarp();
+          if (lane < 8) { ypad[lane] = ypad[8]; ypad[8 + N + lane] = ypad[8 + N - 1]; }
+          __syncwarp();
+          float ee[8], sq = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            ee[e] = 0.f;
+            if (col0 + e < N) {
+              float s = 0.f;
+#pragma unroll
+              for (int k = 0; k < 17; ++k) s = fmaf(kGauss17[k], ypad[col0 + e + k], s);
+              ee[e] = y[e] - s;
+              sq = fmaf(ee[e], ee[e], sq);
+            }
+          }
+          loss_b += (double)sq / ((double)nB * (double)nN);
+          if (mode == kLastSmooth) {
+            // adjoint: zero-padded full correlation of e with the taps, overhang folded into the end points
+            if (lane < 16) { ezp[lane] = 0.f; ezp[16 + N + lane] = 0.f; }
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (col0 + e < N) ezp[16 + col0 + e] = ee[e];
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int j = col0 + e;
+              if (j < N) {
+                // (K^T e)[i] = sum_t w[t] e[i - t], padded index i = j + 8
+                float kt = 0.f;
+#pragma unroll
+                for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], ezp[16 + j + 8 - k], kt);
+                if (j == 0) {
+                  for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], ezp[16 + i - k], kt);
+                }
+                if (j == N - 1) {
+                  for (int i = N + 8; i < N + 16; ++i)
+#pragma unroll
+                    for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], ezp[16 + i - k], kt);
+                }
+                dy[e] = (2.f / (nB * nN)) * (ee[e] - kt);
+              }
+            }
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float g = 0.f;
+          if (col0 + e < N) g = dy[e] * (act == 1 ? softplus2_grad_f(v[e]) : (v[e] > 0.f ? 1.f : 0.f));
+          yrow[col0 + e] = g;
+        }
+      }
+      __syncthreads();
+    }
+    if (want_bwd) {
+      // db, dW += dv^T a, g = (dv @ W) * dropout
+      {
+        float s = dbp;
+        for (int r = 0; r < kTM; ++r) s += Y[r * kLDW + tid];
+        dbp = s;
+      }
+      mma_tn8(Y, kLDW, 8 * (tid >> 3), At, kLD, 8 * (tid & 7), 0, kTM, accW);
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int n0 = 0; n0 < N; n0 += kH) {
+        __syncthreads();
+        load_w_rows(Wc, kLD, Wg, kH, n0, N);
+        __syncthreads();
+        mma_nn<kH>(Y + n0, kLDW, Wc, kLD, acc, ty, tx);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int r = ty + 16 * i;
+        if (r < nv) {
+          uint32_t kb = mask_keep4(in.mask, row0 + r, c4);
+          float4 a = *reinterpret_cast<const float4*>(At + r * kLD + c4);
+          float4 gm;
+          gm.x = (kb & 1u) ? acc[i][0] * in.mask.scale : 0.f;
+          gm.y = (kb & 2u) ? acc[i][1] * in.mask.scale : 0.f;
+          gm.z = (kb & 4u) ? acc[i][2] * in.mask.scale : 0.f;
+          gm.w = (kb & 8u) ? acc[i][3] * in.mask.scale : 0.f;
+          sg4[0] += gm.x; sg4[1] += gm.y; sg4[2] += gm.z; sg4[3] += gm.w;
+          sgx4[0] = fmaf(acc[i][0], a.x, sgx4[0]); sgx4[1] = fmaf(acc[i][1], a.y, sgx4[1]);
+          sgx4[2] = fmaf(acc[i][2], a.z, sgx4[2]); sgx4[3] = fmaf(acc[i][3], a.w, sgx4[3]);
+          *reinterpret_cast<float4*>(c.sc + c.p->sl.g[0] + (size_t)(row0 + r) * kH + c4) = gm;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (mode == kLastRecon || mode == kLastEval) {
+    double s = block_sum_d(loss_a, sm->redd);
+    if (tid == 0) sm->loss_acc[kRecon] = s;
+  }
+  if (mode == kLastSmooth || mode == kLastEval) {
+    double s = block_sum_d(loss_b, sm->redd);
+    if (tid == 0) sm->loss_acc[kSmooth] = s;
+  }
+  if (want_bwd) {
+    sm->red[ty][c4 + 0] = sg4[0]; sm->red[ty][c4 + 1] = sg4[1]; sm->red[ty][c4 + 2] = sg4[2]; sm->red[ty][c4 + 3] = sg4[3];
+    __syncthreads();
+    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sg[tid] = s; }
+    __syncthreads();
+    sm->red[ty][c4 + 0] = sgx4[0]; sm->red[ty][c4 + 1] = sgx4[1]; sm->red[ty][c4 + 2] = sgx4[2]; sm->red[ty][c4 + 3] = sgx4[3];
+    __syncthreads();
+    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sgx[tid] = s; }
+    float* gradW = Y;            // dense [N][64]
+    float* gradb = At;           // [N]
+    const int m0 = 8 * (tid >> 3), n0 = 8 * (tid & 7);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (m0 + i < N) gradW[(m0 + i) * kH + n0 + j] = accW[i][j];
+    if (tid < N) gradb[tid] = dbp;
+    __syncthreads();
+    adam_apply(c, o, kD, nl.w_off[l], N * kH, gradW);
+    adam_apply(c, o, kD, nl.b_off[l], N, gradb);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// Style discriminator on z_real and on the encoder output, BCE-with-logits, backward through the
+// gradient-reversal layer.  adversarial_loss functions.py:109-132, DiscriminatorFC model.py:631-663,
+// GradientReversalLayer model.py:8-22.  dis_layers == 3:  Linear(ns,64) PReLU Drop Linear(64,64) PReLU Drop Linear(64,1)
+// Output: sm->loss_acc[kAdv]; with backward: discriminator gradients (AdamW / export) and
+// sc.dz = -alpha * dL/dstyles for the fake rows.
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void dis_stage(const Ctx& c, int backward, int o, const float* z_real_ptr, uint32_t key_zreal) {
+  SmemFixed* sm = c.sm;
+  const raae_net_layout& nl = NL(c, kS);
+  const raae_net_layout& el = NL(c, kE);
+  const int ns = nl.in_dim[0];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, ch = tid & 63, q = tid >> 6, lane = tid & 31,
+            warp = tid >> 5;
+  float* U1 = c.arena;
+  float* H1 = U1 + kTile;
+  float* U2 = H1 + kTile;
+  float* H2 = U2 + kTile;
+  float* W1s = H2 + kTile;            // [64][kLD]
+  float* Zt = W1s + kWTile;           // [kTM][kZ]
+  float* W0s = Zt + kTM * kZ;         // [64][9]
+  float* w2s = W0s + kH * 9;          // [64]
+  float* a0s = w2s + kH;              // [64] slopes of layer 0
+  float* a1s = a0s + kH;              // [64] slopes of layer 1
+  float* b0s = a1s + kH;
+  float* b1s = b0s + kH;
+  const float* P = netp(c, kS);
+  const float* zE = c.sc + c.p->sl.zE;
+  const int lE = el.n_linear - 1;
+  const float noise = c.train ? (float)c.hp[RAAE_HP_DIS_NOISE] : 0.f;
+  const float* eps_real = c.a->debug ? c.a->dbg.dis_eps_real : nullptr;
+  const float* eps_fake = c.a->debug ? c.a->dbg.dis_eps_fake : nullptr;
+  const uint32_t key_er = stream_key(c.seed, c.step_id, kStreamDisEpsReal);
+  const uint32_t key_ef = stream_key(c.seed, c.step_id, kStreamDisEpsFake);
+  const MaskSrc mk_real[2] = {make_mask(c, kS, 0, 0), make_mask(c, kS, 0, 1)};
+  const MaskSrc mk_fake[2] = {make_mask(c, kS, 1, 0), make_mask(c, kS, 1, 1)};
+  __syncthreads();
+  load_w_rows(W1s, kLD, P + nl.w_off[1], kH, 0, kH);
+  for (int i = tid; i < kH * 9; i += kThreads) {
+    int n = i / 9, k = i - n * 9;
+    W0s[i] = k < ns ? P[nl.w_off[0] + n * ns + k] : 0.f;
+  }
+  if (tid < kH) {
+    w2s[tid] = P[nl.w_off[2] + tid];
+    a0s[tid] = P[nl.a_off[0] + tid];
+    a1s[tid] = P[nl.a_off[1] + tid];
+    b0s[tid] = P[nl.b_off[0] + tid];
+    b1s[tid] = P[nl.b_off[1] + tid];
+  }
+  __syncthreads();
+  const float b2 = P[nl.b_off[2]];
+  const float alpha = sm->alpha;
+  float accW1[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accW1[i][j] = 0.f;
+  float accW0[2] = {0.f, 0.f};
+  float dW2p = 0.f, da1p = 0.f, db1p = 0.f;          // (ch, q) partials
+  float da0p[4] = {0.f, 0.f, 0.f, 0.f}, db0p[4] = {0.f, 0.f, 0.f, 0.f};   // (ty, c4) partials
+  float db2p = 0.f;                                   // thread 0
+  double lossp = 0.0;
+  const int tiles_real = (c.Breal + kTM - 1) / kTM, tiles_fake = (c.B + kTM - 1) / kTM;
+  for (int t = 0; t < tiles_real + tiles_fake; ++t) {
+    const bool fake = t >= tiles_real;
+    const int nrows = fake ? c.B : c.Breal;
+    const int row0 = (fake ? t - tiles_real : t) * kTM, nv = min(kTM, nrows - row0);
+    const MaskSrc& mk0 = fake ? mk_fake[0] : mk_real[0];
+    const MaskSrc& mk1 = fake ? mk_fake[1] : mk_real[1];
+    const float label = fake ? 0.f : 1.f;
+    // ---- input rows (+ input noise, model.py:659-660) ----
+    for (int i = tid; i < kTM * kZ; i += kThreads) {
+      int r = i >> 3, k = i & 7;
+      float v = 0.f;
+      if (r < nv && k < ns) {
+        int row = row0 + r;
+        if (fake) v = (zE[(size_t)row * kZ + k] - sm->mean[kE][lE][k]) * sm->inv[kE][lE][k];
+        else v = z_real_ptr ? z_real_ptr[(size_t)row * ns + k] : normal_at(key_zreal, (uint32_t)(row * kZ + k));
+        if (noise != 0.f) {
+          const float* ep = fake ? eps_fake : eps_real;
+          float e = ep ? ep[(size_t)row * ns + k] : normal_at(fake ? key_ef : key_er, (uint32_t)(row * kZ + k));
+          v = v + noise * e;
+        }
+      }
+      Zt[i] = v;
+    }
+    __syncthreads();
+    // ---- layer 0 ----
+    for (int i = 0; i < kTM / 4; ++i) {
+      int r = q + 4 * i;
+      float u = 0.f, h = 0.f;
+      if (r < nv) {
+        u = b0s[ch];
+#pragma unroll
+        for (int k = 0; k < kZ; ++k) u = fmaf(Zt[r * kZ + k], W0s[ch * 9 + k], u);
+        h = mask_keep(mk0, row0 + r, ch) ? prelu_f(u, a0s[ch]) * mk0.scale : 0.f;
+      }
+      U1[r * kLD + ch] = u;
+      H1[r * kLD + ch] = h;
+    }
+    __syncthreads();
+    // ---- layer 1 ----
+    {
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      mma_nt<kH>(H1, kLD, W1s, kLD, acc, ty, tx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) U2[(ty + 16 * i) * kLD + tx + 16 * j] = acc[i][j] + b1s[tx + 16 * j];
+    }
+    __syncthreads();
+    for (int i = 0; i < kTM / 4; ++i) {
+      int r = q + 4 * i;
+      float h = 0.f;
+      if (r < nv) h = mask_keep(mk1, row0 + r, ch) ? prelu_f(U2[r * kLD + ch], a1s[ch]) * mk1.scale : 0.f;
+      H2[r * kLD + ch] = h;
+    }
+    __syncthreads();
+    // ---- logits, BCE-with-logits (mean over the rows of this half), dL/dlogit ----
+    for (int r = warp; r < kTM; r += kThreads / 32) {
+      float s = H2[r * kLD + lane] * w2s[lane] + H2[r * kLD + lane + 32] * w2s[lane + 32];
+#pragma unroll
+      for (int of = 16; of > 0; of >>= 1) s += __shfl_xor_sync(0xffffffffu, s, of);
+      if (lane == 0) {
+        float dl = 0.f;
+        if (r < nv) {
+          float x = s + b2;
+          float li = fmaxf(x, 0.f) - x * label + log1pf(expf(-fabsf(x)));
+          lossp += (double)li / (double)nrows;
+          dl = (sigmoid_f(x) - label) / (float)nrows;
+        }
+        sm->dlogit[r] = dl;
+      }
+    }
+    __syncthreads();
+    if (backward) {
+      // ---- layer 2 and the PReLU/dropout of layer 1 ----
+      for (int i = 0; i < kTM / 4; ++i) {
+        int r = q + 4 * i;
+        float du = 0.f;
+        if (r < nv) {
+          float dl = sm->dlogit[r];
+          dW2p = fmaf(dl, H2[r * kLD + ch], dW2p);
+          float g = mask_keep(mk1, row0 + r, ch) ? dl * w2s[ch] * mk1.scale : 0.f;
+          float u = U2[r * kLD + ch];
+          bool pos = u > 0.f;
+          du = pos ? g : a1s[ch] * g;
+          da1p += pos ? 0.f : u * g;
+          db1p += du;
+        }
+        U2[r * kLD + ch] = du;
+      }
+      if (tid == 0) { float s = db2p; for (int r = 0; r < kTM; ++r) s += sm->dlogit[r]; db2p = s; }
+      __syncthreads();
+      // ---- layer 1: dW1 += du2^T h1, dh1 = du2 @ W1 ----
+      {
+        const int qq = tid >> 6, tt = tid & 63;
+        mma_tn8(U2, kLD, 8 * (tt >> 3), H1, kLD, 8 * (tt & 7), 32 * qq, 32 * qq + 32, accW1);
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        mma_nn<kH>(U2, kLD, W1s, kLD, acc, ty, tx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int r = ty + 16 * i;
+          float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < nv) {
+            uint32_t kb = mask_keep4(mk0, row0 + r, c4);
+            float4 u = *reinterpret_cast<const float4*>(U1 + r * kLD + c4);
+#define RAAE_DIS(comp, idx, bit)                                             \
+            {                                                                \
+              float g = (kb & bit) ? acc[i][idx] * mk0.scale : 0.f;          \
+              bool pos = u.comp > 0.f;                                       \
+              du.comp = pos ? g : a0s[c4 + idx] * g;                         \
+              da0p[idx] += pos ? 0.f : u.comp * g;                           \
+              db0p[idx] += du.comp;                                          \
+            }
+            RAAE_DIS(x, 0, 1u) RAAE_DIS(y, 1, 2u) RAAE_DIS(z, 2, 4u) RAAE_DIS(w, 3, 8u)
+#undef RAAE_DIS
+          }
+          *reinterpret_cast<float4*>(U1 + r * kLD + c4) = du;
+        }
+      }
+      __syncthreads();
+      // ---- layer 0: dW0 += du1^T z;  fake rows: dz = -alpha * du1 @ W0 (gradient reversal) ----
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
+        float s = accW0[e];
+        for (int r = 0; r < kTM; ++r) s = fmaf(U1[r * kLD + n], Zt[r * kZ + k], s);
+        accW0[e] = s;
+      }
+      if (fake) {
+        float* dz = c.sc + c.p->sl.dz;
+        for (int i = tid; i < kTM * kZ; i += kThreads) {
+          int r = i >> 3, k = i & 7;
+          if (r < nv) {
+            float s = 0.f;
+            if (k < ns)
+              for (int n = 0; n < kH; ++n) s = fmaf(U1[r * kLD + n], W0s[n * 9 + k], s);
+            dz[(size_t)(row0 + r) * kZ + k] = -alpha * s;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  {
+    double s = block_sum_d(lossp, sm->redd);
+    if (tid == 0) sm->loss_acc[kAdv] = s;
+  }
+  if (backward) {
+    float* gW1 = c.arena;              // [64][64]
+    float* gsm = gW1 + kH * kH;        // W0 [64*ns] | b0 64 | a0 64 | b1 64 | a1 64 | W2 64 | b2 1
+    float* gW0 = gsm;
+    float* gb0 = gW0 + kH * kZ;
+    float* ga0 = gb0 + kH;
+    float* gb1 = ga0 + kH;
+    float* ga1 = gb1 + kH;
+    float* gW2 = ga1 + kH;
+    float* gb2 = gW2 + kH;
+    __syncthreads();
+    {
+      const int qq = tid >> 6, tt = tid & 63, m0 = 8 * (tt >> 3), n0 = 8 * (tt & 7);
+      for (int pass = 0; pass < 4; ++pass) {
+        if (qq == pass) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float* dst = gW1 + (m0 + i) * kH + n0 + j;
+              *dst = pass == 0 ? accW1[i][j] : *dst + accW1[i][j];
+            }
+        }
+        __syncthreads();
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
+      if (k < ns) gW0[n * ns + k] = accW0[e];
+    }
+    sm->red[q][ch] = dW2p; sm->red[4 + q][ch] = da1p; sm->red[8 + q][ch] = db1p;
+    __syncthreads();
+    if (q == 0) {
+      gW2[ch] = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
+      ga1[ch] = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
+      gb1[ch] = sm->red[8][ch] + sm->red[9][ch] + sm->red[10][ch] + sm->red[11][ch];
+    }
+    if (tid == 0) gb2[0] = db2p;
+    __syncthreads();
+    sm->red[ty][c4 + 0] = da0p[0]; sm->red[ty][c4 + 1] = da0p[1]; sm->red[ty][c4 + 2] = da0p[2]; sm->red[ty][c4 + 3] = da0p[3];
+    __syncthreads();
+    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; ga0[tid] = s; }
+    __syncthreads();
+    sm->red[ty][c4 + 0] = db0p[0]; sm->red[ty][c4 + 1] = db0p[1]; sm->red[ty][c4 + 2] = db0p[2]; sm->red[ty][c4 + 3] = db0p[3];
+    __syncthreads();
+    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb0[tid] = s; }
+    __syncthreads();
+    adam_apply(c, o, kS, nl.w_off[0], kH * ns, gW0);
+    adam_apply(c, o, kS, nl.b_off[0], kH, gb0);
+    adam_apply(c, o, kS, nl.a_off[0], kH, ga0);
+    adam_apply(c, o, kS, nl.w_off[1], kH * kH, gW1);
+    adam_apply(c, o, kS, nl.b_off[1], kH, gb1);
+    adam_apply(c, o, kS, nl.a_off[1], kH, ga1);
+    adam_apply(c, o, kS, nl.w_off[2], kH, gW2);
+    adam_apply(c, o, kS, nl.b_off[2], 1, gb2);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// Kendall rank constraint, kendall_constraint functions.py:37-79, over all ordered pairs of rows.
+//   t = sign(d_i - d_j), p = (s_i - s_j) t;  per descriptor k: n_same = #(p > 0), n_opp = #(p < 0) (>= 1),
+//   w_k = n_opp / max(n_same, n_opp) rescales the p > 0 entries (kendall_activation);
+//   loss = -sum(p) / ((B^2 - B) n_aux);   dloss/ds_ik = -2/norm * sum_j t_ijk (w_k if p_ijk > 0 else 1)
+// The pair tensor is never materialised: one pass accumulates, per row, A = sum_j [p>0] t and
+// Bn = sum_j [p<=0] t, and per descriptor the counts and partial sums.
+// Output: sm->loss_acc[kCorr]; with want_grad: sc.dz (zero beyond n_aux).
+// ------------------------------------------------------------------------------------------
+constexpr int kKendallChunk = 2048;
+
+__device__ __noinline__ void kendall_stage(const Ctx& c, const float* __restrict__ aux, int want_grad) {
+  SmemFixed* sm = c.sm;
+  const raae_net_layout& el = NL(c, kE);
+  const int lE = el.n_linear - 1;
+  const int K = c.p->cfg.n_aux, B = c.B, tid = threadIdx.x;
+  float* Ss = c.arena;                        // [chunk][kZ] styles
+  float* Ds = Ss + kKendallChunk * kZ;        // [chunk][kZ] descriptors
+  const float* zE = c.sc + c.p->sl.zE;
+  float* kacc = c.sc + c.p->sl.g[0];          // [rows][16] per-row A | Bn (spill for multi-chunk batches)
+  float* dz = c.sc + c.p->sl.dz;
+  int cs[kZ], co[kZ];
+  double sp[kZ], sn[kZ];
+#pragma unroll
+  for (int k = 0; k < kZ; ++k) { cs[k] = 0; co[k] = 0; sp[k] = 0.0; sn[k] = 0.0; }
+  const int nchunks = (B + kKendallChunk - 1) / kKendallChunk;
+  for (int ck = 0; ck < nchunks; ++ck) {
+    const int j0 = ck * kKendallChunk, nj = min(kKendallChunk, B - j0);
+    __syncthreads();
+    for (int i = tid; i < nj * kZ; i += kThreads) {
+      int r = i >> 3, k = i & 7;
+      float s = 0.f, d = 0.f;
+      if (k < K) {
+        s = (zE[(size_t)(j0 + r) * kZ + k] - sm->mean[kE][lE][k]) * sm->inv[kE][lE][k];
+        d = aux[(size_t)(j0 + r) * kZ + k];
+      }
+      Ss[i] = s; Ds[i] = d;
+    }
+    __syncthreads();
+    for (int i = tid; i < B; i += kThreads) {
+      float si[kZ], di[kZ], A[kZ], Bn[kZ], fp[kZ], fn[kZ];
+#pragma unroll
+      for (int k = 0; k < kZ; ++k) {
+        si[k] = k < K ? (zE[(size_t)i * kZ + k] - sm->mean[kE][lE][k]) * sm->inv[kE][lE][k] : 0.f;
+        di[k] = k < K ? aux[(size_t)i * kZ + k] : 0.f;
+        A[k] = 0.f; Bn[k] = 0.f; fp[k] = 0.f; fn[k] = 0.f;
+      }
+      if (ck > 0 && want_grad) {
+#pragma unroll
+        for (int k = 0; k < kZ; ++k) { A[k] = kacc[(size_t)i * 16 + k]; Bn[k] = kacc[(size_t)i * 16 + 8 + k]; }
+      }
+      for (int j = 0; j < nj; ++j) {
+        const float4 s0 = *reinterpret_cast<const float4*>(Ss + j * kZ);
+        const float4 s1 = *reinterpret_cast<const float4*>(Ss + j * kZ + 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(Ds + j * kZ);
+        const float4 d1 = *reinterpret_cast<const float4*>(Ds + j * kZ + 4);
+        const float sj[kZ] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float dj[kZ] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int k = 0; k < kZ; ++k) {
+          float dd = di[k] - dj[k];
+          float tt = dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f);
+          float p = (si[k] - sj[k]) * tt;
+          bool pos = p > 0.f, neg = p < 0.f;
+          cs[k] += pos ? 1 : 0;
+          co[k] += neg ? 1 : 0;
+          fp[k] += pos ? p : 0.f;
+          fn[k] += neg ? p : 0.f;
+          A[k] += pos ? tt : 0.f;
+          Bn[k] += pos ? 0.f : tt;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kZ; ++k) { sp[k] += (double)fp[k]; sn[k] += (double)fn[k]; }
+      if (want_grad) {
+#pragma unroll
+        for (int k = 0; k < kZ; ++k) { kacc[(size_t)i * 16 + k] = A[k]; kacc[(size_t)i * 16 + 8 + k] = Bn[k]; }
+      }
+    }
+  }
+  // block totals per descriptor
+  double loss = 0.0;
+  for (int k = 0; k < kZ; ++k) {
+    if (k >= K) break;
+    double tsp = block_sum_d(sp[k], sm->redd);
+    double tsn = block_sum_d(sn[k], sm->redd);
+    double tcs = block_sum_d((double)cs[k], sm->redd);
+    double tco = block_sum_d((double)co[k], sm->redd);
+    double w = 1.0;
+    if (c.p->cfg.kendall_activation) {
+      double n_same = tcs > 1.0 ? tcs : 1.0, n_opp = tco > 1.0 ? tco : 1.0;
+      w = n_opp / (n_same > n_opp ? n_same : n_opp);
+    }
+    loss += (double)(float)w * tsp + tsn;
+    if (tid == 0) sm->kw[k] = (float)w;
+  }
+  const double norm = ((double)B * (double)B - (double)B) * (double)K;
+  if (tid == 0) sm->loss_acc[kCorr] = -loss / norm;
+  __syncthreads();
+  if (want_grad) {
+    const float scale = (float)(-2.0 / norm);
+    for (int i = tid; i < B * kZ; i += kThreads) {
+      int r = i >> 3, k = i & 7;
+      float g = 0.f;
+      if (k < K) g = scale * (sm->kw[k] * kacc[(size_t)r * 16 + k] + kacc[(size_t)r * 16 + 8 + k]);
+      dz[i] = g;
+    }
+  }
+  __syncthreads();
+}
+
+// MSE between the re-encoded latent and z_sample (mutual_info_loss functions.py:174-192)
+__device__ __noinline__ void mi_mse_stage(const Ctx& c, int want_grad) {
+  SmemFixed* sm = c.sm;
+  const raae_net_layout& el = NL(c, kE);
+  const int lE = el.n_linear - 1, ns = c.p->cfg.nstyle, tid = threadIdx.x;
+  const float* zE = c.sc + c.p->sl.zE;
+  const float* zs = c.sc + c.p->sl.zs;
+  float* dz = c.sc + c.p->sl.dz;
+  const float cnt = (float)c.B * (float)ns;
+  double lp = 0.0;
+  __syncthreads();
+  for (int i = tid; i < c.B * kZ; i += kThreads) {
+    int k = i & 7;
+    float d = 0.f;
+    if (k < ns) d = (zE[i] - sm->mean[kE][lE][k]) * sm->inv[kE][lE][k] - zs[i];
+    lp += (double)(d * d);
+    if (want_grad) dz[i] = 2.f * d / cnt;
+  }
+  double s = block_sum_d(lp, sm->redd);
+  if (tid == 0) sm->loss_acc[kMI] = s / (double)cnt;
+  __syncthreads();
+}
+
+}  // namespace raae

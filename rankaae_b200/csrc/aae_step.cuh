@@ -1,0 +1,835 @@
+// The fused AAE train step: stage functions executed by ONE CTA per trial (256 threads).
+//
+// Data flow: per-row activations live in the trial's scratch block in HBM/L2 as
+// row-major [rows][64] panels; a stage streams 128-row tiles of them through shared memory, runs the
+// dense contractions as register-tiled FP32 FMA on the smem tiles, and fuses bias / PReLU / BatchNorm
+// statistics / dropout / loss gradients / AdamW around them.  BatchNorm couples the whole batch, so a
+// stage == one layer (forward) or one layer's backward; stages are separated by __syncthreads().
+#pragma once
+#include "aae_common.cuh"
+
+namespace raae {
+
+struct SmemFixed {
+  float mean[2][RAAE_MAX_LAYERS][kH];   // per net (E, D) / layer: BN mean used by the current forward
+  float inv[2][RAAE_MAX_LAYERS][kH];    // 1/sqrt(var + eps)
+  float bias[kMaxDim];
+  float slope[kH];
+  float shift[kH];
+  float cg[kH], cgx[kH];                // mean(g), mean(g * xhat) of the layer being back-propagated
+  float sg[kH], sgx[kH];                // the same sums being produced for the next lower layer
+  float red[16][kH];
+  float redw[32];
+  double redd[8];
+  float ad[8];                          // AdamW scalars of the running phase
+  float zs[4][kZ];                      // latent-channel scalars: [0] mean(dz) [1] mean(dz*zhat) ...
+  float logit[kTM], dlogit[kTM];
+  double loss_acc[8];
+  int kcount[2][kZ];
+  float kw[kZ];
+  float alpha;
+};
+
+struct Ctx {
+  const KParams* p;
+  const RunArgs* a;
+  float* st;          // trial state block
+  float* sc;          // trial scratch block
+  const double* hp;   // trial hyper-parameters
+  SmemFixed* sm;
+  float* arena;       // dynamic shared memory behind SmemFixed
+  int B;              // rows of the current batch
+  int Breal;          // rows of z_real (cfg batch_size; trainer.py:121)
+  const float* x;     // input spectra rows of the current batch / validation set
+  int xld;
+  uint32_t seed, step_id;
+  int train;          // BN batch statistics + dropout + noise
+  int apply;          // apply optimizer updates
+  int epoch;
+};
+
+constexpr int kArenaFloats = 51200;     // 200 KB; see the per-stage carve-ups below
+constexpr int kTile = kTM * kLD;        // 8704 floats
+constexpr int kWideTile = kTM * kLDW;   // 33280 floats
+constexpr int kWTile = kH * kLD;        // 4352 floats
+
+__device__ __forceinline__ const raae_net_layout& NL(const Ctx& c, int net) { return c.p->lay.net[net]; }
+__device__ __forceinline__ float* netp(const Ctx& c, int net) { return c.st + c.p->lay.net[net].param_off; }
+
+__device__ inline MaskSrc make_mask(const Ctx& c, int net, int inst, int layer) {
+  MaskSrc m;
+  m.ptr = nullptr; m.key = 0u; m.thresh = 0u; m.scale = 1.f;
+  if (!c.train) return m;
+  double pd = c.hp[net == kS ? RAAE_HP_DIS_DROPOUT : RAAE_HP_DROPOUT];
+  if (pd <= 0.0) return m;
+  m.scale = 1.f / (float)(1.0 - pd);
+  if (c.a->debug) {
+    const uint8_t* ptr = net == kE ? c.a->dbg.mask_enc[inst][layer]
+                       : net == kD ? c.a->dbg.mask_dec[inst][layer] : c.a->dbg.mask_dis[inst][layer];
+    if (ptr) { m.ptr = ptr; return m; }
+  }
+  uint32_t kind = (net == kE ? kStreamEncMask : net == kD ? kStreamDecMask : kStreamDisMask) + inst * 8 + layer;
+  m.key = stream_key(c.seed, c.step_id, kind);
+  m.thresh = (uint32_t)(pd * 65536.0 + 0.5);
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// tile builders (global -> transformed smem tile, zero-filled beyond `nv` rows)
+// ------------------------------------------------------------------------------------------
+// a = dropout(BN(PReLU(u)))  for a [kTM][64] panel of pre-activations
+__device__ __forceinline__ void build_act_tile(float* __restrict__ At, const float* __restrict__ u, int row0, int nv,
+                                               const float* mean, const float* inv, const float* __restrict__ slope_g,
+                                               const MaskSrc& mk) {
+  const int c4 = (threadIdx.x & 15) * 4;
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c4);
+  const float4 is = *reinterpret_cast<const float4*>(inv + c4);
+  const float4 sl = *reinterpret_cast<const float4*>(slope_g + c4);
+  for (int r = threadIdx.x >> 4; r < kTM; r += 16) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nv) {
+      float4 uu = *reinterpret_cast<const float4*>(u + (size_t)(row0 + r) * kH + c4);
+      uint32_t kb = mask_keep4(mk, row0 + r, c4);
+      o.x = (kb & 1u) ? (prelu_f(uu.x, sl.x) - mu.x) * is.x * mk.scale : 0.f;
+      o.y = (kb & 2u) ? (prelu_f(uu.y, sl.y) - mu.y) * is.y * mk.scale : 0.f;
+      o.z = (kb & 4u) ? (prelu_f(uu.z, sl.z) - mu.z) * is.z * mk.scale : 0.f;
+      o.w = (kb & 8u) ? (prelu_f(uu.w, sl.w) - mu.w) * is.w * mk.scale : 0.f;
+    }
+    *reinterpret_cast<float4*>(At + r * kLD + c4) = o;
+  }
+}
+
+// columns [k0, k0 + 64) of wide rows -> [kTM][kLD]; optional decoder activation on load
+__device__ __forceinline__ void build_wide_chunk(float* __restrict__ At, const float* __restrict__ src, int ld, int dim,
+                                                 int k0, int row0, int nv, int act /*0 none 1 softplus 2 relu*/) {
+  const int c4 = (threadIdx.x & 15) * 4;
+  for (int r = threadIdx.x >> 4; r < kTM; r += 16) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nv && k0 + c4 < dim) {
+      o = *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + k0 + c4);
+      if (act == 1) { o.x = softplus2_f(o.x); o.y = softplus2_f(o.y); o.z = softplus2_f(o.z); o.w = softplus2_f(o.w); }
+      else if (act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    }
+    *reinterpret_cast<float4*>(At + r * kLD + c4) = o;
+  }
+}
+
+// whole wide rows -> [kTM][kLDW]
+__device__ __forceinline__ void build_wide_tile(float* __restrict__ Xt, const float* __restrict__ src, int ld, int dim,
+                                                int row0, int nv, int act) {
+  const int c4 = (threadIdx.x & 63) * 4;
+  for (int r = threadIdx.x >> 6; r < kTM; r += 4) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nv && c4 < dim) {
+      o = *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + c4);
+      if (act == 1) { o.x = softplus2_f(o.x); o.y = softplus2_f(o.y); o.z = softplus2_f(o.z); o.w = softplus2_f(o.w); }
+      else if (act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    }
+    *reinterpret_cast<float4*>(Xt + r * kLDW + c4) = o;
+  }
+}
+
+// latent rows [rows][kZ] -> [kTM][kZ]; optional BN transform (encoder output)
+__device__ __forceinline__ void build_latent_tile(float* __restrict__ Zt, const float* __restrict__ src, int row0, int nv,
+                                                  int nstyle, const float* mean, const float* inv) {
+  for (int o = threadIdx.x; o < kTM * kZ; o += kThreads) {
+    int r = o >> 3, k = o & 7;
+    float v = 0.f;
+    if (r < nv && k < nstyle) {
+      v = src[(size_t)(row0 + r) * kZ + k];
+      if (mean) v = (v - mean[k]) * inv[k];
+    }
+    Zt[o] = v;
+  }
+}
+
+// weights [n_rows][K] (nn.Linear layout) rows [n0, n0+64) -> smem [64][ld], zero-filled
+__device__ __forceinline__ void load_w_rows(float* __restrict__ Ws, int ld, const float* __restrict__ W, int K, int n0,
+                                            int n_rows) {
+  const int k4n = (K + 3) >> 2;  // K is a multiple of 4 for every wide/hidden layer
+  for (int o = threadIdx.x; o < kH * (ld >> 2); o += kThreads) {
+    int n = o / (ld >> 2), k4 = o - n * (ld >> 2);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + n < n_rows && k4 < k4n) v = *reinterpret_cast<const float4*>(W + (size_t)(n0 + n) * K + 4 * k4);
+    *reinterpret_cast<float4*>(Ws + n * ld + 4 * k4) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// AdamW (torch/optim/adam.py single-tensor path)
+// ------------------------------------------------------------------------------------------
+// thread 0 only; followed by __syncthreads() at the call site
+__device__ inline void adam_prepare(const Ctx& c, int o) {
+  const raae_opt_layout& ol = c.p->lay.opt[o];
+  double lr = (double)c.st[ol.scalar_off + 0];
+  double t = (double)c.st[ol.scalar_off + 1] + 1.0;
+  double b1 = c.hp[RAAE_HP_BETA1 + o], b2 = c.hp[RAAE_HP_BETA2 + o], wd = c.hp[RAAE_HP_WD + o];
+  double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
+  c.sm->ad[0] = (float)(1.0 - lr * wd);
+  c.sm->ad[1] = (float)(1.0 - b1);
+  c.sm->ad[2] = (float)b2;
+  c.sm->ad[3] = (float)(1.0 - b2);
+  c.sm->ad[4] = (float)(lr / bc1);
+  c.sm->ad[5] = (float)sqrt(bc2);
+}
+
+// thread 0 only, after every parameter of the phase has been updated
+__device__ inline void adam_finish(const Ctx& c, int o) {
+  if (c.apply) c.st[c.p->lay.opt[o].scalar_off + 1] += 1.f;
+}
+
+// all threads: update `n` parameters at offset `poff` of net `net` with gradient g (shared memory),
+// and/or export the gradient to the debug buffer.
+__device__ __forceinline__ void adam_apply(const Ctx& c, int o, int net, int poff, int n, const float* __restrict__ g) {
+  const raae_opt_layout& ol = c.p->lay.opt[o];
+  float* dbg = c.a->debug ? c.a->dbg.grads[o] : nullptr;
+  if (dbg && ol.net_off[net] >= 0)
+    for (int i = threadIdx.x; i < n; i += kThreads) dbg[ol.net_off[net] + poff + i] = g[i];
+  if (!c.apply || ol.net_off[net] < 0) return;
+  float* P = c.st + c.p->lay.net[net].param_off + poff;
+  float* M = c.st + ol.m_off + ol.net_off[net] + poff;
+  float* V = c.st + ol.v_off + ol.net_off[net] + poff;
+  const float decay = c.sm->ad[0], w1 = c.sm->ad[1], b2 = c.sm->ad[2], w2 = c.sm->ad[3], ss = c.sm->ad[4],
+              bc2s = c.sm->ad[5];
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    float gi = g[i];
+    float pp = P[i] * decay;
+    float m = M[i];
+    m = m + (gi - m) * w1;
+    float v = V[i] * b2 + (w2 * gi) * gi;
+    float denom = sqrtf(v) / bc2s + kAdamEps;
+    pp = pp - ss * (m / denom);
+    P[i] = pp; M[i] = m; V[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward of one hidden block:  u = in @ W^T + b  (stored),  batch statistics of PReLU(u)
+// ------------------------------------------------------------------------------------------
+enum InKind { kInHidden = 0, kInWide = 1, kInLatent = 2 };
+
+struct LayerIn {
+  int kind;
+  const float* src;    // hidden: u_prev [rows][64]; wide: [rows][ld]; latent: [rows][kZ]
+  int ld, dim, act;    // wide only
+  const float* mean;   // hidden: stats of the producing layer; latent: BN of the encoder output or null
+  const float* inv;
+  const float* slope;  // hidden: PReLU slopes (global) of the producing layer
+  MaskSrc mask;        // hidden: dropout of the producing layer
+};
+
+// finalize BN statistics of channel c from the shifted sums; updates running buffers in train mode
+__device__ __forceinline__ void bn_finalize(const Ctx& c, int net, int l, int ch, float shift, float s1, float s2,
+                                            int nrows) {
+  const raae_net_layout& nl = NL(c, net);
+  float n = (float)nrows;
+  float d = s1 / n;
+  float mean = shift + d;
+  float var = fmaxf(s2 / n - d * d, 0.f);
+  c.sm->mean[net][l][ch] = mean;
+  c.sm->inv[net][l][ch] = 1.f / sqrtf(var + kBnEps);
+  float* rm = c.st + nl.rm_off[l];
+  float* rv = c.st + nl.rv_off[l];
+  float unb = nrows > 1 ? var * (n / (n - 1.f)) : var;
+  rm[ch] = (1.f - kBnMomentum) * rm[ch] + kBnMomentum * mean;
+  rv[ch] = (1.f - kBnMomentum) * rv[ch] + kBnMomentum * unb;
+}
+
+__device__ __noinline__ void fwd_hidden(const Ctx& c, int net, int l, const LayerIn& in, float* __restrict__ u_out) {
+  SmemFixed* sm = c.sm;
+  const raae_net_layout& nl = NL(c, net);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, ch = tid & 63, q = tid >> 6;
+  const int K = nl.in_dim[l];
+  const float* Wg = netp(c, net) + nl.w_off[l];
+  float* Ws = c.arena;                        // hidden: [64][kLD]; wide: [64][kLDW]; latent: [64][9]
+  float* At = c.arena + kH * kLDW;            // [kTM][kLD] or [kTM][kZ]
+  float* Ot = At + kTile;                     // [kTM][kLD]
+  __syncthreads();
+  if (in.kind == kInLatent) {
+    for (int o = tid; o < kH * 9; o += kThreads) {
+      int n = o / 9, k = o - n * 9;
+      Ws[o] = k < K ? Wg[n * K + k] : 0.f;
+    }
+  } else {
+    load_w_rows(Ws, in.kind == kInWide ? kLDW : kLD, Wg, K, 0, kH);
+  }
+  if (tid < kH) {
+    sm->bias[tid] = netp(c, net)[nl.b_off[l] + tid];
+    sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
+    if (!c.train) {
+      sm->mean[net][l][tid] = c.st[nl.rm_off[l] + tid];
+      sm->inv[net][l][tid] = 1.f / sqrtf(c.st[nl.rv_off[l] + tid] + kBnEps);
+    }
+  }
+  __syncthreads();
+  float s1 = 0.f, s2 = 0.f;
+  const int ntiles = (c.B + kTM - 1) / kTM;
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    if (in.kind == kInLatent) {
+      build_latent_tile(At, in.src, row0, nv, K, in.mean, in.inv);
+      __syncthreads();
+      for (int i = 0; i < kTM / 4; ++i) {
+        int r = q + 4 * i;
+        float acc = sm->bias[ch];
+#pragma unroll
+        for (int k = 0; k < kZ; ++k) acc = fmaf(At[r * kZ + k], Ws[ch * 9 + k], acc);
+        Ot[r * kLD + ch] = acc;
+      }
+    } else {
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      if (in.kind == kInHidden) {
+        build_act_tile(At, in.src, row0, nv, in.mean, in.inv, in.slope, in.mask);
+        __syncthreads();
+        mma_nt<kH>(At, kLD, Ws, kLD, acc, ty, tx);
+      } else {
+        for (int k0 = 0; k0 < K; k0 += kH) {
+          build_wide_chunk(At, in.src, in.ld, in.dim, k0, row0, nv, in.act);
+          __syncthreads();
+          mma_nt<kH>(At, kLD, Ws + k0, kLDW, acc, ty, tx);
+          __syncthreads();
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Ot[(ty + 16 * i) * kLD + tx + 16 * j] = acc[i][j] + sm->bias[tx + 16 * j];
+    }
+    __syncthreads();
+    // elementwise epilogue: thread (ch, q) owns channel ch of rows q, q+4, ...
+    const float a_sl = sm->slope[ch];
+    if (c.train && t == 0) {
+      float s = 0.f;
+      for (int i = 0; i < kTM / 4; ++i) {
+        int r = q + 4 * i;
+        if (r < nv) s += prelu_f(Ot[r * kLD + ch], a_sl);
+      }
+      sm->red[q][ch] = s;
+      __syncthreads();
+      if (q == 0) sm->shift[ch] = (sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch]) / (float)nv;
+      __syncthreads();
+    }
+    const float sh = c.train ? sm->shift[ch] : 0.f;
+    for (int i = 0; i < kTM / 4; ++i) {
+      int r = q + 4 * i;
+      if (r < nv) {
+        float u = Ot[r * kLD + ch];
+        u_out[(size_t)(row0 + r) * kH + ch] = u;
+        float d = prelu_f(u, a_sl) - sh;
+        s1 += d;
+        s2 = fmaf(d, d, s2);
+      }
+    }
+    __syncthreads();
+  }
+  if (c.train) {
+    sm->red[q][ch] = s1;
+    sm->red[4 + q][ch] = s2;
+    __syncthreads();
+    if (q == 0) {
+      float a1 = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
+      float a2 = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
+      bn_finalize(c, net, l, ch, sm->shift[ch], a1, a2, c.B);
+    }
+  }
+  __syncthreads();
+}
+
+// statistics of nstyle columns of a [rows][kZ] panel (two-pass); results in sm->zs[0] (mean), zs[1] (biased var)
+__device__ __forceinline__ void latent_colstats(const Ctx& c, const float* __restrict__ z, int nrows) {
+  SmemFixed* sm = c.sm;
+  const int tid = threadIdx.x, k = tid & 7, g = tid >> 3;
+  float s = 0.f;
+  for (int r = g; r < nrows; r += 32) s += z[(size_t)r * kZ + k];
+  float* red = &sm->red[0][0];
+  __syncthreads();
+  red[tid] = s;
+  __syncthreads();
+  if (tid < kZ) {
+    float t = 0.f;
+    for (int i = 0; i < 32; ++i) t += red[i * 8 + tid];
+    sm->zs[0][tid] = t / (float)nrows;
+  }
+  __syncthreads();
+  const float mu = sm->zs[0][k];
+  s = 0.f;
+  for (int r = g; r < nrows; r += 32) { float d = z[(size_t)r * kZ + k] - mu; s = fmaf(d, d, s); }
+  __syncthreads();
+  red[tid] = s;
+  __syncthreads();
+  if (tid < kZ) {
+    float t = 0.f;
+    for (int i = 0; i < 32; ++i) t += red[i * 8 + tid];
+    sm->zs[1][tid] = t / (float)nrows;
+  }
+  __syncthreads();
+}
+
+// last encoder Linear (64 -> nstyle) + BatchNorm1d(nstyle).  zE receives the PRE-BN output; the BN
+// statistics go to sm->mean/inv[kE][L-1][0..nstyle).
+__device__ __noinline__ void fwd_enc_last(const Ctx& c, const LayerIn& in) {
+  SmemFixed* sm = c.sm;
+  const raae_net_layout& nl = NL(c, kE);
+  const int L = nl.n_linear, l = L - 1, ns = nl.out_dim[l];
+  const int tid = threadIdx.x;
+  float* Ws = c.arena;                 // [kZ][kLD]
+  float* At = c.arena + kH * kLDW;     // [kTM][kLD]
+  float* zE = c.sc + c.p->sl.zE;
+  __syncthreads();
+  for (int o = tid; o < kZ * kH; o += kThreads) {
+    int n = o >> 6, k = o & 63;
+    Ws[n * kLD + k] = n < ns ? netp(c, kE)[nl.w_off[l] + n * kH + k] : 0.f;
+  }
+  if (tid < kZ) sm->bias[tid] = tid < ns ? netp(c, kE)[nl.b_off[l] + tid] : 0.f;
+  __syncthreads();
+  const int ntiles = (c.B + kTM - 1) / kTM;
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    build_act_tile(At, in.src, row0, nv, in.mean, in.inv, in.slope, in.mask);
+    __syncthreads();
+    for (int o = tid; o < kTM * kZ; o += kThreads) {
+      int r = o >> 3, n = o & 7;
+      if (r < nv) {
+        float acc = sm->bias[n];
+#pragma unroll 4
+        for (int k = 0; k < kH; k += 4) {
+          float4 a = *reinterpret_cast<const float4*>(At + r * kLD + k);
+          float4 w = *reinterpret_cast<const float4*>(Ws + n * kLD + k);
+          acc = fmaf(a.x, w.x, acc); acc = fmaf(a.y, w.y, acc); acc = fmaf(a.z, w.z, acc); acc = fmaf(a.w, w.w, acc);
+        }
+        zE[(size_t)(row0 + r) * kZ + n] = n < ns ? acc : 0.f;
+      }
+    }
+    __syncthreads();
+  }
+  if (c.train) {
+    __threadfence_block();
+    latent_colstats(c, zE, c.B);
+    if (tid < ns) {
+      float mean = sm->zs[0][tid], var = sm->zs[1][tid], n = (float)c.B;
+      sm->mean[kE][l][tid] = mean;
+      sm->inv[kE][l][tid] = 1.f / sqrtf(var + kBnEps);
+      float* rm = c.st + nl.rm_off[l];
+      float* rv = c.st + nl.rv_off[l];
+      float unb = c.B > 1 ? var * (n / (n - 1.f)) : var;
+      rm[tid] = (1.f - kBnMomentum) * rm[tid] + kBnMomentum * mean;
+      rv[tid] = (1.f - kBnMomentum) * rv[tid] + kBnMomentum * unb;
+    }
+  } else if (tid < ns) {
+    sm->mean[kE][l][tid] = c.st[nl.rm_off[l] + tid];
+    sm->inv[kE][l][tid] = 1.f / sqrtf(c.st[nl.rv_off[l] + tid] + kBnEps);
+  }
+  if (tid >= ns && tid < kZ) { sm->mean[kE][l][tid] = 0.f; sm->inv[kE][l][tid] = 0.f; }
+  __syncthreads();
+}
+
+// LayerIn describing "the activations coming out of hidden layer l of `net`, forward instance inst"
+__device__ __forceinline__ LayerIn hidden_out(const Ctx& c, int net, int l, int inst) {
+  LayerIn in;
+  in.kind = kInHidden;
+  in.src = c.sc + (net == kE ? c.p->sl.uE[l] : c.p->sl.uD[l]);
+  in.ld = kH; in.dim = kH; in.act = 0;
+  in.mean = c.sm->mean[net][l];
+  in.inv = c.sm->inv[net][l];
+  in.slope = netp(c, net) + NL(c, net).a_off[l];
+  in.mask = make_mask(c, net, inst, l);
+  return in;
+}
+
+__device__ __forceinline__ LayerIn wide_in(const float* src, int ld, int dim, int act) {
+  LayerIn in;
+  in.kind = kInWide; in.src = src; in.ld = ld; in.dim = dim; in.act = act;
+  in.mean = nullptr; in.inv = nullptr; in.slope = nullptr;
+  in.mask.ptr = nullptr; in.mask.key = 0; in.mask.thresh = 0; in.mask.scale = 1.f;
+  return in;
+}
+
+__device__ __forceinline__ LayerIn latent_in(const float* src, int nstyle, const float* mean, const float* inv) {
+  LayerIn in;
+  in.kind = kInLatent; in.src = src; in.ld = kZ; in.dim = nstyle; in.act = 0;
+  in.mean = mean; in.inv = inv; in.slope = nullptr;
+  in.mask.ptr = nullptr; in.mask.key = 0; in.mask.thresh = 0; in.mask.scale = 1.f;
+  return in;
+}
+
+// FCEncoder.forward (model.py:330-378): x -> zE (pre-BN) + BN statistics of every layer
+__device__ __forceinline__ void encoder_forward(const Ctx& c, const LayerIn& x, int inst) {
+  const raae_net_layout& nl = NL(c, kE);
+  const int L = nl.n_linear;
+  fwd_hidden(c, kE, 0, x, c.sc + c.p->sl.uE[0]);
+  for (int l = 1; l < L - 1; ++l) fwd_hidden(c, kE, l, hidden_out(c, kE, l - 1, inst), c.sc + c.p->sl.uE[l]);
+  fwd_enc_last(c, hidden_out(c, kE, L - 2, inst));
+  if (c.train && threadIdx.x == 0) c.st[nl.nbt_off] += 1.f;
+}
+
+// hidden blocks of FCDecoder.forward (model.py:518-570); the output Linear is a separate stage
+__device__ __forceinline__ void decoder_forward_hidden(const Ctx& c, const LayerIn& z, int inst) {
+  const raae_net_layout& nl = NL(c, kD);
+  const int L = nl.n_linear;
+  fwd_hidden(c, kD, 0, z, c.sc + c.p->sl.uD[0]);
+  for (int l = 1; l < L - 1; ++l) fwd_hidden(c, kD, l, hidden_out(c, kD, l - 1, inst), c.sc + c.p->sl.uD[l]);
+  if (c.train && threadIdx.x == 0) c.st[nl.nbt_off] += 1.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of one hidden block (PReLU -> BN -> dropout already folded into g_in), fused AdamW
+// ------------------------------------------------------------------------------------------
+// On entry sm->sg / sm->sgx hold sum_r g and sum_r g * xhat of THIS layer (g = dL/dxhat).
+// Produces dW, db, dslope (-> AdamW / debug export) and, if g_out != null, the gradient w.r.t. the
+// producing layer's xhat plus its sums in sm->sg / sm->sgx.
+//   in.kind == kInHidden : input activations rebuilt from in.src;    g_out [rows][64]
+//   in.kind == kInWide   : input rows in.src (K = dim);              dx_out (optional) [rows][ld]: receives
+//                           dL/dx * act'(v) IN PLACE of the pre-activation stored there (MI phase)
+//   in.kind == kInLatent : input latent rows;                        dz_out (optional) [rows][kZ]
+__device__ __noinline__ void bwd_hidden(const Ctx& c, int net, int l, const LayerIn& in, const float* __restrict__ u_l,
+                                        const float* __restrict__ g_in, float* g_out, int o) {
+  SmemFixed* sm = c.sm;
+  const raae_net_layout& nl = NL(c, net);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int K = nl.in_dim[l];
+  const float* Wg = netp(c, net) + nl.w_off[l];
+  // arena: [Dt kTile][At: kTile | wide kWideTile][Ws kWTile (hidden NN operand / wide chunk / latent [64][9])]
+  float* Dt = c.arena;
+  float* At = c.arena + kTile;
+  float* Ws = At + (in.kind == kInWide ? kWideTile : kTile);
+  float* gradW = At;                          // reused after the tile loop: dense [64][K]
+  const bool want_out = g_out != nullptr;
+  __syncthreads();
+  if (tid < kH) {
+    float nB = (float)c.B;
+    sm->cg[tid] = sm->sg[tid] / nB;
+    sm->cgx[tid] = sm->sgx[tid] / nB;
+    sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
+  }
+  if (in.kind == kInHidden && want_out) load_w_rows(Ws, kLD, Wg, K, 0, kH);
+  if (in.kind == kInLatent)
+    for (int i = tid; i < kH * 9; i += kThreads) {
+      int n = i / 9, k = i - n * 9;
+      Ws[i] = k < K ? Wg[n * K + k] : 0.f;
+    }
+  __syncthreads();
+  const int c4 = tx * 4;
+  const float4 mu = *reinterpret_cast<const float4*>(sm->mean[net][l] + c4);
+  const float4 is = *reinterpret_cast<const float4*>(sm->inv[net][l] + c4);
+  const float4 sl = *reinterpret_cast<const float4*>(sm->slope + c4);
+  const float4 cg = *reinterpret_cast<const float4*>(sm->cg + c4);
+  const float4 cgx = *reinterpret_cast<const float4*>(sm->cgx + c4);
+  float db4[4] = {0.f, 0.f, 0.f, 0.f}, ds4[4] = {0.f, 0.f, 0.f, 0.f};
+  float sg4[4] = {0.f, 0.f, 0.f, 0.f}, sgx4[4] = {0.f, 0.f, 0.f, 0.f};
+  float accW[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accW[i][j] = 0.f;
+  float accS[2] = {0.f, 0.f};                // latent dW: 2 outputs per thread
+  const int ntiles = (c.B + kTM - 1) / kTM;
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    // 1. du = PReLU'(u) * BN'(g)
+    for (int r = ty; r < kTM; r += 16) {
+      float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nv) {
+        const float4 g = *reinterpret_cast<const float4*>(g_in + (size_t)(row0 + r) * kH + c4);
+        const float4 u = *reinterpret_cast<const float4*>(u_l + (size_t)(row0 + r) * kH + c4);
+#define RAAE_DU(comp, idx)                                                        \
+        {                                                                         \
+          float xh = (prelu_f(u.comp, sl.comp) - mu.comp) * is.comp;              \
+          float dh = (g.comp - cg.comp - xh * cgx.comp) * is.comp;                \
+          bool pos = u.comp > 0.f;                                                \
+          du.comp = pos ? dh : sl.comp * dh;                                      \
+          ds4[idx] += pos ? 0.f : u.comp * dh;                                    \
+          db4[idx] += du.comp;                                                    \
+        }
+        RAAE_DU(x, 0) RAAE_DU(y, 1) RAAE_DU(z, 2) RAAE_DU(w, 3)
+#undef RAAE_DU
+      }
+      *reinterpret_cast<float4*>(Dt + r * kLD + c4) = du;
+    }
+    // 2. the layer's input activations
+    if (in.kind == kInHidden) build_act_tile(At, in.src, row0, nv, in.mean, in.inv, in.slope, in.mask);
+    else if (in.kind == kInWide) build_wide_tile(At, in.src, in.ld, in.dim, row0, nv, in.act);
+    else build_latent_tile(At, in.src, row0, nv, K, in.mean, in.inv);
+    __syncthreads();
+    // 3. dW += du^T a
+    if (in.kind == kInHidden) {
+      const int qq = tid >> 6, tt = tid & 63;
+      mma_tn8(Dt, kLD, 8 * (tt >> 3), At, kLD, 8 * (tt & 7), 32 * qq, 32 * qq + 32, accW);
+    } else if (in.kind == kInWide) {
+      mma_tn8(Dt, kLD, 8 * (tid >> 5), At, kLDW, 8 * (tid & 31), 0, kTM, accW);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
+        float s = accS[e];
+        for (int r = 0; r < kTM; ++r) s = fmaf(Dt[r * kLD + n], At[r * kZ + k], s);
+        accS[e] = s;
+      }
+    }
+    // 4. gradient w.r.t. the input
+    if (want_out && in.kind == kInHidden) {
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      mma_nn<kH>(Dt, kLD, Ws, kLD, acc, ty, tx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int r = ty + 16 * i;
+        if (r < nv) {
+          uint32_t kb = mask_keep4(in.mask, row0 + r, c4);
+          float4 a = *reinterpret_cast<const float4*>(At + r * kLD + c4);
+          float4 gm;
+          gm.x = (kb & 1u) ? acc[i][0] * in.mask.scale : 0.f;
+          gm.y = (kb & 2u) ? acc[i][1] * in.mask.scale : 0.f;
+          gm.z = (kb & 4u) ? acc[i][2] * in.mask.scale : 0.f;
+          gm.w = (kb & 8u) ? acc[i][3] * in.mask.scale : 0.f;
+          sg4[0] += gm.x; sg4[1] += gm.y; sg4[2] += gm.z; sg4[3] += gm.w;
+          sgx4[0] = fmaf(acc[i][0], a.x, sgx4[0]); sgx4[1] = fmaf(acc[i][1], a.y, sgx4[1]);
+          sgx4[2] = fmaf(acc[i][2], a.z, sgx4[2]); sgx4[3] = fmaf(acc[i][3], a.w, sgx4[3]);
+          *reinterpret_cast<float4*>(g_out + (size_t)(row0 + r) * kH + c4) = gm;
+        }
+      }
+    } else if (want_out && in.kind == kInWide) {
+      // dL/dx chunk by chunk; multiplied by act'(v) and written over v (g_out == the v panel, stride in.ld)
+      for (int k0 = 0; k0 < in.dim; k0 += kH) {
+        __syncthreads();
+        for (int i = tid; i < kH * (kH / 4); i += kThreads) {   // Ws[n][kk] = W[n][k0 + kk]
+          int n = i >> 4, k4 = (i & 15) * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k0 + k4 < K) v = *reinterpret_cast<const float4*>(Wg + (size_t)n * K + k0 + k4);
+          *reinterpret_cast<float4*>(Ws + n * kLD + k4) = v;
+        }
+        __syncthreads();
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        mma_nn<kH>(Dt, kLD, Ws, kLD, acc, ty, tx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int r = ty + 16 * i;
+          if (r < nv && k0 + c4 < in.dim) {
+            float* vp = g_out + (size_t)(row0 + r) * in.ld + k0 + c4;
+            float4 v = *reinterpret_cast<const float4*>(vp);
+            if (in.act == 1) {
+              v.x = acc[i][0] * softplus2_grad_f(v.x); v.y = acc[i][1] * softplus2_grad_f(v.y);
+              v.z = acc[i][2] * softplus2_grad_f(v.z); v.w = acc[i][3] * softplus2_grad_f(v.w);
+            } else {
+              v.x = v.x > 0.f ? acc[i][0] : 0.f; v.y = v.y > 0.f ? acc[i][1] : 0.f;
+              v.z = v.z > 0.f ? acc[i][2] : 0.f; v.w = v.w > 0.f ? acc[i][3] : 0.f;
+            }
+            *reinterpret_cast<float4*>(vp) = v;
+          }
+        }
+      }
+    } else if (want_out && in.kind == kInLatent) {
+      for (int oo = tid; oo < kTM * kZ; oo += kThreads) {
+        int r = oo >> 3, k = oo & 7;
+        if (r < nv) {
+          float s = 0.f;
+          if (k < K)
+            for (int n = 0; n < kH; ++n) s = fmaf(Dt[r * kLD + n], Ws[n * 9 + k], s);
+          g_out[(size_t)(row0 + r) * kZ + k] = s;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- reductions, gradient export, AdamW ----
+  float* gb = Dt;                // [64] db | [64] dslope
+  sm->red[ty][c4 + 0] = db4[0]; sm->red[ty][c4 + 1] = db4[1]; sm->red[ty][c4 + 2] = db4[2]; sm->red[ty][c4 + 3] = db4[3];
+  __syncthreads();
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[tid] = s; }
+  __syncthreads();
+  sm->red[ty][c4 + 0] = ds4[0]; sm->red[ty][c4 + 1] = ds4[1]; sm->red[ty][c4 + 2] = ds4[2]; sm->red[ty][c4 + 3] = ds4[3];
+  __syncthreads();
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[kH + tid] = s; }
+  __syncthreads();
+  if (want_out && in.kind == kInHidden) {
+    sm->red[ty][c4 + 0] = sg4[0]; sm->red[ty][c4 + 1] = sg4[1]; sm->red[ty][c4 + 2] = sg4[2]; sm->red[ty][c4 + 3] = sg4[3];
+    __syncthreads();
+    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sg[tid] = s; }
+    __syncthreads();
+    sm->red[ty][c4 + 0] = sgx4[0]; sm->red[ty][c4 + 1] = sgx4[1]; sm->red[ty][c4 + 2] = sgx4[2]; sm->red[ty][c4 + 3] = sgx4[3];
+    __syncthreads();
+    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sgx[tid] = s; }
+    __syncthreads();
+  }
+  if (in.kind == kInHidden) {
+    const int qq = tid >> 6, tt = tid & 63, m0 = 8 * (tt >> 3), n0 = 8 * (tt & 7);
+    for (int pass = 0; pass < 4; ++pass) {
+      if (qq == pass) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float* dst = gradW + (m0 + i) * kH + n0 + j;
+            *dst = pass == 0 ? accW[i][j] : *dst + accW[i][j];
+          }
+      }
+      __syncthreads();
+    }
+  } else if (in.kind == kInWide) {
+    const int m0 = 8 * (tid >> 5), n0 = 8 * (tid & 31);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n0 + j < K) gradW[(m0 + i) * K + n0 + j] = accW[i][j];
+    __syncthreads();
+  } else {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
+      if (k < K) gradW[n * K + k] = accS[e];
+    }
+    __syncthreads();
+  }
+  adam_apply(c, o, net, nl.w_off[l], kH * K, gradW);
+  adam_apply(c, o, net, nl.b_off[l], kH, gb);
+  adam_apply(c, o, net, nl.a_off[l], kH, gb + kH);
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// last encoder layer backward: BN(nstyle) -> Linear(64, nstyle); input gradient for hidden layer L-2
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void bwd_enc_last(const Ctx& c, const LayerIn& in, float* __restrict__ g_out, int o) {
+  SmemFixed* sm = c.sm;
+  const raae_net_layout& nl = NL(c, kE);
+  const int L = nl.n_linear, l = L - 1, ns = nl.out_dim[l];
+  const int tid = threadIdx.x, ch = tid & 63, q = tid >> 6;
+  const float* zE = c.sc + c.p->sl.zE;
+  const float* dz = c.sc + c.p->sl.dz;
+  float* Ws = c.arena;                 // [kZ][kLD]
+  float* At = Ws + kZ * kLD;           // [kTM][kLD]
+  float* D5 = At + kTile;              // [kTM][kZ]
+  float* gradW = D5 + kTM * kZ;        // [kZ][64] + [kZ]
+  __syncthreads();
+  // batch means of dz and dz * zhat
+  {
+    const int k = tid & 7, g = tid >> 3;
+    const float mu = sm->mean[kE][l][k], is = sm->inv[kE][l][k];
+    float s0 = 0.f, s1 = 0.f;
+    for (int r = g; r < c.B; r += 32) {
+      float d = dz[(size_t)r * kZ + k];
+      float zh = (zE[(size_t)r * kZ + k] - mu) * is;
+      s0 += d;
+      s1 = fmaf(d, zh, s1);
+    }
+    float* red = &sm->red[0][0];
+    red[tid] = s0;
+    red[256 + tid] = s1;
+    __syncthreads();
+    if (tid < kZ) {
+      float t0 = 0.f, t1 = 0.f;
+      for (int i = 0; i < 32; ++i) { t0 += red[i * 8 + tid]; t1 += red[256 + i * 8 + tid]; }
+      sm->zs[2][tid] = t0 / (float)c.B;
+      sm->zs[3][tid] = t1 / (float)c.B;
+    }
+  }
+  for (int i = tid; i < kZ * kH; i += kThreads) {
+    int n = i >> 6, k = i & 63;
+    Ws[n * kLD + k] = n < ns ? netp(c, kE)[nl.w_off[l] + n * kH + k] : 0.f;
+  }
+  __syncthreads();
+  float accW[2] = {0.f, 0.f};
+  float accB = 0.f, sgp = 0.f, sgxp = 0.f;
+  const int ntiles = (c.B + kTM - 1) / kTM;
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    build_act_tile(At, in.src, row0, nv, in.mean, in.inv, in.slope, in.mask);
+    for (int i = tid; i < kTM * kZ; i += kThreads) {
+      int r = i >> 3, k = i & 7;
+      float v = 0.f;
+      if (r < nv && k < ns) {
+        float is = sm->inv[kE][l][k];
+        float zh = (zE[(size_t)(row0 + r) * kZ + k] - sm->mean[kE][l][k]) * is;
+        v = (dz[(size_t)(row0 + r) * kZ + k] - sm->zs[2][k] - zh * sm->zs[3][k]) * is;
+      }
+      D5[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {          // dW[n][k], n < 8, k < 64
+      int oo = tid + kThreads * e, n = oo >> 6, k = oo & 63;
+      float s = accW[e];
+      for (int r = 0; r < kTM; ++r) s = fmaf(D5[r * kZ + n], At[r * kLD + k], s);
+      accW[e] = s;
+    }
+    if (tid < kZ) {
+      float s = accB;
+      for (int r = 0; r < kTM; ++r) s += D5[r * kZ + tid];
+      accB = s;
+    }
+    for (int i = 0; i < kTM / 4; ++i) {
+      int r = q + 4 * i;
+      if (r < nv) {
+        float gg = 0.f;
+#pragma unroll
+        for (int n = 0; n < kZ; ++n) gg = fmaf(D5[r * kZ + n], Ws[n * kLD + ch], gg);
+        bool keep = mask_keep(in.mask, row0 + r, ch);
+        float gm = keep ? gg * in.mask.scale : 0.f;
+        sgp += gm;
+        sgxp = fmaf(gg, At[r * kLD + ch], sgxp);
+        g_out[(size_t)(row0 + r) * kH + ch] = gm;
+      }
+    }
+    __syncthreads();
+  }
+  sm->red[q][ch] = sgp;
+  sm->red[4 + q][ch] = sgxp;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    int oo = tid + kThreads * e, n = oo >> 6, k = oo & 63;
+    if (n < ns) gradW[n * kH + k] = accW[e];
+  }
+  if (tid < ns) gradW[kZ * kH + tid] = accB;
+  __syncthreads();
+  if (q == 0) {
+    sm->sg[ch] = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
+    sm->sgx[ch] = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
+  }
+  adam_apply(c, o, kE, nl.w_off[l], ns * kH, gradW);
+  adam_apply(c, o, kE, nl.b_off[l], ns, gradW + kZ * kH);
+  __syncthreads();
+}
+
+// FCEncoder backward from sc.dz; x = the encoder's input rows.  dx_out != null (MI phase): the decoder
+// pre-activation panel that receives dL/dv in place.
+__device__ __forceinline__ void encoder_backward(const Ctx& c, const LayerIn& x, int inst, int o, float* dx_out) {
+  const raae_net_layout& nl = NL(c, kE);
+  const int L = nl.n_linear;
+  float* g0 = c.sc + c.p->sl.g[0];
+  float* g1 = c.sc + c.p->sl.g[1];
+  bwd_enc_last(c, hidden_out(c, kE, L - 2, inst), g0, o);
+  float* gin = g0;
+  float* gout = g1;
+  for (int l = L - 2; l >= 1; --l) {
+    bwd_hidden(c, kE, l, hidden_out(c, kE, l - 1, inst), c.sc + c.p->sl.uE[l], gin, gout, o);
+    float* t = gin; gin = gout; gout = t;
+  }
+  bwd_hidden(c, kE, 0, x, c.sc + c.p->sl.uE[0], gin, dx_out, o);
+}
+
+// hidden blocks of the decoder backward; on entry g[0] / sm->sg,sgx hold the gradient w.r.t. the last
+// hidden block's output.  dz_out != null: gradient w.r.t. the latent input -> sc.dz
+__device__ __forceinline__ void decoder_backward_hidden(const Ctx& c, const LayerIn& z, int inst, int o, float* dz_out) {
+  const raae_net_layout& nl = NL(c, kD);
+  const int L = nl.n_linear;
+  float* gin = c.sc + c.p->sl.g[0];
+  float* gout = c.sc + c.p->sl.g[1];
+  for (int l = L - 2; l >= 1; --l) {
+    bwd_hidden(c, kD, l, hidden_out(c, kD, l - 1, inst), c.sc + c.p->sl.uD[l], gin, gout, o);
+    float* t = gin; gin = gout; gout = t;
+  }
+  bwd_hidden(c, kD, 0, z, c.sc + c.p->sl.uD[0], gin, dz_out, o);
+}
+
+}  // namespace raae

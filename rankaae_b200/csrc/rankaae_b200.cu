@@ -1,0 +1,304 @@
+// Host side of the C ABI declared in include/rankaae_b200.h.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "aae_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define RAAE_CUDA(expr)                                                                           \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess) return fail(-2, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
+  } while (0)
+
+int round4(int x) { return (x + 3) & ~3; }
+
+int validate_config(const raae_config& c) {
+  if (c.dim_in <= 0 || c.dim_in > raae::kMaxDim || (c.dim_in & 3)) return fail(-1, "dim_in must be a multiple of 4 in [4, 256]");
+  if (c.dim_out <= 0 || c.dim_out > raae::kMaxDim || (c.dim_out & 3)) return fail(-1, "dim_out must be a multiple of 4 in [4, 256]");
+  if (c.dim_in != c.dim_out) return fail(-1, "dim_in must equal dim_out (the mutual-information phase feeds the decoder output to the encoder)");
+  if (c.nstyle <= 0 || c.nstyle > RAAE_ZPAD) return fail(-1, "nstyle must be in [1, 8]");
+  if (c.n_aux < 1 || c.n_aux > c.nstyle) return fail(-1, "n_aux must be in [1, nstyle]");
+  if (c.n_layers < 2 || c.n_layers > RAAE_MAX_LAYERS) return fail(-1, "n_layers must be in [2, 8]");
+  if (c.dis_layers != 3) return fail(-1, "only FC_discriminator_layers == 3 is implemented");
+  if (c.batch_size <= 1) return fail(-1, "batch_size must be > 1");
+  if (c.n_trials <= 0) return fail(-1, "n_trials must be positive");
+  if (c.max_rows < c.batch_size) return fail(-1, "max_rows must be >= batch_size");
+  if (c.ctas_per_trial != 1) return fail(-1, "ctas_per_trial must be 1 in this version");
+  return 0;
+}
+
+// parameters()-order vector of an MLP: per Linear: weight, bias, then the PReLU slopes of the block
+void layout_net(raae_net_layout& n, const int* dims, int n_linear, bool last_has_prelu_none, int& cursor_params) {
+  (void)last_has_prelu_none;
+  n.n_linear = n_linear;
+  int off = 0;
+  for (int l = 0; l < RAAE_MAX_LAYERS; ++l) {
+    n.in_dim[l] = n.out_dim[l] = 0;
+    n.w_off[l] = n.b_off[l] = n.a_off[l] = n.rm_off[l] = n.rv_off[l] = -1;
+  }
+  for (int l = 0; l < n_linear; ++l) {
+    n.in_dim[l] = dims[l];
+    n.out_dim[l] = dims[l + 1];
+    n.w_off[l] = off; off += dims[l] * dims[l + 1];
+    n.b_off[l] = off; off += dims[l + 1];
+    if (l < n_linear - 1) { n.a_off[l] = off; off += dims[l + 1]; }
+  }
+  n.n_params = off;
+  n.param_off = cursor_params;
+  cursor_params += round4(off);
+}
+
+void build_layout(const raae_config& c, raae_layout& L, raae::ScratchLayout& S) {
+  std::memset(&L, 0, sizeof(L));
+  std::memset(&S, 0, sizeof(S));
+  const int H = RAAE_HIDDEN;
+  int cur = 0;
+  int dims[RAAE_MAX_LAYERS + 1];
+  // encoder: dim_in -> H x (n_layers-1) -> nstyle            (model.py:330-378)
+  dims[0] = c.dim_in;
+  for (int l = 1; l < c.n_layers; ++l) dims[l] = H;
+  dims[c.n_layers] = c.nstyle;
+  layout_net(L.net[raae::kE], dims, c.n_layers, true, cur);
+  // decoder: nstyle -> H x (n_layers-1) -> dim_out            (model.py:518-570)
+  dims[0] = c.nstyle;
+  for (int l = 1; l < c.n_layers; ++l) dims[l] = H;
+  dims[c.n_layers] = c.dim_out;
+  layout_net(L.net[raae::kD], dims, c.n_layers, true, cur);
+  // discriminator: nstyle -> H x (dis_layers-1) -> 1          (model.py:631-663)
+  dims[0] = c.nstyle;
+  for (int l = 1; l < c.dis_layers; ++l) dims[l] = H;
+  dims[c.dis_layers] = 1;
+  layout_net(L.net[raae::kS], dims, c.dis_layers, true, cur);
+  // BatchNorm buffers: encoder every layer, decoder hidden layers only
+  for (int net = 0; net < 2; ++net) {
+    raae_net_layout& n = L.net[net];
+    int nbn = net == raae::kE ? n.n_linear : n.n_linear - 1;
+    for (int l = 0; l < nbn; ++l) {
+      n.rm_off[l] = cur; cur += round4(n.out_dim[l]);
+      n.rv_off[l] = cur; cur += round4(n.out_dim[l]);
+    }
+    n.nbt_off = cur; cur += 4;
+  }
+  L.net[raae::kS].nbt_off = -1;
+  // optimizers (trainer.py:333-397): adversarial (S+E), correlation (E), reconstruction (E+D),
+  // mutual_info (E+D), smoothness (D); vector order = param-group order
+  const int members[RAAE_NUM_PHASES][3] = {{raae::kS, raae::kE, -1}, {raae::kE, -1, -1}, {raae::kE, raae::kD, -1},
+                                           {raae::kE, raae::kD, -1}, {raae::kD, -1, -1}};
+  for (int o = 0; o < RAAE_NUM_PHASES; ++o) {
+    raae_opt_layout& ol = L.opt[o];
+    for (int k = 0; k < RAAE_NUM_NETS; ++k) ol.net_off[k] = -1;
+    int n = 0;
+    for (int k = 0; k < 3 && members[o][k] >= 0; ++k) { ol.net_off[members[o][k]] = n; n += L.net[members[o][k]].n_params; }
+    ol.n = n;
+    ol.m_off = cur; cur += round4(n);
+    ol.v_off = cur; cur += round4(n);
+    ol.scalar_off = cur; cur += 4;
+  }
+  L.misc_off = cur; cur += 16;
+  L.state_floats = round4(cur);
+  // scratch
+  const int rows = c.max_rows;
+  int s = 0;
+  S.xld = round4(c.dim_in);
+  S.vld = round4(c.dim_out);
+  S.xn = s; s += rows * S.xld;
+  S.aux = s; s += rows * RAAE_ZPAD;
+  for (int l = 0; l < c.n_layers - 1; ++l) { S.uE[l] = s; s += rows * H; }
+  S.zE = s; s += rows * RAAE_ZPAD;
+  S.dz = s; s += rows * RAAE_ZPAD;
+  for (int l = 0; l < c.n_layers - 1; ++l) { S.uD[l] = s; s += rows * H; }
+  S.v = s; s += rows * S.vld;
+  S.g[0] = s; s += rows * H;
+  S.g[1] = s; s += rows * H;
+  S.zs = s; s += rows * RAAE_ZPAD;
+  S.rank = s; s += rows * RAAE_ZPAD;
+  S.total = round4(s);
+  L.scratch_floats = S.total;
+}
+
+}  // namespace
+
+struct raae_handle {
+  raae::KParams kp;
+  int device;
+  int64_t launches;
+  bool bound_state, bound_data;
+  int shapiro_n;
+};
+
+extern "C" {
+
+const char* raae_last_error(void) { return g_err.c_str(); }
+int raae_version(void) { return 100; }
+
+int raae_query_layout(const raae_config* cfg, raae_layout* out) {
+  if (!cfg || !out) return fail(-1, "null argument");
+  if (int rc = validate_config(*cfg)) return rc;
+  raae::ScratchLayout sl;
+  build_layout(*cfg, *out, sl);
+  return 0;
+}
+
+int raae_create(const raae_config* cfg, int device, raae_handle** out) {
+  if (!cfg || !out) return fail(-1, "null argument");
+  if (int rc = validate_config(*cfg)) return rc;
+  int ndev = 0;
+  RAAE_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(-1, "no such CUDA device");
+  RAAE_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RAAE_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(-3, "rankaae_b200 requires an sm_100a (B200) device; there is no fallback path");
+  raae_handle* h = new (std::nothrow) raae_handle();
+  if (!h) return fail(-4, "out of host memory");
+  std::memset(&h->kp, 0, sizeof(h->kp));
+  h->kp.cfg = *cfg;
+  build_layout(*cfg, h->kp.lay, h->kp.sl);
+  h->device = device;
+  h->launches = 0;
+  h->bound_state = h->bound_data = false;
+  h->shapiro_n = 0;
+  RAAE_CUDA(cudaFuncSetAttribute(raae::raae_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raae::kSmemBytes));
+  RAAE_CUDA(cudaFuncSetAttribute(raae::raae_val_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raae::kSmemBytes));
+  *out = h;
+  return 0;
+}
+
+int raae_destroy(raae_handle* h) {
+  delete h;
+  return 0;
+}
+
+int raae_bind_state(raae_handle* h, float* state, float* scratch, const double* hp) {
+  if (!h || !state || !scratch || !hp) return fail(-1, "null argument");
+  if (((uintptr_t)state | (uintptr_t)scratch) & 15) return fail(-1, "state/scratch must be 16-byte aligned");
+  h->kp.state = state;
+  h->kp.scratch = scratch;
+  h->kp.hp = hp;
+  h->bound_state = true;
+  return 0;
+}
+
+int raae_bind_dataset(raae_handle* h, const float* spec_train, const float* aux_train, int n_train,
+                      const float* spec_val, const float* aux_val, int n_val) {
+  if (!h) return fail(-1, "null handle");
+  if (n_train < 0 || n_val < 0) return fail(-1, "negative row count");
+  if (n_val > h->kp.cfg.max_rows) return fail(-1, "n_val exceeds max_rows");
+  if (n_val > 16384) return fail(-1, "n_val > 16384 is not supported by the in-kernel sort (cap the validation split)");
+  if (((uintptr_t)spec_train | (uintptr_t)spec_val) & 15) return fail(-1, "spectra must be 16-byte aligned");
+  h->kp.spec_train = spec_train;
+  h->kp.aux_train = aux_train;
+  h->kp.n_train = n_train;
+  h->kp.spec_val = spec_val;
+  h->kp.aux_val = aux_val;
+  h->kp.n_val = n_val;
+  h->bound_data = true;
+  return 0;
+}
+
+int raae_bind_shapiro_weights(raae_handle* h, const float* w, int n) {
+  if (!h || !w) return fail(-1, "null argument");
+  h->kp.shapiro_w = w;
+  h->shapiro_n = n;
+  return 0;
+}
+
+int raae_reset_optimizers(raae_handle* h, void* stream) {
+  if (!h || !h->bound_state) return fail(-1, "state not bound");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  int n = h->kp.cfg.n_trials;
+  raae::raae_reset_opt_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->kp, n);
+  RAAE_CUDA(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int raae_step_debug(raae_handle* h, int trial, const raae_debug_io* io, void* stream) {
+  if (!h || !io) return fail(-1, "null argument");
+  if (!h->bound_state) return fail(-1, "state not bound");
+  if (trial < 0 || trial >= h->kp.cfg.n_trials) return fail(-1, "trial out of range");
+  if (io->rows <= 1 || io->rows > h->kp.cfg.batch_size) return fail(-1, "rows must be in (1, batch_size]");
+  if (!io->x_noisy || (h->kp.cfg.n_aux > 0 && !io->aux)) return fail(-1, "x_noisy / aux are required");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  raae::RunArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.trial0 = trial;
+  a.debug = 1;
+  a.epoch = io->epoch;
+  a.dbg = *io;
+  raae::raae_train_kernel<<<1, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+  RAAE_CUDA(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int raae_validate(raae_handle* h, int trial, const raae_val_io* io, void* stream) {
+  if (!h || !io) return fail(-1, "null argument");
+  if (!h->bound_state || !h->bound_data) return fail(-1, "state / dataset not bound");
+  if (h->shapiro_n != h->kp.n_val) return fail(-1, "Shapiro-Wilk weights are not bound for n_val");
+  if (trial < 0 || trial >= h->kp.cfg.n_trials) return fail(-1, "trial out of range");
+  if (h->kp.n_val < 3) return fail(-1, "validation split too small");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  raae::RunArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.trial0 = trial;
+  a.debug = 1;
+  a.epoch = io->epoch;
+  a.val = *io;
+  raae::raae_val_kernel<<<1, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+  RAAE_CUDA(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int raae_train_epochs(raae_handle* h, int epoch_begin, int n_epochs, const int32_t* perm, float* out_losses,
+                      float* out_metrics, void* stream) {
+  if (!h || !perm) return fail(-1, "null argument");
+  if (!h->bound_state || !h->bound_data) return fail(-1, "state / dataset not bound");
+  if (h->kp.n_train <= 1) return fail(-1, "training split too small");
+  if (h->kp.n_val >= 3 && h->shapiro_n != h->kp.n_val) return fail(-1, "Shapiro-Wilk weights are not bound for n_val");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  const int nt = h->kp.cfg.n_trials, bs = h->kp.cfg.batch_size;
+  const int n_steps = (h->kp.n_train + bs - 1) / bs;
+  // a short last batch of one row would make BatchNorm statistics undefined (torch raises there too)
+  if (h->kp.n_train - (n_steps - 1) * bs < 2) return fail(-1, "last batch has fewer than 2 rows");
+  for (int e = 0; e < n_epochs; ++e) {
+    raae::RunArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.trial0 = 0;
+    a.debug = 0;
+    a.epoch = epoch_begin + e;
+    a.n_steps = n_steps;
+    a.perm = perm + (size_t)e * nt * h->kp.n_train;
+    a.out_losses = out_losses ? out_losses + (size_t)e * nt * 12 : nullptr;
+    a.out_metrics = out_metrics ? out_metrics + (size_t)e * nt * 6 : nullptr;
+    a.val.avg_mutual_info = -INFINITY;
+    raae::raae_train_kernel<<<nt, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+    RAAE_CUDA(cudaGetLastError());
+    h->launches++;
+    if (h->kp.n_val >= 3) {
+      raae::raae_val_kernel<<<nt, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+      RAAE_CUDA(cudaGetLastError());
+      h->launches++;
+    }
+  }
+  return 0;
+}
+
+int64_t raae_launch_count(const raae_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

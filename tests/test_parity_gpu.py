@@ -1,0 +1,236 @@
+"""GPU parity tests: the fused sm_100a step (called through the C ABI) against the pinned oracle.
+
+All tests here need a B200 (`-m gpu`).  Sizes: the committed golden fixtures (B = 200 / 80 with
+batch_size 200, example architecture) and seeded full-size batches (B = 1024 and the ragged 804 of
+the 7000-row example dataset)."""
+import numpy as np
+import pytest
+
+from oracle import aae_oracle as O
+from tests import parity_util as PU
+from tests.golden_util import Golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _engine(cfg_dict, n_trials=1, max_rows=None):
+    from rankaae_b200.engine import Engine
+    return Engine(cfg_dict, n_trials=n_trials, device="cuda:0", max_rows=max_rows)
+
+
+def _golden_states(g):
+    """Oracle replay (float64) -> the float32-rounded state/opt at the start of every recorded batch."""
+    state, opt = g.state("state0"), g.opt("opt0")
+    out = []
+    for b in range(g.n_batches):
+        out.append((PU.f32_state(state), PU.f32_opt(opt)))
+        x, aux, rnd = g.batch(b)
+        O.train_step(state, opt, g.cfg, x, aux, rnd, epoch=g.record_epoch)
+    return out, state
+
+
+@pytest.fixture(scope="module", params=["step_warm.npz", "step_fresh.npz"])
+def golden_case(request, torch_cuda):
+    g = Golden(request.param)
+    eng = _engine(g.cfg_dict, max_rows=max(g.cfg.batch_size, g.n_val))
+    states, end_state = _golden_states(g)
+    yield g, eng, states, end_state
+    PU.dump_report(f"parity_{request.param.split('.')[0]}.json")
+    eng.close()
+
+
+@pytest.mark.parametrize("phase", O.PHASES)
+@pytest.mark.parametrize("batch", [0, 1])
+def test_golden_phase_parity(golden_case, batch, phase):
+    g, eng, states, _ = golden_case
+    state, opt = states[batch]
+    x, aux, rnd = g.batch(batch)
+    x = np.float32(x).astype(np.float64)
+    rep, got, ref = PU.compare_phase(eng, 0, g.cfg, state, opt, x, aux, PU.f32_rnd(rnd), g.record_epoch, phase,
+                                     tag=f"golden-b{batch}")
+    PU.check_phase_report(rep)
+    if batch == 0:
+        # the oracle's loss at batch 0 is the reference's own number (float64), up to the float32
+        # rounding of the noised input
+        ref_loss = g.losses(0)[phase]
+        assert abs(rep["loss_cuda"] - ref_loss) <= 2 * PU.LOSS_TOL[phase] * max(1.0, abs(ref_loss))
+
+
+@pytest.mark.parametrize("phase", O.PHASES)
+def test_golden_adamw(golden_case, phase):
+    g, eng, states, _ = golden_case
+    state, opt = states[1]
+    x, aux, rnd = g.batch(1)
+    x = np.float32(x).astype(np.float64)
+    PU.check_adam(eng, 0, g.cfg, state, opt, x, aux, PU.f32_rnd(rnd), g.record_epoch, phase)
+
+
+def test_golden_full_step_sequential(golden_case):
+    """All five phases with their updates in one call (warm case only: with fresh AdamW state the first
+    update is sign-like and float32/float64 trajectories legitimately split)."""
+    g, eng, states, _ = golden_case
+    if g.record_epoch == 0:
+        pytest.skip("fresh AdamW state")
+    state, opt = states[0]
+    x, aux, rnd = g.batch(0)
+    x = np.float32(x).astype(np.float64)
+    eng.set_state(0, state, opt)
+    got = eng.step_debug(0, x, aux, PU.f32_rnd(rnd), epoch=g.record_epoch, phase_mask=0x1f, apply_updates=True)
+    ref_losses = g.losses(0)
+    for ph in O.PHASES:
+        assert abs(got["losses"][ph] - ref_losses[ph]) <= 5e-4 * max(1.0, abs(ref_losses[ph])), (ph, got["losses"], ref_losses)
+    new_state, _ = eng.get_state(0)
+    st = O.clone_state(state)
+    op = {k: dict(v) for k, v in opt.items()}
+    import copy
+    op = copy.deepcopy(opt)
+    O.train_step(st, op, g.cfg, x, aux, PU.f32_rnd(rnd), epoch=g.record_epoch)
+    for net in ("E", "D", "S"):
+        a = PU.net_vec(new_state[net], skip_last_bias=(net == "E"))
+        b = PU.net_vec(st[net], skip_last_bias=(net == "E"))
+        assert PU.rel_l2(a, b) <= 1e-4, net
+    assert new_state["E"]["nbt"] == st["E"]["nbt"] and new_state["D"]["nbt"] == st["D"]["nbt"]
+
+
+def test_golden_validation_block(golden_case):
+    """Eval block (trainer.py:207-297): val losses, Shapiro-Wilk, Spearman coupling, combined metric against
+    the reference's own float64 numbers."""
+    g, eng, _, end_state = golden_case
+    v = g.val()
+    eng.set_state(0, PU.f32_state(end_state))
+    eng.bind_dataset(g.spec[:g.n_train], g.aux[:g.n_train], v["spec"], v["aux"])
+    avg_mi = float(v["metrics"][2])
+    out = eng.validate(0, z_sample=v["z_sample"], z_real=v["z_real"], epoch=g.record_epoch, avg_mutual_info=avg_mi)
+    rep = {"tag": "val", "losses_cuda": out["losses"], "losses_ref": {k: float(x) for k, x in v["losses"].items()},
+           "metrics_cuda": list(out["metrics"]), "metrics_ref": list(v["metrics"])}
+    PU.REPORT.append(rep)
+    for ph in O.PHASES:
+        assert abs(out["losses"][ph] - v["losses"][ph]) <= 5e-4 * max(1.0, abs(v["losses"][ph])), (ph, rep)
+    m = out["metrics"]
+    assert abs(m[0] - v["metrics"][0]) <= 2e-4, rep           # min Shapiro W
+    assert abs(m[1] - v["metrics"][1]) <= 5e-4 * max(1.0, abs(v["metrics"][1])), rep
+    assert abs(m[3] - v["metrics"][3]) <= 1e-3, rep           # Spearman coupling (rank ties are impossible here)
+    assert abs(m[4] - v["metrics"][4]) <= 5e-4, rep
+    combined = -(m[0] - m[1] - 0.01 * m[2] - m[3] - m[4])
+    assert abs(m[5] - combined) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# full-size seeded batches of the example configuration (BASELINE.json configs[1])
+# ------------------------------------------------------------------------------------------
+EXAMPLE = dict(
+    max_epoch=2000, batch_size=1024, gradient_reversal=True, alpha_flat_step=739, alpha_limit=0.7172,
+    decoder_activation="Softplus", dis_beta=1.1, dis_dropout_rate=0.056, dis_noise=0.56, n_aux=5, nstyle=6,
+    ae_form="FC", dim_in=256, dim_out=256, n_layers=5, FC_discriminator_layers=3, use_cnn_discriminator=False,
+    dropout_rate=0.04, sch_factor=0.1, sch_patience=100, lr_base=0.001, lr_ratio_Corr=10, lr_ratio_Mutual=1,
+    lr_ratio_Reconn=10, lr_ratio_Smooth=1, lr_ratio_dis=1, optimizer_name="AdamW", spec_noise=0.02,
+    use_flex_spec_target=True, weight_decay=0.01, kendall_activation=True, epoch_stop_smooth=1500)
+
+
+@pytest.fixture(scope="module")
+def example_engine(torch_cuda):
+    eng = _engine(EXAMPLE, max_rows=1056)
+    yield eng
+    PU.dump_report("parity_fullsize.json")
+    eng.close()
+
+
+@pytest.mark.parametrize("rows", [1024, 804])
+@pytest.mark.parametrize("phase", O.PHASES)
+def test_fullsize_phase_parity(example_engine, rows, phase):
+    cfg = O.Config.from_dict(EXAMPLE)
+    rng = np.random.default_rng(100 + rows)
+    state = PU.f32_state(O.init_state(cfg, rng))
+    # a "trained-like" perturbation of the PReLU slopes and BN buffers so that nothing sits at its init value
+    for net in ("E", "D", "S"):
+        state[net]["a"] = [np.float32(a + rng.uniform(-0.005, 0.2, a.shape)).astype(np.float64) for a in state[net]["a"]]
+    spec, aux = O.synthetic_dataset(rows, cfg, seed=rows, dtype=np.float32)
+    x = np.float32(spec + cfg.spec_noise * rng.standard_normal(spec.shape)).astype(np.float64)
+    rnd = PU.f32_rnd(O.draw_step_randoms(cfg, rows, rng))
+    rep, _, _ = PU.compare_phase(example_engine, 0, cfg, state, None, x, aux.astype(np.float64), rnd, 700, phase,
+                                 tag=f"full-{rows}")
+    PU.check_phase_report(rep)
+
+
+def test_row_permutation_invariance(example_engine):
+    """Size-independent property: BatchNorm statistics, the Kendall pair sums and every mean-reduced loss
+    are invariant under a permutation of the batch rows (draws permuted alongside)."""
+    cfg = O.Config.from_dict(EXAMPLE)
+    rows = 804
+    rng = np.random.default_rng(7)
+    state = PU.f32_state(O.init_state(cfg, rng))
+    spec, aux = O.synthetic_dataset(rows, cfg, seed=3, dtype=np.float32)
+    rnd = O.draw_step_randoms(cfg, rows, rng)
+    perm = rng.permutation(rows)
+
+    def permuted(r):
+        out = {}
+        for k, v in r.items():
+            if k in ("z_real", "S_real_eps", "S_real_masks") or v is None:
+                out[k] = v
+            elif isinstance(v, list):
+                out[k] = [m[perm] for m in v]
+            else:
+                out[k] = v[perm]
+        return out
+
+    example_engine.set_state(0, state)
+    a = example_engine.step_debug(0, spec, aux, rnd, epoch=10, apply_updates=False)
+    example_engine.set_state(0, state)
+    b = example_engine.step_debug(0, spec[perm], aux[perm], permuted(rnd), epoch=10, apply_updates=False)
+    for ph in O.PHASES:
+        assert abs(a["losses"][ph] - b["losses"][ph]) <= 2e-5 * max(1.0, abs(a["losses"][ph])), ph
+    for ph, nets in a["grads"].items():
+        for net in nets:
+            va = PU.net_vec(a["grads"][ph][net], skip_last_bias=(net == "E"))
+            vb = PU.net_vec(b["grads"][ph][net], skip_last_bias=(net == "E"))
+            assert PU.rel_l2(va, vb) <= 5e-3, (ph, net)
+
+
+def test_repeatability_bitwise(example_engine):
+    """The same call twice gives bit-identical losses, gradients and state (no atomics, fixed reduction order)."""
+    cfg = O.Config.from_dict(EXAMPLE)
+    rng = np.random.default_rng(11)
+    state = PU.f32_state(O.init_state(cfg, rng))
+    spec, aux = O.synthetic_dataset(300, cfg, seed=5, dtype=np.float32)
+    rnd = O.draw_step_randoms(cfg, 300, rng)
+    outs = []
+    for _ in range(2):
+        example_engine.set_state(0, state)
+        example_engine.reset_optimizers()
+        r = example_engine.step_debug(0, spec, aux, rnd, epoch=3, apply_updates=True)
+        outs.append((r, example_engine.state[0].clone()))
+    assert all(outs[0][0]["losses"][ph] == outs[1][0]["losses"][ph] for ph in O.PHASES)
+    assert bool((outs[0][1] == outs[1][1]).all())
+
+
+def test_production_epochs_learn(torch_cuda):
+    """The production path (in-kernel RNG, device-resident dataset, per-epoch validation + scheduler): a few
+    epochs of an 8-trial ensemble on the synthetic set must reduce the validation reconstruction error and
+    move the Kendall loss negative for every trial, with finite metrics."""
+    import torch
+    cfg = dict(EXAMPLE, batch_size=256, max_epoch=40)
+    ocfg = O.Config.from_dict(cfg)
+    spec, aux = O.synthetic_dataset(1400, ocfg, seed=1, dtype=np.float32)
+    from rankaae_b200.trainer import init_trial_state
+    eng = _engine(cfg, n_trials=8, max_rows=512)
+    for t in range(8):
+        init_trial_state(eng, t, cfg, seed=t)
+    eng.bind_dataset(spec[:980], aux[:980], spec[980:1190], aux[980:1190])
+    losses, metrics = eng.train_epochs(0, 40)
+    torch.cuda.synchronize()
+    losses, metrics = losses.cpu().numpy(), metrics.cpu().numpy()
+    assert np.isfinite(losses).all() and np.isfinite(metrics).all()
+    assert (metrics[-1, :, 1] < 0.5 * metrics[0, :, 1]).all(), metrics[[0, -1], :, 1]
+    assert (metrics[-1, :, 4] < -0.02).all(), metrics[-1, :, 4]
+    assert (metrics[:, :, 0] > 0).all() and (metrics[:, :, 0] <= 1.0001).all()
+    # trials are independent: different seeds give different trajectories
+    assert len(np.unique(np.round(metrics[-1, :, 1], 6))) > 1
+    eng.close()
