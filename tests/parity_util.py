@@ -4,10 +4,10 @@ Every comparison starts both sides from the SAME float32-representable state and
 explicit random draws; the oracle runs in float64.  Tolerances (see DESIGN.md "Parity"):
   * losses: |cuda - oracle| <= 1e-4 * max(1, |oracle|)   (Kendall: 5e-4, its pair classification
     flips for |s_i - s_j| ~ 1e-7)
-  * gradients: rel-L2 per network per phase <= 1e-2 — the reference's OWN float32 path differs from
+  * gradients: rel-L2 per network per phase <= 2e-3 — the reference's OWN float32 path differs from
     its float64 run by up to 3.5e-3 on these networks (BatchNorm divides
     by sqrt(var + 1e-5) with var << eps for dead PReLU channels and amplifies rounding noise);
-    typical measured values are 1e-6..1e-4 and are written to gpurun_out/parity_report.json
+    measured on B200: 7e-7..4e-4 (profiles/parity_r01.md); every value is written to gpurun_out/parity_*.json
   * AdamW: parameters / moments after the update, given the kernel's own gradient, to 2e-6 rel.
 """
 import json
@@ -19,7 +19,7 @@ from oracle import aae_oracle as O
 
 PHASES = O.PHASES
 LOSS_TOL = {"adversarial": 1e-4, "correlation": 5e-4, "reconstruction": 1e-4, "mutual_info": 1e-4, "smoothness": 1e-4}
-GRAD_TOL = 1e-2
+GRAD_TOL = 2e-3
 REPORT = []
 
 
@@ -147,3 +147,4 @@ def dump_report(name="parity_report.json"):
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, name), "w") as f:
         json.dump(REPORT, f, indent=1, default=float)
+    del REPORT[:]
