@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — AAE train throughput of the fused sm_100a path (and, with --impl reference, of the CPU
+restatement of the reference's path) on BASELINE.json's ensemble workload.
+
+Workload (config.workload): the example fix_config.yaml network (FC, n_layers 5, nstyle 6, n_aux 5,
+256-point spectra, batch 1024, AdamW) on the seeded synthetic 7000-spectrum set (4900 train /
+1050 val rows), as an ensemble of independent trials resident on each GPU (BASELINE.json configs[2]:
+the ipyparallel trial farm replaced by per-GPU trial ensembles; trials are sharded across ranks with
+no collective in the data path, so scaling is weak).
+
+One STEP = one epoch of every resident trial: 5 train batches (4 x 1024 + 804) with all five loss
+phases and their AdamW updates, followed by the validation block, the Shapiro/Spearman metrics and
+the ReduceLROnPlateau step — i.e. one iteration of the reference's `for epoch in range(max_epoch)`
+loop (trainer.py:89-307) per trial.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--trials T] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EXAMPLE = dict(
+    max_epoch=2000, batch_size=1024, gradient_reversal=True, alpha_flat_step=739, alpha_limit=0.7172,
+    decoder_activation="Softplus", dis_beta=1.1, dis_dropout_rate=0.056, dis_noise=0.56, n_aux=5, nstyle=6,
+    ae_form="FC", dim_in=256, dim_out=256, n_layers=5, FC_discriminator_layers=3, use_cnn_discriminator=False,
+    dropout_rate=0.04, sch_factor=0.1, sch_patience=100, lr_base=0.001, lr_ratio_Corr=10, lr_ratio_Mutual=1,
+    lr_ratio_Reconn=10, lr_ratio_Smooth=1, lr_ratio_dis=1, optimizer_name="AdamW", spec_noise=0.02,
+    use_flex_spec_target=True, weight_decay=0.01, kendall_activation=True, epoch_stop_smooth=1500)
+N_ROWS, N_TRAIN, N_VAL = 7000, 4900, 1050
+# algorithmic work of the train step: 612 032 MAC = 1.224 MFLOP per train sample per step
+FLOP_PER_SAMPLE = 2.0 * 612032.0
+# validation forward per val row: E+D (recon/smooth) + D+E (MI) + 2 x Dis = 125 312 MAC
+FLOP_PER_VAL_ROW = 2.0 * 125312.0
+METRIC = "aae_train_samples_per_sec"
+UNIT = "samples/s"
+
+
+def synthetic_arrays():
+    """Seeded synthetic spectra in the reference CSV's schema/value range (oracle.synthetic_dataset is the
+    generator used by every test as well; it is data generation, not the path being measured)."""
+    from oracle.aae_oracle import Config, synthetic_dataset
+    spec, aux = synthetic_dataset(N_ROWS, Config.from_dict(EXAMPLE), seed=0, dtype=np.float32)
+    return (spec[:N_TRAIN], aux[:N_TRAIN], spec[N_TRAIN:N_TRAIN + N_VAL], aux[N_TRAIN:N_TRAIN + N_VAL])
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][2]) if self.rows else None,
+                "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU side: the oracle port of the reference's epoch (numpy, float64), one trial per process
+# ------------------------------------------------------------------------------------------
+def _cpu_epoch_worker(args):
+    seed, n_epochs = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(1)
+    except Exception:
+        ctx = None
+    from oracle import aae_oracle as O
+    cfg = O.Config.from_dict(EXAMPLE)
+    rng = np.random.default_rng(seed)
+    st, at, sv, av = [a.astype(np.float64) for a in synthetic_arrays()]
+    state = O.init_state(cfg, rng)
+    opt = O.new_opt_state(state, cfg)
+    times = []
+    for e in range(n_epochs):
+        t0 = time.perf_counter()
+        perm = rng.permutation(N_TRAIN)
+        mi = []
+        for s in range(0, N_TRAIN, cfg.batch_size):
+            idx = perm[s:s + cfg.batch_size]
+            x = st[idx] + cfg.spec_noise * rng.standard_normal((len(idx), cfg.dim_in))
+            r = O.train_step(state, opt, cfg, x, at[idx], O.draw_step_randoms(cfg, len(idx), rng), epoch=e)
+            mi.append(r["losses"]["mutual_info"])
+        O.validate(state, cfg, sv, av, rng.standard_normal((cfg.batch_size, cfg.nstyle)),
+                   rng.standard_normal((N_VAL, cfg.nstyle)), e, avg_mutual_info=float(np.mean(mi)))
+        times.append(time.perf_counter() - t0)
+    if ctx is not None:
+        ctx.__exit__(None, None, None)
+    return times
+
+
+def cpu_epochs(n_proc, n_epochs):
+    """n_proc independent single-thread trials in parallel (the reference's own deployment model,
+    run_training.sh:3-9 / train_sc.py:68-70); returns per-epoch wall times (max over processes)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(n_proc) as pool:
+        res = pool.map(_cpu_epoch_worker, [(1000 + i, n_epochs) for i in range(n_proc)])
+    return np.max(np.array(res), axis=0)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    n_epochs = args.warmup + args.steps
+    t = cpu_epochs(cores, n_epochs)[args.warmup:]
+    ms = float(np.mean(t) * 1e3)
+    value = cores * N_TRAIN / float(np.mean(t))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"example fix_config ensemble, synthetic 7000x256 (4900 train/1050 val), batch 1024, "
+                               f"{cores} trials (one per host core), 1 step = 1 epoch of every trial incl. validation"},
+        "trials_per_hour_2000_epochs": cores * 3600.0 / (np.mean(t) * 2000.0),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} epochs x {cores} single-thread trials of the numpy oracle port "
+                                   "(the reference is Python/PyTorch and cannot travel to the GPU box)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as graft
+    graft.build()
+    from rankaae_b200.engine import Engine
+    from rankaae_b200.trainer import init_trial_state
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    T = args.trials
+    st, at, sv, av = synthetic_arrays()
+    eng = Engine(EXAMPLE, n_trials=T, device=dev, max_rows=1056, seeds=[rank * T + t for t in range(T)])
+    for t in range(T):
+        init_trial_state(eng, t, EXAMPLE, seed=rank * T + t)
+    # pinned host copies (the e2e leg re-uploads them every step) and the resident device copies
+    host = [torch.from_numpy(a).pin_memory() for a in (st, at, sv, av)]
+    eng.bind_dataset(*[h.to(dev) for h in host])
+    dset = eng._data
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    K, W = args.steps, args.warmup
+    epoch = 0
+    eng.train_epochs(epoch, W)
+    epoch += W
+    barrier()
+
+    # ---- value: inputs resident, K epochs back to back, device-timed ----
+    perm = eng.make_perm(K)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.launch_count
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses, metrics = eng.train_epochs(epoch, K, perm)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launch_count - l0
+    clocks = sampler.summary()
+    epoch += K
+    finite = bool(torch.isfinite(losses).all().item() and torch.isfinite(metrics).all().item())
+    ms_per_step = ms_total / K
+    value = world * T * N_TRAIN / (ms_per_step * 1e-3)
+
+    # ---- e2e: every step uploads the dataset from pinned host memory and reads the epoch's results back ----
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(K):
+        for d, h in zip(dset, host):
+            d.copy_(h, non_blocking=True)
+        lo, me = eng.train_epochs(epoch + k, 1)
+        lo_h, me_h = lo.cpu(), me.cpu()
+    t1.record()
+    barrier()
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1)) / K
+    epoch += K
+    h2d = sum(h.numel() * h.element_size() for h in host)
+    d2h = lo_h.numel() * 4 + me_h.numel() * 4
+
+    # ---- roofline of the dominant kernel (raae_train_kernel): train-only launches, CUDA events ----
+    eng.lib.raae_bind_dataset(eng.handle, dset[0].data_ptr(), dset[1].data_ptr(), N_TRAIN, dset[2].data_ptr(),
+                              dset[3].data_ptr(), 0)
+    perm = eng.make_perm(K)
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    eng.train_epochs(epoch, K, perm)
+    r1.record()
+    barrier()
+    train_ms = r0.elapsed_time(r1) / K
+    eng.bind_dataset(*dset)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    achieved_tf = T * N_TRAIN * FLOP_PER_SAMPLE / (train_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "raae_train_kernel", "achieved": achieved_tf, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
+                "traffic": None, "launch_ms": train_ms,
+                "note": "parity-mode kernel computes the contractions as FP32 FMA on CUDA cores (B200 FP32 peak "
+                        "~ 148 SM x 128 FMA x 2 x 1.9 GHz = 72 TFLOP/s); frac is against the tensor-core peak"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"example fix_config ensemble, synthetic 7000x256 (4900 train/1050 val), batch 1024, "
+                               f"{T} trials per GPU, 1 step = 1 epoch of every trial incl. validation + metrics",
+                   "trials_per_gpu": T, "l2": "per-step working set 5 MB x trials > 126 MB L2"},
+        "steps_per_sec": world * T * 5 / (ms_per_step * 1e-3),
+        "trials_per_hour_2000_epochs": world * T * 3600.0 / (ms_per_step * 1e-3 * 2000.0),
+        "e2e": {"value": world * T * N_TRAIN / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "finite": finite,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+        t = cpu_epochs(cores, 3)[1:]
+        line["cpu_baseline"] = {"value": cores * N_TRAIN / float(np.mean(t)), "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"2 timed epochs (after 1 warm-up) x {cores} single-thread trials of the numpy "
+                                          "float64 oracle port of trainer.py:89-307, same dataset and config"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--trials", type=int, default=148, help="trials resident per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
