@@ -61,7 +61,7 @@ __device__ __noinline__ void build_batch(const Ctx& c, const int32_t* __restrict
 // One iteration of the batch loop body, trainer.py:112-204 (gradient-reversal branch).
 __device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
   const KParams& p = *c.p;
-  SmemFixed* sm = c.sm;
+  RAAE_SMEM();
   const int tid = threadIdx.x, ns = p.cfg.nstyle;
   const int LE = p.lay.net[kE].n_linear;
   c.train = 1;
@@ -76,6 +76,7 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
   const float* invZ = sm->inv[kE][LE - 1];
   float* dz = c.sc + p.sl.dz;
   const int act = p.cfg.decoder_softplus ? 1 : 2;
+  const LayerIn zin = latent_in(zE, ns, LE - 1);
 
   // P0 (trainer.py:113-114): styles = E(x); spec_out = D(styles) is unused, but the decoder's BatchNorm
   // buffers advance, so its hidden blocks run (the output Linear has no side effect and is skipped).
@@ -86,11 +87,11 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
       c.a->dbg.styles[i] = (zE[(size_t)r * kZ + k] - meanZ[k]) * invZ[k];
     }
   }
-  decoder_forward_hidden(c, latent_in(zE, ns, meanZ, invZ), 0);
+  decoder_forward_hidden(c, zin, 0);
 
   // P1 adversarial (trainer.py:118-127)
   if (phase_mask & (1 << kAdv)) {
-    if (tid == 0) adam_prepare(c, kAdv);
+    if (tid == 0) adam_prepare(c, sm, kAdv);
     __syncthreads();
     dis_stage(c, 1, kAdv, c.a->debug ? c.a->dbg.z_real : nullptr, stream_key(c.seed, c.step_id, kStreamZReal));
     encoder_backward(c, x, 0, kAdv, nullptr);
@@ -101,7 +102,7 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
   if (phase_mask & (1 << kCorr)) {
     encoder_forward(c, x, 1);
     kendall_stage(c, c.sc + p.sl.aux, 1);
-    if (tid == 0) adam_prepare(c, kCorr);
+    if (tid == 0) adam_prepare(c, sm, kCorr);
     __syncthreads();
     encoder_backward(c, x, 1, kCorr, nullptr);
     if (tid == 0) adam_finish(c, kCorr);
@@ -110,9 +111,9 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
   // P3 reconstruction (trainer.py:164-172)
   if (phase_mask & (1 << kRecon)) {
     encoder_forward(c, x, 2);
-    const LayerIn z = latent_in(zE, ns, meanZ, invZ);
+    const LayerIn z = zin;
     decoder_forward_hidden(c, z, 1);
-    if (tid == 0) adam_prepare(c, kRecon);
+    if (tid == 0) adam_prepare(c, sm, kRecon);
     __syncthreads();
     dec_last(c, kLastRecon, 1, kRecon);
     decoder_backward_hidden(c, z, 1, kRecon, dz);
@@ -123,13 +124,13 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
   // P4 mutual information (trainer.py:175-186)
   if (phase_mask & (1 << kMI)) {
     encoder_forward(c, x, 3);                       // trainer.py:176: result unused, BN buffers advance
-    const LayerIn zs = latent_in(c.sc + p.sl.zs, ns, nullptr, nullptr);
+    const LayerIn zs = latent_in(c.sc + p.sl.zs, ns, -1);
     decoder_forward_hidden(c, zs, 2);
     dec_last(c, kLastStoreV, 2, kMI);
     const LayerIn y = wide_in(c.sc + p.sl.v, p.sl.vld, p.cfg.dim_out, act);
     encoder_forward(c, y, 4);
     mi_mse_stage(c, 1);
-    if (tid == 0) adam_prepare(c, kMI);
+    if (tid == 0) adam_prepare(c, sm, kMI);
     __syncthreads();
     encoder_backward(c, y, 4, kMI, c.sc + p.sl.v);
     dec_last(c, kLastFromDv, 2, kMI);
@@ -140,9 +141,9 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
   // P5 smoothness (trainer.py:189-200): only the decoder is stepped, so the encoder backward is skipped
   if ((phase_mask & (1 << kSmooth)) && (double)c.epoch < c.hp[RAAE_HP_EPOCH_STOP_SMOOTH]) {
     encoder_forward(c, x, 5);
-    const LayerIn z = latent_in(zE, ns, meanZ, invZ);
+    const LayerIn z = zin;
     decoder_forward_hidden(c, z, 3);
-    if (tid == 0) adam_prepare(c, kSmooth);
+    if (tid == 0) adam_prepare(c, sm, kSmooth);
     __syncthreads();
     dec_last(c, kLastSmooth, 3, kSmooth);
     decoder_backward_hidden(c, z, 3, kSmooth, nullptr);
@@ -160,14 +161,12 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
   __syncthreads();
 }
 
-__device__ __forceinline__ void init_ctx(Ctx& c, const KParams& p, const RunArgs& a, unsigned char* smem_raw, int trial) {
+__device__ __forceinline__ void init_ctx(Ctx& c, const KParams& p, const RunArgs& a, int trial) {
   c.p = &p;
   c.a = &a;
   c.st = p.state + (size_t)trial * p.lay.state_floats;
   c.sc = p.scratch + (size_t)trial * p.lay.scratch_floats;
   c.hp = p.hp + (size_t)trial * RAAE_HP_COUNT;
-  c.sm = reinterpret_cast<SmemFixed*>(smem_raw);
-  c.arena = reinterpret_cast<float*>(smem_raw + ((sizeof(SmemFixed) + 15) / 16) * 16);
   c.Breal = p.cfg.batch_size;
   c.seed = mix32((uint32_t)(long long)c.hp[RAAE_HP_SEED] * 0x9e3779b9U + (uint32_t)trial * 0x85ebca6bU + 1u);
   c.epoch = a.epoch;
@@ -177,14 +176,13 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const KParams& p, const RunArgs
   c.xld = p.sl.xld;
 }
 
-constexpr size_t kSmemBytes = ((sizeof(SmemFixed) + 15) / 16) * 16 + (size_t)kArenaFloats * sizeof(float);
+constexpr size_t kSmemBytes = kArenaOffset + (size_t)kArenaFloats * sizeof(float);
 
 __global__ void __launch_bounds__(kThreads, 1)
 raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int trial = a.trial0 + blockIdx.x;
   Ctx c;
-  init_ctx(c, p, a, smem_raw, trial);
+  init_ctx(c, p, a, trial);
   if (a.debug) {
     c.B = a.dbg.rows;
     c.epoch = a.dbg.epoch;
@@ -232,7 +230,7 @@ __device__ __forceinline__ void bitonic_sort(float* key, int* idx, int npad) {
 // scipy.stats.shapiro(z_k).statistic per style (Royston weights supplied by the host)
 // and max |Spearman| over style pairs (trainer.py:286-293).  Results: sm->zs[2][0] = min W, zs[2][1] = coupling.
 __device__ __noinline__ void latent_metrics(const Ctx& c) {
-  SmemFixed* sm = c.sm;
+  RAAE_SMEM();
   const KParams& p = *c.p;
   const int n = c.B, ns = p.cfg.nstyle, tid = threadIdx.x;
   const int lE = p.lay.net[kE].n_linear - 1;
@@ -241,8 +239,8 @@ __device__ __noinline__ void latent_metrics(const Ctx& c) {
   const int rstride = p.cfg.max_rows;
   int npad = 1;
   while (npad < n) npad <<= 1;
-  float* key = c.arena;
-  int* idx = reinterpret_cast<int*>(c.arena + npad);
+  float* key = arena;
+  int* idx = reinterpret_cast<int*>(arena + npad);
   float wmin = 1e30f;
   for (int k = 0; k < ns; ++k) {
     __syncthreads();
@@ -314,11 +312,10 @@ __device__ inline void plateau_step(const Ctx& c, double metric) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RAAE_SMEM();
   const int trial = a.trial0 + blockIdx.x;
   Ctx c;
-  init_ctx(c, p, a, smem_raw, trial);
-  SmemFixed* sm = c.sm;
+  init_ctx(c, p, a, trial);
   const int tid = threadIdx.x, ns = p.cfg.nstyle, K = p.cfg.n_aux;
   const int LE = p.lay.net[kE].n_linear;
   c.train = 0;
@@ -357,10 +354,10 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
   const float wmin = sm->zs[2][0], coupling = sm->zs[2][1];
   kendall_stage(c, aux, 0);
   dis_stage(c, 0, kAdv, io.z_real, stream_key(c.seed, c.step_id, kStreamValZReal));
-  decoder_forward_hidden(c, latent_in(zE, ns, meanZ, invZ), 0);
+  decoder_forward_hidden(c, latent_in(zE, ns, LE - 1), 0);
   dec_last(c, kLastEval, 0, kRecon);
   // mutual information on z_sample (trainer.py:240-246)
-  decoder_forward_hidden(c, latent_in(zs, ns, nullptr, nullptr), 0);
+  decoder_forward_hidden(c, latent_in(zs, ns, -1), 0);
   dec_last(c, kLastStoreV, 0, kMI);
   encoder_forward(c, wide_in(c.sc + p.sl.v, p.sl.vld, p.cfg.dim_out, act), 0);
   mi_mse_stage(c, 0);

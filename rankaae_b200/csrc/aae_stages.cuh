@@ -17,13 +17,13 @@ enum LastMode { kLastRecon = 0, kLastSmooth = 1, kLastStoreV = 2, kLastFromDv = 
 // Losses land in sm->loss_acc[kRecon] / [kSmooth].
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
-  SmemFixed* sm = c.sm;
+  RAAE_SMEM();
   const raae_net_layout& nl = NL(c, kD);
   const int L = nl.n_linear, l = L - 1, N = nl.out_dim[l];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, lane = tid & 31, warp = tid >> 5;
   const float* Wg = netp(c, kD) + nl.w_off[l];
   const int act = c.p->cfg.decoder_softplus ? 1 : 2;
-  float* Y = c.arena;                       // [kTM][kLDW]
+  float* Y = arena;                         // [kTM][kLDW]
   float* At = Y + kWideTile;                // [kTM][kLD]
   float* Wc = At + kTile;                   // [64][kLD]
   float* rowbuf = Wc + kWTile + warp * 576; // per warp: ypad[272] | ezp[288]
@@ -47,7 +47,7 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
   const int ntiles = (c.B + kTM - 1) / kTM;
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
-    build_act_tile(At, in.src, row0, nv, in.mean, in.inv, in.slope, in.mask);
+    build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
     if (mode != kLastFromDv) {
       for (int n0 = 0; n0 < N; n0 += kH) {
         __syncthreads();
@@ -252,8 +252,8 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
         if (m0 + i < N) gradW[(m0 + i) * kH + n0 + j] = accW[i][j];
     if (tid < N) gradb[tid] = dbp;
     __syncthreads();
-    adam_apply(c, o, kD, nl.w_off[l], N * kH, gradW);
-    adam_apply(c, o, kD, nl.b_off[l], N, gradb);
+    adam_apply(c, sm, o, kD, nl.w_off[l], N * kH, gradW);
+    adam_apply(c, sm, o, kD, nl.b_off[l], N, gradb);
   }
   __syncthreads();
 }
@@ -266,13 +266,13 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
 // sc.dz = -alpha * dL/dstyles for the fake rows.
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void dis_stage(const Ctx& c, int backward, int o, const float* z_real_ptr, uint32_t key_zreal) {
-  SmemFixed* sm = c.sm;
+  RAAE_SMEM();
   const raae_net_layout& nl = NL(c, kS);
   const raae_net_layout& el = NL(c, kE);
   const int ns = nl.in_dim[0];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, ch = tid & 63, q = tid >> 6, lane = tid & 31,
             warp = tid >> 5;
-  float* U1 = c.arena;
+  float* U1 = arena;
   float* H1 = U1 + kTile;
   float* U2 = H1 + kTile;
   float* H2 = U2 + kTile;
@@ -476,7 +476,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c, int backward, int o, const 
     if (tid == 0) sm->loss_acc[kAdv] = s;
   }
   if (backward) {
-    float* gW1 = c.arena;              // [64][64]
+    float* gW1 = arena;                // [64][64]
     float* gsm = gW1 + kH * kH;        // W0 [64*ns] | b0 64 | a0 64 | b1 64 | a1 64 | W2 64 | b2 1
     float* gW0 = gsm;
     float* gb0 = gW0 + kH * kZ;
@@ -523,14 +523,14 @@ __device__ __noinline__ void dis_stage(const Ctx& c, int backward, int o, const 
     __syncthreads();
     if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb0[tid] = s; }
     __syncthreads();
-    adam_apply(c, o, kS, nl.w_off[0], kH * ns, gW0);
-    adam_apply(c, o, kS, nl.b_off[0], kH, gb0);
-    adam_apply(c, o, kS, nl.a_off[0], kH, ga0);
-    adam_apply(c, o, kS, nl.w_off[1], kH * kH, gW1);
-    adam_apply(c, o, kS, nl.b_off[1], kH, gb1);
-    adam_apply(c, o, kS, nl.a_off[1], kH, ga1);
-    adam_apply(c, o, kS, nl.w_off[2], kH, gW2);
-    adam_apply(c, o, kS, nl.b_off[2], 1, gb2);
+    adam_apply(c, sm, o, kS, nl.w_off[0], kH * ns, gW0);
+    adam_apply(c, sm, o, kS, nl.b_off[0], kH, gb0);
+    adam_apply(c, sm, o, kS, nl.a_off[0], kH, ga0);
+    adam_apply(c, sm, o, kS, nl.w_off[1], kH * kH, gW1);
+    adam_apply(c, sm, o, kS, nl.b_off[1], kH, gb1);
+    adam_apply(c, sm, o, kS, nl.a_off[1], kH, ga1);
+    adam_apply(c, sm, o, kS, nl.w_off[2], kH, gW2);
+    adam_apply(c, sm, o, kS, nl.b_off[2], 1, gb2);
   }
   __syncthreads();
 }
@@ -547,11 +547,11 @@ __device__ __noinline__ void dis_stage(const Ctx& c, int backward, int o, const 
 constexpr int kKendallChunk = 2048;
 
 __device__ __noinline__ void kendall_stage(const Ctx& c, const float* __restrict__ aux, int want_grad) {
-  SmemFixed* sm = c.sm;
+  RAAE_SMEM();
   const raae_net_layout& el = NL(c, kE);
   const int lE = el.n_linear - 1;
   const int K = c.p->cfg.n_aux, B = c.B, tid = threadIdx.x;
-  float* Ss = c.arena;                        // [chunk][kZ] styles
+  float* Ss = arena;                          // [chunk][kZ] styles
   float* Ds = Ss + kKendallChunk * kZ;        // [chunk][kZ] descriptors
   const float* zE = c.sc + c.p->sl.zE;
   float* kacc = c.sc + c.p->sl.g[0];          // [rows][16] per-row A | Bn (spill for multi-chunk batches)
@@ -648,7 +648,7 @@ __device__ __noinline__ void kendall_stage(const Ctx& c, const float* __restrict
 
 // MSE between the re-encoded latent and z_sample (mutual_info_loss functions.py:174-192)
 __device__ __noinline__ void mi_mse_stage(const Ctx& c, int want_grad) {
-  SmemFixed* sm = c.sm;
+  RAAE_SMEM();
   const raae_net_layout& el = NL(c, kE);
   const int lE = el.n_linear - 1, ns = c.p->cfg.nstyle, tid = threadIdx.x;
   const float* zE = c.sc + c.p->sl.zE;

@@ -36,8 +36,6 @@ struct Ctx {
   float* st;          // trial state block
   float* sc;          // trial scratch block
   const double* hp;   // trial hyper-parameters
-  SmemFixed* sm;
-  float* arena;       // dynamic shared memory behind SmemFixed
   int B;              // rows of the current batch
   int Breal;          // rows of z_real (cfg batch_size; trainer.py:121)
   const float* x;     // input spectra rows of the current batch / validation set
@@ -47,6 +45,15 @@ struct Ctx {
   int apply;          // apply optimizer updates
   int epoch;
 };
+
+// Shared memory is always reached through the `extern __shared__` symbol (never through a pointer stored
+// in a struct) so that the compiler emits LDS/STS with 32-bit addresses instead of generic LD/ST.
+constexpr size_t kArenaOffset = ((sizeof(SmemFixed) + 15) / 16) * 16;
+#define RAAE_SMEM()                                                            \
+  extern __shared__ __align__(16) unsigned char raae_smem_raw[];               \
+  SmemFixed* const sm = reinterpret_cast<SmemFixed*>(raae_smem_raw);           \
+  float* const arena = reinterpret_cast<float*>(raae_smem_raw + kArenaOffset); \
+  (void)arena
 
 constexpr int kArenaFloats = 51200;     // 200 KB; see the per-stage carve-ups below
 constexpr int kTile = kTM * kLD;        // 8704 floats
@@ -159,18 +166,18 @@ __device__ __forceinline__ void load_w_rows(float* __restrict__ Ws, int ld, cons
 // AdamW (torch/optim/adam.py single-tensor path)
 // ------------------------------------------------------------------------------------------
 // thread 0 only; followed by __syncthreads() at the call site
-__device__ inline void adam_prepare(const Ctx& c, int o) {
+__device__ __forceinline__ void adam_prepare(const Ctx& c, SmemFixed* sm, int o) {
   const raae_opt_layout& ol = c.p->lay.opt[o];
   double lr = (double)c.st[ol.scalar_off + 0];
   double t = (double)c.st[ol.scalar_off + 1] + 1.0;
   double b1 = c.hp[RAAE_HP_BETA1 + o], b2 = c.hp[RAAE_HP_BETA2 + o], wd = c.hp[RAAE_HP_WD + o];
   double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
-  c.sm->ad[0] = (float)(1.0 - lr * wd);
-  c.sm->ad[1] = (float)(1.0 - b1);
-  c.sm->ad[2] = (float)b2;
-  c.sm->ad[3] = (float)(1.0 - b2);
-  c.sm->ad[4] = (float)(lr / bc1);
-  c.sm->ad[5] = (float)sqrt(bc2);
+  sm->ad[0] = (float)(1.0 - lr * wd);
+  sm->ad[1] = (float)(1.0 - b1);
+  sm->ad[2] = (float)b2;
+  sm->ad[3] = (float)(1.0 - b2);
+  sm->ad[4] = (float)(lr / bc1);
+  sm->ad[5] = (float)sqrt(bc2);
 }
 
 // thread 0 only, after every parameter of the phase has been updated
@@ -180,7 +187,8 @@ __device__ inline void adam_finish(const Ctx& c, int o) {
 
 // all threads: update `n` parameters at offset `poff` of net `net` with gradient g (shared memory),
 // and/or export the gradient to the debug buffer.
-__device__ __forceinline__ void adam_apply(const Ctx& c, int o, int net, int poff, int n, const float* __restrict__ g) {
+__device__ __forceinline__ void adam_apply(const Ctx& c, const SmemFixed* sm, int o, int net, int poff, int n,
+                                           const float* __restrict__ g) {
   const raae_opt_layout& ol = c.p->lay.opt[o];
   float* dbg = c.a->debug ? c.a->dbg.grads[o] : nullptr;
   if (dbg && ol.net_off[net] >= 0)
@@ -189,8 +197,7 @@ __device__ __forceinline__ void adam_apply(const Ctx& c, int o, int net, int pof
   float* P = c.st + c.p->lay.net[net].param_off + poff;
   float* M = c.st + ol.m_off + ol.net_off[net] + poff;
   float* V = c.st + ol.v_off + ol.net_off[net] + poff;
-  const float decay = c.sm->ad[0], w1 = c.sm->ad[1], b2 = c.sm->ad[2], w2 = c.sm->ad[3], ss = c.sm->ad[4],
-              bc2s = c.sm->ad[5];
+  const float decay = sm->ad[0], w1 = sm->ad[1], b2 = sm->ad[2], w2 = sm->ad[3], ss = sm->ad[4], bc2s = sm->ad[5];
   for (int i = threadIdx.x; i < n; i += kThreads) {
     float gi = g[i];
     float pp = P[i] * decay;
@@ -212,22 +219,22 @@ struct LayerIn {
   int kind;
   const float* src;    // hidden: u_prev [rows][64]; wide: [rows][ld]; latent: [rows][kZ]
   int ld, dim, act;    // wide only
-  const float* mean;   // hidden: stats of the producing layer; latent: BN of the encoder output or null
-  const float* inv;
+  int snet, slayer;    // hidden: BN statistics sm->mean/inv[snet][slayer] of the producing layer;
+                       // latent: BN of the encoder output, or slayer < 0 for raw rows
   const float* slope;  // hidden: PReLU slopes (global) of the producing layer
   MaskSrc mask;        // hidden: dropout of the producing layer
 };
 
 // finalize BN statistics of channel c from the shifted sums; updates running buffers in train mode
-__device__ __forceinline__ void bn_finalize(const Ctx& c, int net, int l, int ch, float shift, float s1, float s2,
-                                            int nrows) {
+__device__ __forceinline__ void bn_finalize(const Ctx& c, SmemFixed* sm, int net, int l, int ch, float shift, float s1,
+                                            float s2, int nrows) {
   const raae_net_layout& nl = NL(c, net);
   float n = (float)nrows;
   float d = s1 / n;
   float mean = shift + d;
   float var = fmaxf(s2 / n - d * d, 0.f);
-  c.sm->mean[net][l][ch] = mean;
-  c.sm->inv[net][l][ch] = 1.f / sqrtf(var + kBnEps);
+  sm->mean[net][l][ch] = mean;
+  sm->inv[net][l][ch] = 1.f / sqrtf(var + kBnEps);
   float* rm = c.st + nl.rm_off[l];
   float* rv = c.st + nl.rv_off[l];
   float unb = nrows > 1 ? var * (n / (n - 1.f)) : var;
@@ -236,13 +243,13 @@ __device__ __forceinline__ void bn_finalize(const Ctx& c, int net, int l, int ch
 }
 
 __device__ __noinline__ void fwd_hidden(const Ctx& c, int net, int l, const LayerIn& in, float* __restrict__ u_out) {
-  SmemFixed* sm = c.sm;
+  RAAE_SMEM();
   const raae_net_layout& nl = NL(c, net);
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, ch = tid & 63, q = tid >> 6;
   const int K = nl.in_dim[l];
   const float* Wg = netp(c, net) + nl.w_off[l];
-  float* Ws = c.arena;                        // hidden: [64][kLD]; wide: [64][kLDW]; latent: [64][9]
-  float* At = c.arena + kH * kLDW;            // [kTM][kLD] or [kTM][kZ]
+  float* Ws = arena;                          // hidden: [64][kLD]; wide: [64][kLDW]; latent: [64][9]
+  float* At = arena + kH * kLDW;              // [kTM][kLD] or [kTM][kZ]
   float* Ot = At + kTile;                     // [kTM][kLD]
   __syncthreads();
   if (in.kind == kInLatent) {
@@ -267,7 +274,8 @@ __device__ __noinline__ void fwd_hidden(const Ctx& c, int net, int l, const Laye
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     if (in.kind == kInLatent) {
-      build_latent_tile(At, in.src, row0, nv, K, in.mean, in.inv);
+      build_latent_tile(At, in.src, row0, nv, K, in.slayer >= 0 ? sm->mean[in.snet][in.slayer] : nullptr,
+                        in.slayer >= 0 ? sm->inv[in.snet][in.slayer] : nullptr);
       __syncthreads();
       for (int i = 0; i < kTM / 4; ++i) {
         int r = q + 4 * i;
@@ -283,7 +291,7 @@ __device__ __noinline__ void fwd_hidden(const Ctx& c, int net, int l, const Laye
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
       if (in.kind == kInHidden) {
-        build_act_tile(At, in.src, row0, nv, in.mean, in.inv, in.slope, in.mask);
+        build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
         __syncthreads();
         mma_nt<kH>(At, kLD, Ws, kLD, acc, ty, tx);
       } else {
@@ -333,15 +341,14 @@ __device__ __noinline__ void fwd_hidden(const Ctx& c, int net, int l, const Laye
     if (q == 0) {
       float a1 = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
       float a2 = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
-      bn_finalize(c, net, l, ch, sm->shift[ch], a1, a2, c.B);
+      bn_finalize(c, sm, net, l, ch, sm->shift[ch], a1, a2, c.B);
     }
   }
   __syncthreads();
 }
 
 // statistics of nstyle columns of a [rows][kZ] panel (two-pass); results in sm->zs[0] (mean), zs[1] (biased var)
-__device__ __forceinline__ void latent_colstats(const Ctx& c, const float* __restrict__ z, int nrows) {
-  SmemFixed* sm = c.sm;
+__device__ __forceinline__ void latent_colstats(SmemFixed* sm, const float* __restrict__ z, int nrows) {
   const int tid = threadIdx.x, k = tid & 7, g = tid >> 3;
   float s = 0.f;
   for (int r = g; r < nrows; r += 32) s += z[(size_t)r * kZ + k];
@@ -372,12 +379,12 @@ __device__ __forceinline__ void latent_colstats(const Ctx& c, const float* __res
 // last encoder Linear (64 -> nstyle) + BatchNorm1d(nstyle).  zE receives the PRE-BN output; the BN
 // statistics go to sm->mean/inv[kE][L-1][0..nstyle).
 __device__ __noinline__ void fwd_enc_last(const Ctx& c, const LayerIn& in) {
-  SmemFixed* sm = c.sm;
+  RAAE_SMEM();
   const raae_net_layout& nl = NL(c, kE);
   const int L = nl.n_linear, l = L - 1, ns = nl.out_dim[l];
   const int tid = threadIdx.x;
-  float* Ws = c.arena;                 // [kZ][kLD]
-  float* At = c.arena + kH * kLDW;     // [kTM][kLD]
+  float* Ws = arena;                   // [kZ][kLD]
+  float* At = arena + kH * kLDW;       // [kTM][kLD]
   float* zE = c.sc + c.p->sl.zE;
   __syncthreads();
   for (int o = tid; o < kZ * kH; o += kThreads) {
@@ -389,7 +396,7 @@ __device__ __noinline__ void fwd_enc_last(const Ctx& c, const LayerIn& in) {
   const int ntiles = (c.B + kTM - 1) / kTM;
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
-    build_act_tile(At, in.src, row0, nv, in.mean, in.inv, in.slope, in.mask);
+    build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
     __syncthreads();
     for (int o = tid; o < kTM * kZ; o += kThreads) {
       int r = o >> 3, n = o & 7;
@@ -408,7 +415,7 @@ __device__ __noinline__ void fwd_enc_last(const Ctx& c, const LayerIn& in) {
   }
   if (c.train) {
     __threadfence_block();
-    latent_colstats(c, zE, c.B);
+    latent_colstats(sm, zE, c.B);
     if (tid < ns) {
       float mean = sm->zs[0][tid], var = sm->zs[1][tid], n = (float)c.B;
       sm->mean[kE][l][tid] = mean;
@@ -433,8 +440,7 @@ __device__ __forceinline__ LayerIn hidden_out(const Ctx& c, int net, int l, int 
   in.kind = kInHidden;
   in.src = c.sc + (net == kE ? c.p->sl.uE[l] : c.p->sl.uD[l]);
   in.ld = kH; in.dim = kH; in.act = 0;
-  in.mean = c.sm->mean[net][l];
-  in.inv = c.sm->inv[net][l];
+  in.snet = net; in.slayer = l;
   in.slope = netp(c, net) + NL(c, net).a_off[l];
   in.mask = make_mask(c, net, inst, l);
   return in;
@@ -443,15 +449,16 @@ __device__ __forceinline__ LayerIn hidden_out(const Ctx& c, int net, int l, int 
 __device__ __forceinline__ LayerIn wide_in(const float* src, int ld, int dim, int act) {
   LayerIn in;
   in.kind = kInWide; in.src = src; in.ld = ld; in.dim = dim; in.act = act;
-  in.mean = nullptr; in.inv = nullptr; in.slope = nullptr;
+  in.snet = 0; in.slayer = -1; in.slope = nullptr;
   in.mask.ptr = nullptr; in.mask.key = 0; in.mask.thresh = 0; in.mask.scale = 1.f;
   return in;
 }
 
-__device__ __forceinline__ LayerIn latent_in(const float* src, int nstyle, const float* mean, const float* inv) {
+// bn_layer >= 0: rows are the pre-BN encoder output, normalised with sm->mean/inv[kE][bn_layer]
+__device__ __forceinline__ LayerIn latent_in(const float* src, int nstyle, int bn_layer) {
   LayerIn in;
   in.kind = kInLatent; in.src = src; in.ld = kZ; in.dim = nstyle; in.act = 0;
-  in.mean = mean; in.inv = inv; in.slope = nullptr;
+  in.snet = kE; in.slayer = bn_layer; in.slope = nullptr;
   in.mask.ptr = nullptr; in.mask.key = 0; in.mask.thresh = 0; in.mask.scale = 1.f;
   return in;
 }
@@ -487,14 +494,14 @@ __device__ __forceinline__ void decoder_forward_hidden(const Ctx& c, const Layer
 //   in.kind == kInLatent : input latent rows;                        dz_out (optional) [rows][kZ]
 __device__ __noinline__ void bwd_hidden(const Ctx& c, int net, int l, const LayerIn& in, const float* __restrict__ u_l,
                                         const float* __restrict__ g_in, float* g_out, int o) {
-  SmemFixed* sm = c.sm;
+  RAAE_SMEM();
   const raae_net_layout& nl = NL(c, net);
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int K = nl.in_dim[l];
   const float* Wg = netp(c, net) + nl.w_off[l];
   // arena: [Dt kTile][At: kTile | wide kWideTile][Ws kWTile (hidden NN operand / wide chunk / latent [64][9])]
-  float* Dt = c.arena;
-  float* At = c.arena + kTile;
+  float* Dt = arena;
+  float* At = arena + kTile;
   float* Ws = At + (in.kind == kInWide ? kWideTile : kTile);
   float* gradW = At;                          // reused after the tile loop: dense [64][K]
   const bool want_out = g_out != nullptr;
@@ -550,9 +557,10 @@ __device__ __noinline__ void bwd_hidden(const Ctx& c, int net, int l, const Laye
       *reinterpret_cast<float4*>(Dt + r * kLD + c4) = du;
     }
     // 2. the layer's input activations
-    if (in.kind == kInHidden) build_act_tile(At, in.src, row0, nv, in.mean, in.inv, in.slope, in.mask);
+    if (in.kind == kInHidden) build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
     else if (in.kind == kInWide) build_wide_tile(At, in.src, in.ld, in.dim, row0, nv, in.act);
-    else build_latent_tile(At, in.src, row0, nv, K, in.mean, in.inv);
+    else build_latent_tile(At, in.src, row0, nv, K, in.slayer >= 0 ? sm->mean[in.snet][in.slayer] : nullptr,
+                        in.slayer >= 0 ? sm->inv[in.snet][in.slayer] : nullptr);
     __syncthreads();
     // 3. dW += du^T a
     if (in.kind == kInHidden) {
@@ -691,9 +699,9 @@ __device__ __noinline__ void bwd_hidden(const Ctx& c, int net, int l, const Laye
     }
     __syncthreads();
   }
-  adam_apply(c, o, net, nl.w_off[l], kH * K, gradW);
-  adam_apply(c, o, net, nl.b_off[l], kH, gb);
-  adam_apply(c, o, net, nl.a_off[l], kH, gb + kH);
+  adam_apply(c, sm, o, net, nl.w_off[l], kH * K, gradW);
+  adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
+  adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
   __syncthreads();
 }
 
@@ -701,13 +709,13 @@ __device__ __noinline__ void bwd_hidden(const Ctx& c, int net, int l, const Laye
 // last encoder layer backward: BN(nstyle) -> Linear(64, nstyle); input gradient for hidden layer L-2
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void bwd_enc_last(const Ctx& c, const LayerIn& in, float* __restrict__ g_out, int o) {
-  SmemFixed* sm = c.sm;
+  RAAE_SMEM();
   const raae_net_layout& nl = NL(c, kE);
   const int L = nl.n_linear, l = L - 1, ns = nl.out_dim[l];
   const int tid = threadIdx.x, ch = tid & 63, q = tid >> 6;
   const float* zE = c.sc + c.p->sl.zE;
   const float* dz = c.sc + c.p->sl.dz;
-  float* Ws = c.arena;                 // [kZ][kLD]
+  float* Ws = arena;                   // [kZ][kLD]
   float* At = Ws + kZ * kLD;           // [kTM][kLD]
   float* D5 = At + kTile;              // [kTM][kZ]
   float* gradW = D5 + kTM * kZ;        // [kZ][64] + [kZ]
@@ -744,7 +752,7 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c, const LayerIn& in, float
   const int ntiles = (c.B + kTM - 1) / kTM;
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
-    build_act_tile(At, in.src, row0, nv, in.mean, in.inv, in.slope, in.mask);
+    build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
     for (int i = tid; i < kTM * kZ; i += kThreads) {
       int r = i >> 3, k = i & 7;
       float v = 0.f;
@@ -796,8 +804,8 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c, const LayerIn& in, float
     sm->sg[ch] = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
     sm->sgx[ch] = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
   }
-  adam_apply(c, o, kE, nl.w_off[l], ns * kH, gradW);
-  adam_apply(c, o, kE, nl.b_off[l], ns, gradW + kZ * kH);
+  adam_apply(c, sm, o, kE, nl.w_off[l], ns * kH, gradW);
+  adam_apply(c, sm, o, kE, nl.b_off[l], ns, gradW + kZ * kH);
   __syncthreads();
 }
 
