@@ -187,6 +187,10 @@ int raae_train_epochs(raae_handle* h, int epoch_begin, int n_epochs, const int32
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 int64_t raae_launch_count(const raae_handle* h);
 
+/* Optional instrumentation: int64 [n_trials][32] device buffer; raae_train_epochs ADDS the SM cycles each trial's
+ * CTA spent per stage type (slot 15 = whole kernel; slots documented in csrc/aae_step.cuh StageId).  NULL disables. */
+int raae_set_profile_buffer(raae_handle* h, long long* prof);
+
 #ifdef __cplusplus
 }
 #endif

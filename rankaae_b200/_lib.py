@@ -66,7 +66,7 @@ class ValIO(C.Structure):
 
 EXPORTS = ("raae_last_error", "raae_version", "raae_query_layout", "raae_create", "raae_destroy", "raae_bind_state",
            "raae_bind_dataset", "raae_bind_shapiro_weights", "raae_reset_optimizers", "raae_step_debug",
-           "raae_validate", "raae_train_epochs", "raae_launch_count")
+           "raae_validate", "raae_train_epochs", "raae_launch_count", "raae_set_profile_buffer")
 
 _lib = None
 
@@ -98,6 +98,7 @@ def load():
     lib.raae_train_epochs.argtypes = [_p, C.c_int, C.c_int, _p, _p, _p, _p]
     lib.raae_launch_count.argtypes = [_p]
     lib.raae_launch_count.restype = C.c_int64
+    lib.raae_set_profile_buffer.argtypes = [_p, _p]
     _lib = lib
     return lib
 

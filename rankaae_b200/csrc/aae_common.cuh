@@ -64,6 +64,7 @@ struct RunArgs {
   const int32_t* perm;          // [n_trials][n_train] shuffled row order of this epoch (production)
   float* out_losses;            // [n_trials][12] (production, may be null)
   float* out_metrics;           // [n_trials][6]
+  long long* prof;              // optional [n_trials][32] stage cycle counters (raae_set_profile_buffer)
   raae_debug_io dbg;
   raae_val_io val;
 };
@@ -101,17 +102,20 @@ __device__ __forceinline__ float normal_at(uint32_t key, uint32_t idx) {
 struct MaskSrc {
   const uint8_t* ptr;   // explicit keep-mask [rows][64] or null
   uint32_t key;
-  uint32_t thresh;      // drop when the 16-bit draw < thresh; 0 = keep everything
+  uint32_t thresh;      // drop when the 16-bit draw < thresh = round(p * 65536); 0 = keep everything
   float scale;          // 1 / (1 - p)
 };
 
+// Branch-free Bernoulli draws: one mixer round per PAIR of channels, 16 bits each; a channel is dropped when its
+// draw < thresh = round(p * 65536).
+__device__ __forceinline__ uint32_t mask_word(uint32_t key, uint32_t pair) { return mix32(pair * 0x9e3779b1U + key); }
+
 __device__ __forceinline__ bool mask_keep(const MaskSrc& m, int row, int c) {
   if (m.ptr) return m.ptr[row * kH + c] != 0;
-  if (m.thresh == 0u) return true;
   uint32_t idx = (uint32_t)(row * kH + c);
-  uint32_t h = hash2(m.key, idx >> 1);
-  uint32_t d = (idx & 1u) ? (h >> 16) : (h & 0xffffu);
-  return d >= m.thresh;
+  uint32_t w = mask_word(m.key, idx >> 1);
+  uint32_t d = (idx & 1u) ? (w >> 16) : (w & 0xffffu);
+  return d >= m.thresh;          // thresh == 0 keeps everything
 }
 
 // four consecutive channels c..c+3 (c % 4 == 0): returns keep bits
@@ -121,10 +125,10 @@ __device__ __forceinline__ uint32_t mask_keep4(const MaskSrc& m, int row, int c)
     return ((w & 0xffu) ? 1u : 0u) | ((w & 0xff00u) ? 2u : 0u) | ((w & 0xff0000u) ? 4u : 0u) | ((w & 0xff000000u) ? 8u : 0u);
   }
   if (m.thresh == 0u) return 0xfu;
-  uint32_t idx = (uint32_t)(row * kH + c);
-  uint32_t h0 = hash2(m.key, idx >> 1), h1 = hash2(m.key, (idx >> 1) + 1u);
-  return ((h0 & 0xffffu) >= m.thresh ? 1u : 0u) | ((h0 >> 16) >= m.thresh ? 2u : 0u) |
-         ((h1 & 0xffffu) >= m.thresh ? 4u : 0u) | ((h1 >> 16) >= m.thresh ? 8u : 0u);
+  uint32_t pair = (uint32_t)(row * kH + c) >> 1;
+  uint32_t w0 = mask_word(m.key, pair), w1 = mask_word(m.key, pair + 1u);
+  return ((w0 & 0xffffu) >= m.thresh ? 1u : 0u) | ((w0 >> 16) >= m.thresh ? 2u : 0u) |
+         ((w1 & 0xffffu) >= m.thresh ? 4u : 0u) | ((w1 >> 16) >= m.thresh ? 8u : 0u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -132,12 +136,17 @@ __device__ __forceinline__ uint32_t mask_keep4(const MaskSrc& m, int row, int c)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float prelu_f(float u, float a) { return u > 0.f ? u : a * u; }
 
-// nn.Softplus(beta=2, threshold=20): model.py:535
+// nn.Softplus(beta=2, threshold=20): model.py:535.  softplus(x) = max(x, 0) + log1p(exp(-|x|)) keeps the
+// argument of the logarithm in (1, 2], where the hardware exp/log pair is accurate to ~1e-7 absolute.
 __device__ __forceinline__ float softplus2_f(float v) {
   float bv = 2.f * v;
-  return bv > 20.f ? v : 0.5f * log1pf(expf(bv));
+  return bv > 20.f ? v : 0.5f * (fmaxf(bv, 0.f) + __logf(1.f + __expf(-fabsf(bv))));
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) {
+  float e = __expf(-fabsf(x));
+  float s = __fdividef(1.f, 1.f + e);
+  return x >= 0.f ? s : e * s;
+}
 __device__ __forceinline__ float softplus2_grad_f(float v) {
   float bv = 2.f * v;
   return bv > 20.f ? 1.f : sigmoid_f(bv);
@@ -216,6 +225,28 @@ __device__ __forceinline__ void mma_tn8(const float* __restrict__ A, int lda, in
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// asynchronous global -> shared copies (LDGSTS): tile prefetch that needs no registers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// rows [row0, row0 + nv) of a row-major [rows][64] panel -> raw smem tile [kTM][kLD]; every thread copies the SAME
+// elements it later transforms in place (c4 = 4 (tid & 15), rows (tid >> 4) + 16 i), so no barrier is needed in between
+__device__ __forceinline__ void prefetch_panel_tile(float* __restrict__ dst, const float* __restrict__ panel, int row0, int nv) {
+  const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < kTM / 16; ++i) {
+    const int r = r0 + 16 * i;
+    if (r < nv) cp_async16(dst + r * kLD + c4, panel + (size_t)(row0 + r) * kH + c4);
   }
 }
 

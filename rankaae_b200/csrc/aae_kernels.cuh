@@ -20,6 +20,8 @@ __device__ __noinline__ void build_batch(const Ctx& c, const int32_t* __restrict
   float* xn = c.sc + p.sl.xn;
   float* aux = c.sc + p.sl.aux;
   float* zs = c.sc + p.sl.zs;
+  RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStBatch]);
   __syncthreads();
   if (c.a->debug) {
     const raae_debug_io& d = c.a->dbg;
@@ -180,9 +182,12 @@ constexpr size_t kSmemBytes = kArenaOffset + (size_t)kArenaFloats * sizeof(float
 
 __global__ void __launch_bounds__(kThreads, 1)
 raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunArgs a) {
+  RAAE_SMEM();
   const int trial = a.trial0 + blockIdx.x;
   Ctx c;
   init_ctx(c, p, a, trial);
+  if (threadIdx.x < 32) sm->prof[threadIdx.x] = 0;
+  const long long t_start = clock64();
   if (a.debug) {
     c.B = a.dbg.rows;
     c.epoch = a.dbg.epoch;
@@ -200,6 +205,11 @@ raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ Run
     c.step_id = (uint32_t)(a.epoch * a.n_steps + s);
     build_batch(c, perm + s * bs);
     train_step(c, 0x1f);
+  }
+  if (a.prof && threadIdx.x == 0) {      // [n_trials][32]: per-stage-type SM cycles, slot 15 = whole kernel, 16.. = probes
+    for (int i = 0; i < 15; ++i) a.prof[(size_t)trial * 32 + i] += sm->prof[i];
+    a.prof[(size_t)trial * 32 + 15] += clock64() - t_start;
+    for (int i = 16; i < 32; ++i) a.prof[(size_t)trial * 32 + i] += sm->prof[i];
   }
 }
 

@@ -18,6 +18,7 @@ enum LastMode { kLastRecon = 0, kLastSmooth = 1, kLastStoreV = 2, kLastFromDv = 
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
   RAAE_SMEM();
+  StageTimer timer_(&sm->prof[mode == kLastStoreV ? kStDecLastStoreV : mode == kLastFromDv ? kStDecLastFromDv : kStDecLastLoss]);
   const raae_net_layout& nl = NL(c, kD);
   const int L = nl.n_linear, l = L - 1, N = nl.out_dim[l];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, lane = tid & 31, warp = tid >> 5;
@@ -135,15 +136,24 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
           if (lane < 8) { ypad[lane] = ypad[8]; ypad[8 + N + lane] = ypad[8 + N - 1]; }
           __syncwarp();
           float ee[8], sq = 0.f;
+          {
+            // sliding window in registers: ypad[col0 .. col0 + 24)
+            float win[24];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            ee[e] = 0.f;
-            if (col0 + e < N) {
-              float s = 0.f;
+            for (int q4 = 0; q4 < 6; ++q4) {
+              float4 t4 = *reinterpret_cast<const float4*>(ypad + col0 + 4 * q4);
+              win[4 * q4] = t4.x; win[4 * q4 + 1] = t4.y; win[4 * q4 + 2] = t4.z; win[4 * q4 + 3] = t4.w;
+            }
 #pragma unroll
-              for (int k = 0; k < 17; ++k) s = fmaf(kGauss17[k], ypad[col0 + e + k], s);
-              ee[e] = y[e] - s;
-              sq = fmaf(ee[e], ee[e], sq);
+            for (int e = 0; e < 8; ++e) {
+              ee[e] = 0.f;
+              if (col0 + e < N) {
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < 17; ++k) s = fmaf(kGauss17[k], win[e + k], s);
+                ee[e] = y[e] - s;
+                sq = fmaf(ee[e], ee[e], sq);
+              }
             }
           }
           loss_b += (double)sq / ((double)nB * (double)nN);
@@ -154,25 +164,33 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
             for (int e = 0; e < 8; ++e)
               if (col0 + e < N) ezp[16 + col0 + e] = ee[e];
             __syncwarp();
+            {
+              // (K^T e)[j + 8] = sum_t w[t] e[j + 8 - t] = sum_m w[m] ezp[j + 8 + m]  (taps symmetric, ezp[16 + i] = e[i])
+              float win[24];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int j = col0 + e;
-              if (j < N) {
-                // (K^T e)[i] = sum_t w[t] e[i - t], padded index i = j + 8
-                float kt = 0.f;
+              for (int q4 = 0; q4 < 6; ++q4) {
+                float4 t4 = *reinterpret_cast<const float4*>(ezp + col0 + 8 + 4 * q4);
+                win[4 * q4] = t4.x; win[4 * q4 + 1] = t4.y; win[4 * q4 + 2] = t4.z; win[4 * q4 + 3] = t4.w;
+              }
 #pragma unroll
-                for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], ezp[16 + j + 8 - k], kt);
-                if (j == 0) {
-                  for (int i = 0; i < 8; ++i)
+              for (int e = 0; e < 8; ++e) {
+                const int j = col0 + e;
+                if (j < N) {
+                  float kt = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], ezp[16 + i - k], kt);
+                  for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], win[e + k], kt);
+                  if (j == 0) {            // overhang of the left replicate padding folds into y[0]
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                      for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], ezp[16 + i - k], kt);
+                  }
+                  if (j == N - 1) {        // right overhang folds into y[N-1]
+                    for (int i = N + 8; i < N + 16; ++i)
+#pragma unroll
+                      for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], ezp[16 + i - k], kt);
+                  }
+                  dy[e] = (2.f / (nB * nN)) * (ee[e] - kt);
                 }
-                if (j == N - 1) {
-                  for (int i = N + 8; i < N + 16; ++i)
-#pragma unroll
-                    for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], ezp[16 + i - k], kt);
-                }
-                dy[e] = (2.f / (nB * nN)) * (ee[e] - kt);
               }
             }
           }
@@ -267,6 +285,7 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void dis_stage(const Ctx& c, int backward, int o, const float* z_real_ptr, uint32_t key_zreal) {
   RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStDis]);
   const raae_net_layout& nl = NL(c, kS);
   const raae_net_layout& el = NL(c, kE);
   const int ns = nl.in_dim[0];
@@ -548,6 +567,7 @@ constexpr int kKendallChunk = 2048;
 
 __device__ __noinline__ void kendall_stage(const Ctx& c, const float* __restrict__ aux, int want_grad) {
   RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStKendall]);
   const raae_net_layout& el = NL(c, kE);
   const int lE = el.n_linear - 1;
   const int K = c.p->cfg.n_aux, B = c.B, tid = threadIdx.x;
@@ -595,6 +615,7 @@ __device__ __noinline__ void kendall_stage(const Ctx& c, const float* __restrict
         const float dj[kZ] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
         for (int k = 0; k < kZ; ++k) {
+          if (k >= K) break;
           float dd = di[k] - dj[k];
           float tt = dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f);
           float p = (si[k] - sj[k]) * tt;
@@ -649,6 +670,7 @@ __device__ __noinline__ void kendall_stage(const Ctx& c, const float* __restrict
 // MSE between the re-encoded latent and z_sample (mutual_info_loss functions.py:174-192)
 __device__ __noinline__ void mi_mse_stage(const Ctx& c, int want_grad) {
   RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStMiMse]);
   const raae_net_layout& el = NL(c, kE);
   const int lE = el.n_linear - 1, ns = c.p->cfg.nstyle, tid = threadIdx.x;
   const float* zE = c.sc + c.p->sl.zE;

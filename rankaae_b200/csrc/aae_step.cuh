@@ -28,6 +28,18 @@ struct SmemFixed {
   int kcount[2][kZ];
   float kw[kZ];
   float alpha;
+  long long prof[32];                   // per-stage-type cycle counters (thread 0), see StageId; 16.. = sub-stage probes
+};
+
+enum StageId { kStBatch = 0, kStFwdWide, kStFwdHidden, kStFwdLatent, kStFwdEncLast, kStBwdWide, kStBwdHidden, kStBwdLatent,
+               kStBwdEncLast, kStDecLastLoss, kStDecLastStoreV, kStDecLastFromDv, kStDis, kStKendall, kStMiMse, kStCount };
+
+// scoped cycle counter: thread 0 adds the elapsed SM cycles of the enclosing stage to sm->prof[id]
+struct StageTimer {
+  long long t0;
+  long long* slot;
+  __device__ __forceinline__ StageTimer(long long* s) : slot(s) { if (threadIdx.x == 0) t0 = clock64(); }
+  __device__ __forceinline__ ~StageTimer() { if (threadIdx.x == 0) *slot += clock64() - t0; }
 };
 
 struct Ctx {
@@ -88,14 +100,44 @@ __device__ inline MaskSrc make_mask(const Ctx& c, int net, int inst, int layer) 
 __device__ __forceinline__ void build_act_tile(float* __restrict__ At, const float* __restrict__ u, int row0, int nv,
                                                const float* mean, const float* inv, const float* __restrict__ slope_g,
                                                const MaskSrc& mk) {
-  const int c4 = (threadIdx.x & 15) * 4;
+  const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;
   const float4 mu = *reinterpret_cast<const float4*>(mean + c4);
   const float4 is = *reinterpret_cast<const float4*>(inv + c4);
   const float4 sl = *reinterpret_cast<const float4*>(slope_g + c4);
-  for (int r = threadIdx.x >> 4; r < kTM; r += 16) {
+  float4 uu[kTM / 16];
+#pragma unroll
+  for (int i = 0; i < kTM / 16; ++i) {       // all loads in flight before the first use
+    const int r = r0 + 16 * i;
+    uu[i] = r < nv ? *reinterpret_cast<const float4*>(u + (size_t)(row0 + r) * kH + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < kTM / 16; ++i) {
+    const int r = r0 + 16 * i;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < nv) {
-      float4 uu = *reinterpret_cast<const float4*>(u + (size_t)(row0 + r) * kH + c4);
+      uint32_t kb = mask_keep4(mk, row0 + r, c4);
+      o.x = (kb & 1u) ? (prelu_f(uu[i].x, sl.x) - mu.x) * is.x * mk.scale : 0.f;
+      o.y = (kb & 2u) ? (prelu_f(uu[i].y, sl.y) - mu.y) * is.y * mk.scale : 0.f;
+      o.z = (kb & 4u) ? (prelu_f(uu[i].z, sl.z) - mu.z) * is.z * mk.scale : 0.f;
+      o.w = (kb & 8u) ? (prelu_f(uu[i].w, sl.w) - mu.w) * is.w * mk.scale : 0.f;
+    }
+    *reinterpret_cast<float4*>(At + r * kLD + c4) = o;
+  }
+}
+
+// same transform applied IN PLACE to a raw tile prefetched by prefetch_panel_tile (own elements only)
+__device__ __forceinline__ void transform_act_tile(float* __restrict__ At, int row0, int nv, const float* mean,
+                                                   const float* inv, const float* __restrict__ slope_s, const MaskSrc& mk) {
+  const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c4);
+  const float4 is = *reinterpret_cast<const float4*>(inv + c4);
+  const float4 sl = *reinterpret_cast<const float4*>(slope_s + c4);
+#pragma unroll
+  for (int i = 0; i < kTM / 16; ++i) {
+    const int r = r0 + 16 * i;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nv) {
+      const float4 uu = *reinterpret_cast<const float4*>(At + r * kLD + c4);
       uint32_t kb = mask_keep4(mk, row0 + r, c4);
       o.x = (kb & 1u) ? (prelu_f(uu.x, sl.x) - mu.x) * is.x * mk.scale : 0.f;
       o.y = (kb & 2u) ? (prelu_f(uu.y, sl.y) - mu.y) * is.y * mk.scale : 0.f;
@@ -109,11 +151,19 @@ __device__ __forceinline__ void build_act_tile(float* __restrict__ At, const flo
 // columns [k0, k0 + 64) of wide rows -> [kTM][kLD]; optional decoder activation on load
 __device__ __forceinline__ void build_wide_chunk(float* __restrict__ At, const float* __restrict__ src, int ld, int dim,
                                                  int k0, int row0, int nv, int act /*0 none 1 softplus 2 relu*/) {
-  const int c4 = (threadIdx.x & 15) * 4;
-  for (int r = threadIdx.x >> 4; r < kTM; r += 16) {
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;
+  float4 v[kTM / 16];
+#pragma unroll
+  for (int i = 0; i < kTM / 16; ++i) {
+    const int r = r0 + 16 * i;
+    v[i] = (r < nv && k0 + c4 < dim) ? *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + k0 + c4)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < kTM / 16; ++i) {
+    const int r = r0 + 16 * i;
+    float4 o = v[i];
     if (r < nv && k0 + c4 < dim) {
-      o = *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + k0 + c4);
       if (act == 1) { o.x = softplus2_f(o.x); o.y = softplus2_f(o.y); o.z = softplus2_f(o.z); o.w = softplus2_f(o.w); }
       else if (act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     }
@@ -124,15 +174,25 @@ __device__ __forceinline__ void build_wide_chunk(float* __restrict__ At, const f
 // whole wide rows -> [kTM][kLDW]
 __device__ __forceinline__ void build_wide_tile(float* __restrict__ Xt, const float* __restrict__ src, int ld, int dim,
                                                 int row0, int nv, int act) {
-  const int c4 = (threadIdx.x & 63) * 4;
-  for (int r = threadIdx.x >> 6; r < kTM; r += 4) {
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < nv && c4 < dim) {
-      o = *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + c4);
-      if (act == 1) { o.x = softplus2_f(o.x); o.y = softplus2_f(o.y); o.z = softplus2_f(o.z); o.w = softplus2_f(o.w); }
-      else if (act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+  const int c4 = (threadIdx.x & 63) * 4, r0 = threadIdx.x >> 6;
+  for (int b = 0; b < kTM / 4; b += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + 4 * (b + i);
+      v[i] = (r < nv && c4 < dim) ? *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + c4)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    *reinterpret_cast<float4*>(Xt + r * kLDW + c4) = o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + 4 * (b + i);
+      float4 o = v[i];
+      if (r < nv && c4 < dim) {
+        if (act == 1) { o.x = softplus2_f(o.x); o.y = softplus2_f(o.y); o.z = softplus2_f(o.z); o.w = softplus2_f(o.w); }
+        else if (act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      }
+      *reinterpret_cast<float4*>(Xt + r * kLDW + c4) = o;
+    }
   }
 }
 
@@ -242,8 +302,9 @@ __device__ __forceinline__ void bn_finalize(const Ctx& c, SmemFixed* sm, int net
   rv[ch] = (1.f - kBnMomentum) * rv[ch] + kBnMomentum * unb;
 }
 
-__device__ __noinline__ void fwd_hidden(const Ctx& c, int net, int l, const LayerIn& in, float* __restrict__ u_out) {
+__device__ __noinline__ void fwd_hidden_edge(const Ctx& c, int net, int l, const LayerIn& in, float* __restrict__ u_out) {
   RAAE_SMEM();
+  StageTimer timer_(&sm->prof[in.kind == kInWide ? kStFwdWide : in.kind == kInHidden ? kStFwdHidden : kStFwdLatent]);
   const raae_net_layout& nl = NL(c, net);
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, ch = tid & 63, q = tid >> 6;
   const int K = nl.in_dim[l];
@@ -269,7 +330,7 @@ __device__ __noinline__ void fwd_hidden(const Ctx& c, int net, int l, const Laye
     }
   }
   __syncthreads();
-  float s1 = 0.f, s2 = 0.f;
+  float4 s1v = make_float4(0.f, 0.f, 0.f, 0.f), s2v = make_float4(0.f, 0.f, 0.f, 0.f);
   const int ntiles = (c.B + kTM - 1) / kTM;
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
@@ -291,9 +352,14 @@ __device__ __noinline__ void fwd_hidden(const Ctx& c, int net, int l, const Laye
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
       if (in.kind == kInHidden) {
+        long long p0 = clock64();
         build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
+        long long p1 = clock64();
         __syncthreads();
+        long long p2 = clock64();
         mma_nt<kH>(At, kLD, Ws, kLD, acc, ty, tx);
+        long long p3 = clock64();
+        if (tid == 0) { sm->prof[16] += p1 - p0; sm->prof[17] += p2 - p1; sm->prof[18] += p3 - p2; }
       } else {
         for (int k0 = 0; k0 < K; k0 += kH) {
           build_wide_chunk(At, in.src, in.ld, in.dim, k0, row0, nv, in.act);
@@ -307,41 +373,175 @@ __device__ __noinline__ void fwd_hidden(const Ctx& c, int net, int l, const Laye
 #pragma unroll
         for (int j = 0; j < 4; ++j) Ot[(ty + 16 * i) * kLD + tx + 16 * j] = acc[i][j] + sm->bias[tx + 16 * j];
     }
+    long long p4 = clock64();
     __syncthreads();
-    // elementwise epilogue: thread (ch, q) owns channel ch of rows q, q+4, ...
-    const float a_sl = sm->slope[ch];
+    long long p5 = clock64();
+    // elementwise epilogue: thread (ty, tx) owns channels 4tx..4tx+3 of rows ty, ty+16, ...
+    const int c4 = tx * 4;
+    const float4 a_sl = *reinterpret_cast<const float4*>(sm->slope + c4);
+    float4 uo[kTM / 16];
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) uo[i] = *reinterpret_cast<const float4*>(Ot + (ty + 16 * i) * kLD + c4);
     if (c.train && t == 0) {
-      float s = 0.f;
-      for (int i = 0; i < kTM / 4; ++i) {
-        int r = q + 4 * i;
-        if (r < nv) s += prelu_f(Ot[r * kLD + ch], a_sl);
-      }
-      sm->red[q][ch] = s;
+      float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < kTM / 16; ++i)
+        if (ty + 16 * i < nv) {
+          sp.x += prelu_f(uo[i].x, a_sl.x); sp.y += prelu_f(uo[i].y, a_sl.y);
+          sp.z += prelu_f(uo[i].z, a_sl.z); sp.w += prelu_f(uo[i].w, a_sl.w);
+        }
+      *reinterpret_cast<float4*>(&sm->red[ty][c4]) = sp;
       __syncthreads();
-      if (q == 0) sm->shift[ch] = (sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch]) / (float)nv;
+      if (tid < kH) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sacc += sm->red[i][tid];
+        sm->shift[tid] = sacc / (float)nv;
+      }
       __syncthreads();
     }
-    const float sh = c.train ? sm->shift[ch] : 0.f;
-    for (int i = 0; i < kTM / 4; ++i) {
-      int r = q + 4 * i;
+    const float4 sh = c.train ? *reinterpret_cast<const float4*>(sm->shift + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
       if (r < nv) {
-        float u = Ot[r * kLD + ch];
-        u_out[(size_t)(row0 + r) * kH + ch] = u;
-        float d = prelu_f(u, a_sl) - sh;
-        s1 += d;
-        s2 = fmaf(d, d, s2);
+        *reinterpret_cast<float4*>(u_out + (size_t)(row0 + r) * kH + c4) = uo[i];
+        float d;
+        d = prelu_f(uo[i].x, a_sl.x) - sh.x; s1v.x += d; s2v.x = fmaf(d, d, s2v.x);
+        d = prelu_f(uo[i].y, a_sl.y) - sh.y; s1v.y += d; s2v.y = fmaf(d, d, s2v.y);
+        d = prelu_f(uo[i].z, a_sl.z) - sh.z; s1v.z += d; s2v.z = fmaf(d, d, s2v.z);
+        d = prelu_f(uo[i].w, a_sl.w) - sh.w; s1v.w += d; s2v.w = fmaf(d, d, s2v.w);
       }
     }
+    long long p6 = clock64();
     __syncthreads();
+    if (tid == 0 && in.kind == kInHidden) { sm->prof[19] += p5 - p4; sm->prof[20] += p6 - p5; sm->prof[21] += clock64() - p6; }
   }
   if (c.train) {
-    sm->red[q][ch] = s1;
-    sm->red[4 + q][ch] = s2;
+    const int c4 = tx * 4;
+    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s1v;
     __syncthreads();
-    if (q == 0) {
-      float a1 = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
-      float a2 = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
-      bn_finalize(c, sm, net, l, ch, sm->shift[ch], a1, a2, c.B);
+    float a1 = 0.f, a2 = 0.f;
+    if (tid < kH) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a1 += sm->red[i][tid];
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s2v;
+    __syncthreads();
+    if (tid < kH) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a2 += sm->red[i][tid];
+      bn_finalize(c, sm, net, l, tid, sm->shift[tid], a1, a2, c.B);
+    }
+  }
+  __syncthreads();
+}
+
+// forward of a hidden block whose input is another hidden block's panel (K = 64): the raw pre-activation tile of
+// tile t+1 is prefetched with cp.async while tile t runs its contraction and epilogue.
+__device__ __noinline__ void fwd_hidden64(const Ctx& c, int net, int l, const LayerIn& in, float* __restrict__ u_out) {
+  RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStFwdHidden]);
+  const raae_net_layout& nl = NL(c, net);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4;
+  const float* Wg = netp(c, net) + nl.w_off[l];
+  float* Ws = arena;                           // [64][kLD]
+  float* Rb[2] = {arena + kWTile, arena + kWTile + kTile};
+  float* Ot = arena + kWTile + 2 * kTile;      // [kTM][kLD]
+  float* slope_in = sm->cg;                    // PReLU slopes of the producing layer (cg is free during forwards)
+  const float* mean_in = sm->mean[in.snet][in.slayer];
+  const float* inv_in = sm->inv[in.snet][in.slayer];
+  const int ntiles = (c.B + kTM - 1) / kTM;
+  __syncthreads();
+  prefetch_panel_tile(Rb[0], in.src, 0, min(kTM, c.B));
+  cp_async_commit();
+  load_w_rows(Ws, kLD, Wg, kH, 0, kH);
+  if (tid < kH) {
+    sm->bias[tid] = netp(c, net)[nl.b_off[l] + tid];
+    sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
+    slope_in[tid] = in.slope[tid];
+    if (!c.train) {
+      sm->mean[net][l][tid] = c.st[nl.rm_off[l] + tid];
+      sm->inv[net][l][tid] = 1.f / sqrtf(c.st[nl.rv_off[l] + tid] + kBnEps);
+    }
+  }
+  __syncthreads();
+  float4 s1v = make_float4(0.f, 0.f, 0.f, 0.f), s2v = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    float* At = Rb[t & 1];
+    if (t + 1 < ntiles) prefetch_panel_tile(Rb[(t + 1) & 1], in.src, row0 + kTM, min(kTM, c.B - row0 - kTM));
+    cp_async_commit();
+    cp_async_wait<1>();
+    transform_act_tile(At, row0, nv, mean_in, inv_in, slope_in, in.mask);
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    mma_nt<kH>(At, kLD, Ws, kLD, acc, ty, tx);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Ot[(ty + 16 * i) * kLD + tx + 16 * j] = acc[i][j] + sm->bias[tx + 16 * j];
+    __syncthreads();
+    const float4 a_sl = *reinterpret_cast<const float4*>(sm->slope + c4);
+    float4 uo[kTM / 16];
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) uo[i] = *reinterpret_cast<const float4*>(Ot + (ty + 16 * i) * kLD + c4);
+    if (c.train && t == 0) {
+      float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < kTM / 16; ++i)
+        if (ty + 16 * i < nv) {
+          sp.x += prelu_f(uo[i].x, a_sl.x); sp.y += prelu_f(uo[i].y, a_sl.y);
+          sp.z += prelu_f(uo[i].z, a_sl.z); sp.w += prelu_f(uo[i].w, a_sl.w);
+        }
+      *reinterpret_cast<float4*>(&sm->red[ty][c4]) = sp;
+      __syncthreads();
+      if (tid < kH) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sacc += sm->red[i][tid];
+        sm->shift[tid] = sacc / (float)nv;
+      }
+      __syncthreads();
+    }
+    const float4 sh = c.train ? *reinterpret_cast<const float4*>(sm->shift + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      if (r < nv) {
+        *reinterpret_cast<float4*>(u_out + (size_t)(row0 + r) * kH + c4) = uo[i];
+        float d;
+        d = prelu_f(uo[i].x, a_sl.x) - sh.x; s1v.x += d; s2v.x = fmaf(d, d, s2v.x);
+        d = prelu_f(uo[i].y, a_sl.y) - sh.y; s1v.y += d; s2v.y = fmaf(d, d, s2v.y);
+        d = prelu_f(uo[i].z, a_sl.z) - sh.z; s1v.z += d; s2v.z = fmaf(d, d, s2v.z);
+        d = prelu_f(uo[i].w, a_sl.w) - sh.w; s1v.w += d; s2v.w = fmaf(d, d, s2v.w);
+      }
+    }
+    // no barrier here: the next iteration's barrier (after its transform) orders these Ot reads before the next
+    // Ot writes, and the buffer prefetched next was last read by the contraction two barriers ago
+  }
+  cp_async_wait<0>();
+  if (c.train) {
+    __syncthreads();
+    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s1v;
+    __syncthreads();
+    float a1 = 0.f, a2 = 0.f;
+    if (tid < kH) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a1 += sm->red[i][tid];
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s2v;
+    __syncthreads();
+    if (tid < kH) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a2 += sm->red[i][tid];
+      bn_finalize(c, sm, net, l, tid, sm->shift[tid], a1, a2, c.B);
     }
   }
   __syncthreads();
@@ -380,6 +580,7 @@ __device__ __forceinline__ void latent_colstats(SmemFixed* sm, const float* __re
 // statistics go to sm->mean/inv[kE][L-1][0..nstyle).
 __device__ __noinline__ void fwd_enc_last(const Ctx& c, const LayerIn& in) {
   RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStFwdEncLast]);
   const raae_net_layout& nl = NL(c, kE);
   const int L = nl.n_linear, l = L - 1, ns = nl.out_dim[l];
   const int tid = threadIdx.x;
@@ -432,6 +633,11 @@ __device__ __noinline__ void fwd_enc_last(const Ctx& c, const LayerIn& in) {
   }
   if (tid >= ns && tid < kZ) { sm->mean[kE][l][tid] = 0.f; sm->inv[kE][l][tid] = 0.f; }
   __syncthreads();
+}
+
+__device__ __forceinline__ void fwd_hidden(const Ctx& c, int net, int l, const LayerIn& in, float* __restrict__ u_out) {
+  if (in.kind == kInHidden) fwd_hidden64(c, net, l, in, u_out);
+  else fwd_hidden_edge(c, net, l, in, u_out);
 }
 
 // LayerIn describing "the activations coming out of hidden layer l of `net`, forward instance inst"
@@ -492,9 +698,10 @@ __device__ __forceinline__ void decoder_forward_hidden(const Ctx& c, const Layer
 //   in.kind == kInWide   : input rows in.src (K = dim);              dx_out (optional) [rows][ld]: receives
 //                           dL/dx * act'(v) IN PLACE of the pre-activation stored there (MI phase)
 //   in.kind == kInLatent : input latent rows;                        dz_out (optional) [rows][kZ]
-__device__ __noinline__ void bwd_hidden(const Ctx& c, int net, int l, const LayerIn& in, const float* __restrict__ u_l,
-                                        const float* __restrict__ g_in, float* g_out, int o) {
+__device__ __noinline__ void bwd_hidden_edge(const Ctx& c, int net, int l, const LayerIn& in, const float* __restrict__ u_l,
+                                             const float* __restrict__ g_in, float* g_out, int o) {
   RAAE_SMEM();
+  StageTimer timer_(&sm->prof[in.kind == kInWide ? kStBwdWide : in.kind == kInHidden ? kStBwdHidden : kStBwdLatent]);
   const raae_net_layout& nl = NL(c, net);
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int K = nl.in_dim[l];
@@ -536,25 +743,41 @@ __device__ __noinline__ void bwd_hidden(const Ctx& c, int net, int l, const Laye
   const int ntiles = (c.B + kTM - 1) / kTM;
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
-    // 1. du = PReLU'(u) * BN'(g)
-    for (int r = ty; r < kTM; r += 16) {
-      float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < nv) {
-        const float4 g = *reinterpret_cast<const float4*>(g_in + (size_t)(row0 + r) * kH + c4);
-        const float4 u = *reinterpret_cast<const float4*>(u_l + (size_t)(row0 + r) * kH + c4);
-#define RAAE_DU(comp, idx)                                                        \
-        {                                                                         \
-          float xh = (prelu_f(u.comp, sl.comp) - mu.comp) * is.comp;              \
-          float dh = (g.comp - cg.comp - xh * cgx.comp) * is.comp;                \
-          bool pos = u.comp > 0.f;                                                \
-          du.comp = pos ? dh : sl.comp * dh;                                      \
-          ds4[idx] += pos ? 0.f : u.comp * dh;                                    \
-          db4[idx] += du.comp;                                                    \
+    // 1. du = PReLU'(u) * BN'(g); loads batched 4 rows (8 float4) at a time
+#pragma unroll
+    for (int b = 0; b < kTM / 16; b += 4) {
+      float4 gg[4], uu[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = ty + 16 * (b + i);
+        if (r < nv) {
+          gg[i] = *reinterpret_cast<const float4*>(g_in + (size_t)(row0 + r) * kH + c4);
+          uu[i] = *reinterpret_cast<const float4*>(u_l + (size_t)(row0 + r) * kH + c4);
+        } else {
+          gg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          uu[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        RAAE_DU(x, 0) RAAE_DU(y, 1) RAAE_DU(z, 2) RAAE_DU(w, 3)
-#undef RAAE_DU
       }
-      *reinterpret_cast<float4*>(Dt + r * kLD + c4) = du;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = ty + 16 * (b + i);
+        float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nv) {
+          const float4 g = gg[i], u = uu[i];
+#define RAAE_DU(comp, idx)                                                        \
+          {                                                                       \
+            float xh = (prelu_f(u.comp, sl.comp) - mu.comp) * is.comp;            \
+            float dh = (g.comp - cg.comp - xh * cgx.comp) * is.comp;              \
+            bool pos = u.comp > 0.f;                                              \
+            du.comp = pos ? dh : sl.comp * dh;                                    \
+            ds4[idx] += pos ? 0.f : u.comp * dh;                                  \
+            db4[idx] += du.comp;                                                  \
+          }
+          RAAE_DU(x, 0) RAAE_DU(y, 1) RAAE_DU(z, 2) RAAE_DU(w, 3)
+#undef RAAE_DU
+        }
+        *reinterpret_cast<float4*>(Dt + r * kLD + c4) = du;
+      }
     }
     // 2. the layer's input activations
     if (in.kind == kInHidden) build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
@@ -705,11 +928,170 @@ __device__ __noinline__ void bwd_hidden(const Ctx& c, int net, int l, const Laye
   __syncthreads();
 }
 
+// backward of a hidden block whose input is another hidden block's panel (K = 64), software-pipelined: the raw
+// g / u / u_prev tiles of tile t+1 are prefetched with cp.async while tile t runs its two contractions.
+__device__ __noinline__ void bwd_hidden64(const Ctx& c, int net, int l, const LayerIn& in, const float* __restrict__ u_l,
+                                          const float* __restrict__ g_in, float* __restrict__ g_out, int o) {
+  RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStBwdHidden]);
+  const raae_net_layout& nl = NL(c, net);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4;
+  const float* Wg = netp(c, net) + nl.w_off[l];
+  float* Gb[2] = {arena, arena + kTile};                     // g tile -> du in place
+  float* Pb[2] = {arena + 2 * kTile, arena + 3 * kTile};     // u_prev tile -> input activations in place
+  float* Ub = arena + 4 * kTile;                             // u_l tile (free again after the du pass)
+  float* Ws = arena + 5 * kTile;                             // [64][kLD] W_l, natural layout (NN operand)
+  float* slope_in = sm->shift;                               // slopes of the producing layer (shift is free in backward)
+  const float* mean_in = sm->mean[in.snet][in.slayer];
+  const float* inv_in = sm->inv[in.snet][in.slayer];
+  const int ntiles = (c.B + kTM - 1) / kTM;
+  __syncthreads();
+  {
+    const int nv0 = min(kTM, c.B);
+    prefetch_panel_tile(Gb[0], g_in, 0, nv0);
+    prefetch_panel_tile(Ub, u_l, 0, nv0);
+    prefetch_panel_tile(Pb[0], in.src, 0, nv0);
+    cp_async_commit();
+  }
+  if (tid < kH) {
+    float nB = (float)c.B;
+    sm->cg[tid] = sm->sg[tid] / nB;
+    sm->cgx[tid] = sm->sgx[tid] / nB;
+    sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
+    slope_in[tid] = in.slope[tid];
+  }
+  load_w_rows(Ws, kLD, Wg, kH, 0, kH);
+  __syncthreads();
+  const float4 mu = *reinterpret_cast<const float4*>(sm->mean[net][l] + c4);
+  const float4 is = *reinterpret_cast<const float4*>(sm->inv[net][l] + c4);
+  const float4 sl = *reinterpret_cast<const float4*>(sm->slope + c4);
+  const float4 cg = *reinterpret_cast<const float4*>(sm->cg + c4);
+  const float4 cgx = *reinterpret_cast<const float4*>(sm->cgx + c4);
+  float db4[4] = {0.f, 0.f, 0.f, 0.f}, ds4[4] = {0.f, 0.f, 0.f, 0.f};
+  float sg4[4] = {0.f, 0.f, 0.f, 0.f}, sgx4[4] = {0.f, 0.f, 0.f, 0.f};
+  float accW[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accW[i][j] = 0.f;
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    float* Dt = Gb[t & 1];
+    float* At = Pb[t & 1];
+    cp_async_wait<0>();
+    // 1. du = PReLU'(u) * BN'(g), in place over the g tile (own elements)
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nv) {
+        const float4 g = *reinterpret_cast<const float4*>(Dt + r * kLD + c4);
+        const float4 u = *reinterpret_cast<const float4*>(Ub + r * kLD + c4);
+#define RAAE_DU(comp, idx)                                                      \
+        {                                                                       \
+          float xh = (prelu_f(u.comp, sl.comp) - mu.comp) * is.comp;            \
+          float dh = (g.comp - cg.comp - xh * cgx.comp) * is.comp;              \
+          bool pos = u.comp > 0.f;                                              \
+          du.comp = pos ? dh : sl.comp * dh;                                    \
+          ds4[idx] += pos ? 0.f : u.comp * dh;                                  \
+          db4[idx] += du.comp;                                                  \
+        }
+        RAAE_DU(x, 0) RAAE_DU(y, 1) RAAE_DU(z, 2) RAAE_DU(w, 3)
+#undef RAAE_DU
+      }
+      *reinterpret_cast<float4*>(Dt + r * kLD + c4) = du;
+    }
+    // 2. the layer's input activations, in place over the u_prev tile
+    transform_act_tile(At, row0, nv, mean_in, inv_in, slope_in, in.mask);
+    __syncthreads();
+    // prefetch tile t+1 (Ub is free; the other two go to the alternate buffers)
+    if (t + 1 < ntiles) {
+      const int nvn = min(kTM, c.B - row0 - kTM);
+      prefetch_panel_tile(Gb[(t + 1) & 1], g_in, row0 + kTM, nvn);
+      prefetch_panel_tile(Ub, u_l, row0 + kTM, nvn);
+      prefetch_panel_tile(Pb[(t + 1) & 1], in.src, row0 + kTM, nvn);
+    }
+    cp_async_commit();
+    // 3. dW += du^T a
+    {
+      const int qq = tid >> 6, tt = tid & 63;
+      mma_tn8(Dt, kLD, 8 * (tt >> 3), At, kLD, 8 * (tt & 7), 32 * qq, 32 * qq + 32, accW);
+    }
+    // 4. g_prev = (du @ W) * dropout mask of the producing layer, and its BN-backward sums
+    {
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      mma_nn<kH>(Dt, kLD, Ws, kLD, acc, ty, tx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int r = ty + 16 * i;
+        if (r < nv) {
+          uint32_t kb = mask_keep4(in.mask, row0 + r, c4);
+          float4 a = *reinterpret_cast<const float4*>(At + r * kLD + c4);
+          float4 gm;
+          gm.x = (kb & 1u) ? acc[i][0] * in.mask.scale : 0.f;
+          gm.y = (kb & 2u) ? acc[i][1] * in.mask.scale : 0.f;
+          gm.z = (kb & 4u) ? acc[i][2] * in.mask.scale : 0.f;
+          gm.w = (kb & 8u) ? acc[i][3] * in.mask.scale : 0.f;
+          sg4[0] += gm.x; sg4[1] += gm.y; sg4[2] += gm.z; sg4[3] += gm.w;
+          sgx4[0] = fmaf(acc[i][0], a.x, sgx4[0]); sgx4[1] = fmaf(acc[i][1], a.y, sgx4[1]);
+          sgx4[2] = fmaf(acc[i][2], a.z, sgx4[2]); sgx4[3] = fmaf(acc[i][3], a.w, sgx4[3]);
+          *reinterpret_cast<float4*>(g_out + (size_t)(row0 + r) * kH + c4) = gm;
+        }
+      }
+    }
+    // no barrier: the next iteration only touches its own elements of the alternate buffers before its barrier
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- reductions, gradient export, AdamW ----
+  float* gb = Gb[0];               // [64] db | [64] dslope
+  float* gradW = Pb[0];            // dense [64][64]
+  sm->red[ty][c4 + 0] = db4[0]; sm->red[ty][c4 + 1] = db4[1]; sm->red[ty][c4 + 2] = db4[2]; sm->red[ty][c4 + 3] = db4[3];
+  __syncthreads();
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[tid] = s; }
+  __syncthreads();
+  sm->red[ty][c4 + 0] = ds4[0]; sm->red[ty][c4 + 1] = ds4[1]; sm->red[ty][c4 + 2] = ds4[2]; sm->red[ty][c4 + 3] = ds4[3];
+  __syncthreads();
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[kH + tid] = s; }
+  __syncthreads();
+  sm->red[ty][c4 + 0] = sg4[0]; sm->red[ty][c4 + 1] = sg4[1]; sm->red[ty][c4 + 2] = sg4[2]; sm->red[ty][c4 + 3] = sg4[3];
+  __syncthreads();
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sg[tid] = s; }
+  __syncthreads();
+  sm->red[ty][c4 + 0] = sgx4[0]; sm->red[ty][c4 + 1] = sgx4[1]; sm->red[ty][c4 + 2] = sgx4[2]; sm->red[ty][c4 + 3] = sgx4[3];
+  __syncthreads();
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sgx[tid] = s; }
+  {
+    const int qq = tid >> 6, tt = tid & 63, m0 = 8 * (tt >> 3), n0 = 8 * (tt & 7);
+    for (int pass = 0; pass < 4; ++pass) {
+      if (qq == pass) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float* dst = gradW + (m0 + i) * kH + n0 + j;
+            *dst = pass == 0 ? accW[i][j] : *dst + accW[i][j];
+          }
+      }
+      __syncthreads();
+    }
+  }
+  adam_apply(c, sm, o, net, nl.w_off[l], kH * kH, gradW);
+  adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
+  adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------
 // last encoder layer backward: BN(nstyle) -> Linear(64, nstyle); input gradient for hidden layer L-2
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void bwd_enc_last(const Ctx& c, const LayerIn& in, float* __restrict__ g_out, int o) {
   RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStBwdEncLast]);
   const raae_net_layout& nl = NL(c, kE);
   const int L = nl.n_linear, l = L - 1, ns = nl.out_dim[l];
   const int tid = threadIdx.x, ch = tid & 63, q = tid >> 6;
@@ -807,6 +1189,12 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c, const LayerIn& in, float
   adam_apply(c, sm, o, kE, nl.w_off[l], ns * kH, gradW);
   adam_apply(c, sm, o, kE, nl.b_off[l], ns, gradW + kZ * kH);
   __syncthreads();
+}
+
+__device__ __forceinline__ void bwd_hidden(const Ctx& c, int net, int l, const LayerIn& in, const float* __restrict__ u_l,
+                                           const float* __restrict__ g_in, float* g_out, int o) {
+  if (in.kind == kInHidden && g_out != nullptr) bwd_hidden64(c, net, l, in, u_l, g_in, g_out, o);
+  else bwd_hidden_edge(c, net, l, in, u_l, g_in, g_out, o);
 }
 
 // FCEncoder backward from sc.dz; x = the encoder's input rows.  dx_out != null (MI phase): the decoder

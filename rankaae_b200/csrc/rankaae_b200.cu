@@ -138,6 +138,7 @@ struct raae_handle {
   int64_t launches;
   bool bound_state, bound_data;
   int shapiro_n;
+  long long* prof;
 };
 
 extern "C" {
@@ -172,6 +173,7 @@ int raae_create(const raae_config* cfg, int device, raae_handle** out) {
   h->launches = 0;
   h->bound_state = h->bound_data = false;
   h->shapiro_n = 0;
+  h->prof = nullptr;
   RAAE_CUDA(cudaFuncSetAttribute(raae::raae_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raae::kSmemBytes));
   RAAE_CUDA(cudaFuncSetAttribute(raae::raae_val_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raae::kSmemBytes));
   *out = h;
@@ -287,6 +289,7 @@ int raae_train_epochs(raae_handle* h, int epoch_begin, int n_epochs, const int32
     a.out_losses = out_losses ? out_losses + (size_t)e * nt * 12 : nullptr;
     a.out_metrics = out_metrics ? out_metrics + (size_t)e * nt * 6 : nullptr;
     a.val.avg_mutual_info = -INFINITY;
+    a.prof = h->prof;
     raae::raae_train_kernel<<<nt, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
     RAAE_CUDA(cudaGetLastError());
     h->launches++;
@@ -300,5 +303,11 @@ int raae_train_epochs(raae_handle* h, int epoch_begin, int n_epochs, const int32
 }
 
 int64_t raae_launch_count(const raae_handle* h) { return h ? h->launches : 0; }
+
+int raae_set_profile_buffer(raae_handle* h, long long* prof) {
+  if (!h) return fail(-1, "null handle");
+  h->prof = prof;
+  return 0;
+}
 
 }  // extern "C"

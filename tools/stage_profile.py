@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Per-stage-type cycle breakdown of raae_train_kernel (in-kernel clock64 counters, thread 0 of each CTA).
+usage: python tools/stage_profile.py [trials] [epochs]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as graft  # noqa: E402
+
+graft.build()
+from bench import EXAMPLE, synthetic_arrays  # noqa: E402
+from rankaae_b200 import _lib as L  # noqa: E402
+from rankaae_b200.engine import Engine  # noqa: E402
+from rankaae_b200.trainer import init_trial_state  # noqa: E402
+
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+E = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+names = ["build_batch", "fwd_hidden(wide)", "fwd_hidden(64)", "fwd_hidden(latent)", "fwd_enc_last", "bwd_hidden(wide)",
+         "bwd_hidden(64)", "bwd_hidden(latent)", "bwd_enc_last", "dec_last(loss+bwd)", "dec_last(storeV)", "dec_last(fromDv)",
+         "dis_stage", "kendall", "mi_mse", "TOTAL"]
+if os.environ.get("RAAE_NODROP"):
+    EXAMPLE = dict(EXAMPLE, dropout_rate=0.0, dis_dropout_rate=0.0)
+eng = Engine(EXAMPLE, n_trials=T, device="cuda:0", max_rows=1056)
+for t in range(T):
+    init_trial_state(eng, t, EXAMPLE, seed=t)
+eng.bind_dataset(*synthetic_arrays())
+eng.train_epochs(0, 2)
+torch.cuda.synchronize()
+prof = torch.zeros(T, 32, dtype=torch.int64, device="cuda:0")
+L.check(eng.lib.raae_set_profile_buffer(eng.handle, prof.data_ptr()))
+eng.train_epochs(2, E)
+torch.cuda.synchronize()
+p = prof.cpu().numpy().astype(np.float64) / (E * 5)          # cycles per train step
+tot = p[:, 15].mean()
+print(f"trials {T}: {tot/1e6:.3f} Mcycles per step per trial (mean over trials), calls per step in brackets")
+calls = [1, 6, 34, 4, 6, 4, 21, 3, 4, 2, 1, 1, 1, 1, 1, 1]
+for i, n in enumerate(names):
+    v = p[:, i].mean()
+    print(f"  {n:22s} {v/1e3:10.1f} kcyc  {100*v/tot:5.1f}%   [{calls[i]:2d} calls, {v/1e3/calls[i]:8.1f} kcyc each]")
+for i, n in enumerate(["fwd64: build_act_tile", "fwd64: sync", "fwd64: mma_nt", "fwd64: Ot store + sync", "fwd64: epilogue", "fwd64: end sync"]):
+    v = p[:, 16 + i].mean()
+    print(f"    probe {n:26s} {v/1e3:10.1f} kcyc  per tile {v/240:8.0f} cyc")
+print(f"  {'(unaccounted)':22s} {(tot - p[:, :15].sum(1).mean())/1e3:10.1f} kcyc")
