@@ -29,8 +29,8 @@ _L = _i32 * MAX_LAYERS
 class Config(C.Structure):
     _fields_ = [(n, _i32) for n in (
         "dim_in", "dim_out", "nstyle", "n_aux", "n_layers", "dis_layers", "batch_size", "n_trials",
-        "kendall_activation", "use_flex_spec_target", "decoder_softplus", "max_rows", "ctas_per_trial")] + [
-        ("reserved", _i32 * 3)]
+        "kendall_activation", "use_flex_spec_target", "decoder_softplus", "max_rows", "ctas_per_trial",
+        "tensor_cores")] + [("reserved", _i32 * 2)]
 
 
 class NetLayout(C.Structure):

@@ -180,6 +180,25 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const KParams& p, const RunArgs
 
 constexpr size_t kSmemBytes = kArenaOffset + (size_t)kArenaFloats * sizeof(float);
 
+// TMEM accumulator + mbarrier for the tcgen05 path (one CTA per SM, so the allocation never contends)
+__device__ __forceinline__ void tc_setup(const KParams& p, SmemFixed* sm) {
+  if (!p.cfg.tensor_cores) return;
+  if (threadIdx.x < 32) tc::tmem_alloc(&sm->tmem_base, tc::kTmemCols);
+  if (threadIdx.x == 0) {
+    tc::mbar_init(reinterpret_cast<uint64_t*>(&sm->mbar), 1);
+    sm->tc_phase = 0;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+}
+__device__ __forceinline__ void tc_teardown(const KParams& p, SmemFixed* sm) {
+  if (!p.cfg.tensor_cores) return;
+  tc::fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_dealloc(sm->tmem_base, tc::kTmemCols);
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunArgs a) {
   RAAE_SMEM();
@@ -188,6 +207,7 @@ raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ Run
   init_ctx(c, p, a, trial);
   if (threadIdx.x < 32) sm->prof[threadIdx.x] = 0;
   const long long t_start = clock64();
+  tc_setup(p, sm);
   if (a.debug) {
     c.B = a.dbg.rows;
     c.epoch = a.dbg.epoch;
@@ -195,6 +215,7 @@ raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ Run
     c.step_id = 0;
     build_batch(c, nullptr);
     train_step(c, a.dbg.phase_mask);
+    tc_teardown(p, sm);
     return;
   }
   const int bs = p.cfg.batch_size;
@@ -211,6 +232,7 @@ raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ Run
     a.prof[(size_t)trial * 32 + 15] += clock64() - t_start;
     for (int i = 16; i < 32; ++i) a.prof[(size_t)trial * 32 + i] += sm->prof[i];
   }
+  tc_teardown(p, sm);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -335,6 +357,7 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
   c.xld = p.cfg.dim_in;
   c.step_id = 0x40000000u + (uint32_t)a.epoch;
   const raae_val_io& io = a.val;
+  tc_setup(p, sm);
   if (tid == 0) {
     sm->alpha = alpha_schedule(c);
     for (int i = 0; i < 8; ++i) sm->loss_acc[i] = 0.0;
@@ -403,6 +426,7 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
       plateau_step(c, combined);
     }
   }
+  tc_teardown(p, sm);
 }
 
 // lr <- hp, t <- 0, best <- +inf, bad <- 0; misc zeroed

@@ -7,6 +7,7 @@
 // stage == one layer (forward) or one layer's backward; stages are separated by __syncthreads().
 #pragma once
 #include "aae_common.cuh"
+#include "aae_tc.cuh"
 
 namespace raae {
 
@@ -29,6 +30,9 @@ struct SmemFixed {
   float kw[kZ];
   float alpha;
   long long prof[32];                   // per-stage-type cycle counters (thread 0), see StageId; 16.. = sub-stage probes
+  unsigned long long mbar;              // mbarrier the tcgen05 commits arrive on
+  uint32_t tmem_base;                   // TMEM address returned by tcgen05.alloc
+  uint32_t tc_phase;                    // parity of the next mbarrier completion
 };
 
 enum StageId { kStBatch = 0, kStFwdWide, kStFwdHidden, kStFwdLatent, kStFwdEncLast, kStBwdWide, kStBwdHidden, kStBwdLatent,
@@ -60,14 +64,14 @@ struct Ctx {
 
 // Shared memory is always reached through the `extern __shared__` symbol (never through a pointer stored
 // in a struct) so that the compiler emits LDS/STS with 32-bit addresses instead of generic LD/ST.
-constexpr size_t kArenaOffset = ((sizeof(SmemFixed) + 15) / 16) * 16;
+constexpr size_t kArenaOffset = ((sizeof(SmemFixed) + 1023) / 1024) * 1024;   // tcgen05 SWIZZLE_128B tiles need 1 KB alignment
 #define RAAE_SMEM()                                                            \
-  extern __shared__ __align__(16) unsigned char raae_smem_raw[];               \
+  extern __shared__ __align__(1024) unsigned char raae_smem_raw[];             \
   SmemFixed* const sm = reinterpret_cast<SmemFixed*>(raae_smem_raw);           \
   float* const arena = reinterpret_cast<float*>(raae_smem_raw + kArenaOffset); \
   (void)arena
 
-constexpr int kArenaFloats = 51200;     // 200 KB; see the per-stage carve-ups below
+constexpr int kArenaFloats = 50944;     // 199 KB; see the per-stage carve-ups below
 constexpr int kTile = kTM * kLD;        // 8704 floats
 constexpr int kWideTile = kTM * kLDW;   // 33280 floats
 constexpr int kWTile = kH * kLD;        // 4352 floats
@@ -547,6 +551,157 @@ __device__ __noinline__ void fwd_hidden64(const Ctx& c, int net, int l, const La
   __syncthreads();
 }
 
+// fwd_hidden64 with the contraction on the tensor core (tcgen05.mma kind::tf32, 3 x TF32 split, TMEM accumulator)
+__device__ __noinline__ void fwd_hidden64_tc(const Ctx& c, int net, int l, const LayerIn& in, float* __restrict__ u_out) {
+  RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStFwdHidden]);
+  const raae_net_layout& nl = NL(c, net);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, warp = tid >> 5, lane = tid & 31;
+  const float* Wg = netp(c, net) + nl.w_off[l];
+  float* Ahi = arena;                              // [2 K blocks][128 rows][32] swizzled
+  float* Alo = Ahi + tc::kATileFloats;
+  float* Whi = Alo + tc::kATileFloats;             // [2 K blocks][64 rows][32] swizzled
+  float* Wlo = Whi + tc::kBTileFloats;
+  float* Rb[2] = {Wlo + tc::kBTileFloats, Wlo + tc::kBTileFloats + kTile};   // raw prefetch tiles [kTM][kLD]
+  float* Ot = Rb[1] + kTile;                       // [kTM][kLD]
+  float* slope_in = sm->cg;
+  const float* mean_in = sm->mean[in.snet][in.slayer];
+  const float* inv_in = sm->inv[in.snet][in.slayer];
+  const int ntiles = (c.B + kTM - 1) / kTM;
+  const uint32_t d_tmem = sm->tmem_base;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(&sm->mbar);
+  __syncthreads();
+  prefetch_panel_tile(Rb[0], in.src, 0, min(kTM, c.B));
+  cp_async_commit();
+  // W_l [64 n][64 k] -> hi / lo, K-major SWIZZLE_128B
+  for (int i = tid; i < kH * (kH / 4); i += kThreads) {
+    const int n = i >> 4, k4 = (i & 15) * 4;
+    const float4 w = *reinterpret_cast<const float4*>(Wg + (size_t)n * kH + k4);
+    tc::split_store(Whi, Wlo, tc::sw128_chunk_off(n, k4, tc::kBBlockBytes), w);
+  }
+  if (tid < kH) {
+    sm->bias[tid] = netp(c, net)[nl.b_off[l] + tid];
+    sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
+    slope_in[tid] = in.slope[tid];
+    if (!c.train) {
+      sm->mean[net][l][tid] = c.st[nl.rm_off[l] + tid];
+      sm->inv[net][l][tid] = 1.f / sqrtf(c.st[nl.rv_off[l] + tid] + kBnEps);
+    }
+  }
+  __syncthreads();
+  float4 s1v = make_float4(0.f, 0.f, 0.f, 0.f), s2v = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t phase = sm->tc_phase;
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    float* Rt = Rb[t & 1];
+    if (t + 1 < ntiles) prefetch_panel_tile(Rb[(t + 1) & 1], in.src, row0 + kTM, min(kTM, c.B - row0 - kTM));
+    cp_async_commit();
+    cp_async_wait<1>();
+    // transform own elements of the raw tile and stage them as hi / lo tensor-core operands
+    {
+      const float4 mu = *reinterpret_cast<const float4*>(mean_in + c4);
+      const float4 is = *reinterpret_cast<const float4*>(inv_in + c4);
+      const float4 sl = *reinterpret_cast<const float4*>(slope_in + c4);
+#pragma unroll
+      for (int i = 0; i < kTM / 16; ++i) {
+        const int r = ty + 16 * i;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nv) {
+          const float4 uu = *reinterpret_cast<const float4*>(Rt + r * kLD + c4);
+          uint32_t kb = mask_keep4(in.mask, row0 + r, c4);
+          o.x = (kb & 1u) ? (prelu_f(uu.x, sl.x) - mu.x) * is.x * in.mask.scale : 0.f;
+          o.y = (kb & 2u) ? (prelu_f(uu.y, sl.y) - mu.y) * is.y * in.mask.scale : 0.f;
+          o.z = (kb & 4u) ? (prelu_f(uu.z, sl.z) - mu.z) * is.z * in.mask.scale : 0.f;
+          o.w = (kb & 8u) ? (prelu_f(uu.w, sl.w) - mu.w) * is.w * in.mask.scale : 0.f;
+        }
+        tc::split_store(Ahi, Alo, tc::sw128_chunk_off(r, c4, tc::kABlockBytes), o);
+      }
+    }
+    tc::fence_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm_3xtf32(d_tmem, Ahi, Alo, Whi, Wlo);
+      tc::mma_commit(mbar);
+    }
+    tc::mbar_wait(mbar, phase);
+    phase ^= 1u;
+    tc::fence_after_sync();
+    // accumulator -> Ot (+ bias): warp w owns TMEM lanes 32 (w % 4) .. +31 and columns 32 (w / 4) .. +31
+    {
+      float v[32];
+      const int row = 32 * (warp & 3) + lane, col0 = 32 * (warp >> 2);
+      tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o = make_float4(v[j] + sm->bias[col0 + j], v[j + 1] + sm->bias[col0 + j + 1], v[j + 2] + sm->bias[col0 + j + 2],
+                               v[j + 3] + sm->bias[col0 + j + 3]);
+        *reinterpret_cast<float4*>(Ot + row * kLD + col0 + j) = o;
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    const float4 a_sl = *reinterpret_cast<const float4*>(sm->slope + c4);
+    float4 uo[kTM / 16];
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) uo[i] = *reinterpret_cast<const float4*>(Ot + (ty + 16 * i) * kLD + c4);
+    if (c.train && t == 0) {
+      float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < kTM / 16; ++i)
+        if (ty + 16 * i < nv) {
+          sp.x += prelu_f(uo[i].x, a_sl.x); sp.y += prelu_f(uo[i].y, a_sl.y);
+          sp.z += prelu_f(uo[i].z, a_sl.z); sp.w += prelu_f(uo[i].w, a_sl.w);
+        }
+      *reinterpret_cast<float4*>(&sm->red[ty][c4]) = sp;
+      __syncthreads();
+      if (tid < kH) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sacc += sm->red[i][tid];
+        sm->shift[tid] = sacc / (float)nv;
+      }
+      __syncthreads();
+    }
+    const float4 sh = c.train ? *reinterpret_cast<const float4*>(sm->shift + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      if (r < nv) {
+        *reinterpret_cast<float4*>(u_out + (size_t)(row0 + r) * kH + c4) = uo[i];
+        float d;
+        d = prelu_f(uo[i].x, a_sl.x) - sh.x; s1v.x += d; s2v.x = fmaf(d, d, s2v.x);
+        d = prelu_f(uo[i].y, a_sl.y) - sh.y; s1v.y += d; s2v.y = fmaf(d, d, s2v.y);
+        d = prelu_f(uo[i].z, a_sl.z) - sh.z; s1v.z += d; s2v.z = fmaf(d, d, s2v.z);
+        d = prelu_f(uo[i].w, a_sl.w) - sh.w; s1v.w += d; s2v.w = fmaf(d, d, s2v.w);
+      }
+    }
+    // the next iteration's barrier (after its operand staging) orders these Ot reads before the next Ot writes;
+    // the operand tiles are free again because this iteration waited for its MMAs
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  if (tid == 0) sm->tc_phase = phase;
+  if (c.train) {
+    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s1v;
+    __syncthreads();
+    float a1 = 0.f, a2 = 0.f;
+    if (tid < kH) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a1 += sm->red[i][tid];
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s2v;
+    __syncthreads();
+    if (tid < kH) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a2 += sm->red[i][tid];
+      bn_finalize(c, sm, net, l, tid, sm->shift[tid], a1, a2, c.B);
+    }
+  }
+  __syncthreads();
+}
+
 // statistics of nstyle columns of a [rows][kZ] panel (two-pass); results in sm->zs[0] (mean), zs[1] (biased var)
 __device__ __forceinline__ void latent_colstats(SmemFixed* sm, const float* __restrict__ z, int nrows) {
   const int tid = threadIdx.x, k = tid & 7, g = tid >> 3;
@@ -636,8 +791,12 @@ __device__ __noinline__ void fwd_enc_last(const Ctx& c, const LayerIn& in) {
 }
 
 __device__ __forceinline__ void fwd_hidden(const Ctx& c, int net, int l, const LayerIn& in, float* __restrict__ u_out) {
-  if (in.kind == kInHidden) fwd_hidden64(c, net, l, in, u_out);
-  else fwd_hidden_edge(c, net, l, in, u_out);
+  if (in.kind == kInHidden) {
+    if (c.p->cfg.tensor_cores & 1) fwd_hidden64_tc(c, net, l, in, u_out);
+    else fwd_hidden64(c, net, l, in, u_out);
+  } else {
+    fwd_hidden_edge(c, net, l, in, u_out);
+  }
 }
 
 // LayerIn describing "the activations coming out of hidden layer l of `net`, forward instance inst"
@@ -1086,6 +1245,231 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c, int net, int l, const La
   __syncthreads();
 }
 
+// bwd_hidden64 with both contractions on the tensor core: g_prev = du W (128 x 64 x 64, read back every tile) and
+// dW += du^T a (64 x 64, K = batch rows, accumulated in TMEM over the whole batch and read back once).
+// du is staged K-major (SWIZZLE_128B) for the first product and, once that product has completed, re-staged from
+// registers MN-major (SWIZZLE_128B_BASE32B, the only MN-major layout of 32-bit operands) into the same buffer for the
+// second; the input activations are staged MN-major only.  The g_prev epilogue overlaps the dW MMAs.
+__device__ __noinline__ void bwd_hidden64_tc(const Ctx& c, int net, int l, const LayerIn& in, const float* __restrict__ u_l,
+                                             const float* __restrict__ g_in, float* __restrict__ g_out, int o) {
+  RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStBwdHidden]);
+  const raae_net_layout& nl = NL(c, net);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, warp = tid >> 5, lane = tid & 31;
+  const float* Wg = netp(c, net) + nl.w_off[l];
+  float* Dhi = arena;                                  // du tile (K-major, then MN-major)
+  float* Dlo = Dhi + tc::kATileFloats;
+  float* Phi = Dlo + tc::kATileFloats;                 // input-activation tile (MN-major)
+  float* Plo = Phi + tc::kATileFloats;
+  float* Wthi = Plo + tc::kATileFloats;                // W^T (K-major): rows = input channel k, K index = output channel n
+  float* Wtlo = Wthi + tc::kBTileFloats;
+  float* slope_in = sm->shift;
+  const float* mean_in = sm->mean[in.snet][in.slayer];
+  const float* inv_in = sm->inv[in.snet][in.slayer];
+  const int ntiles = (c.B + kTM - 1) / kTM;
+  const uint32_t d_tmem = sm->tmem_base;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(&sm->mbar);
+  __syncthreads();
+  if (tid < kH) {
+    float nB = (float)c.B;
+    sm->cg[tid] = sm->sg[tid] / nB;
+    sm->cgx[tid] = sm->sgx[tid] / nB;
+    sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
+    slope_in[tid] = in.slope[tid];
+  }
+  for (int i = tid; i < kH * kH; i += kThreads) {      // W[n][k] -> W^T operand element (row k, column n)
+    const int n = i >> 6, k = i & 63;
+    const float w = Wg[i];
+    const float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+    const uint32_t off = tc::sw128_chunk_off(k, n & ~3, tc::kBBlockBytes) + (uint32_t)((n & 3) * 4);
+    *reinterpret_cast<float*>(reinterpret_cast<char*>(Wthi) + off) = h;
+    *reinterpret_cast<float*>(reinterpret_cast<char*>(Wtlo) + off) = w - h;
+  }
+  __syncthreads();
+  const float4 mu = *reinterpret_cast<const float4*>(sm->mean[net][l] + c4);
+  const float4 is = *reinterpret_cast<const float4*>(sm->inv[net][l] + c4);
+  const float4 sl = *reinterpret_cast<const float4*>(sm->slope + c4);
+  const float4 cg = *reinterpret_cast<const float4*>(sm->cg + c4);
+  const float4 cgx = *reinterpret_cast<const float4*>(sm->cgx + c4);
+  const float4 mu_in = *reinterpret_cast<const float4*>(mean_in + c4);
+  const float4 is_in = *reinterpret_cast<const float4*>(inv_in + c4);
+  const float4 sl_in = *reinterpret_cast<const float4*>(slope_in + c4);
+  float db4[4] = {0.f, 0.f, 0.f, 0.f}, ds4[4] = {0.f, 0.f, 0.f, 0.f};
+  float sgv[32], sgxv[32];                              // this thread's row (mod 128) x 32 columns partial sums
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { sgv[j] = 0.f; sgxv[j] = 0.f; }
+  uint32_t phase = sm->tc_phase;
+  const int erow = 32 * (warp & 3) + lane, ecol0 = 32 * (warp >> 2);     // epilogue ownership (TMEM lane, column block)
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    // the dW MMAs of the previous tile still read both operand buffers
+    if (t > 0) { tc::mbar_wait(mbar, phase); phase ^= 1u; }
+    // 1. du = PReLU'(u) BN'(g): kept in registers, staged K-major
+    float4 dur[kTM / 16];
+#pragma unroll
+    for (int b = 0; b < kTM / 16; b += 4) {
+      float4 gg[4], uu[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = ty + 16 * (b + i);
+        if (r < nv) {
+          gg[i] = *reinterpret_cast<const float4*>(g_in + (size_t)(row0 + r) * kH + c4);
+          uu[i] = *reinterpret_cast<const float4*>(u_l + (size_t)(row0 + r) * kH + c4);
+        } else {
+          gg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          uu[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = ty + 16 * (b + i);
+        float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nv) {
+          const float4 g = gg[i], u = uu[i];
+#define RAAE_DU(comp, idx)                                                        \
+          {                                                                       \
+            float xh = (prelu_f(u.comp, sl.comp) - mu.comp) * is.comp;            \
+            float dh = (g.comp - cg.comp - xh * cgx.comp) * is.comp;              \
+            bool pos = u.comp > 0.f;                                              \
+            du.comp = pos ? dh : sl.comp * dh;                                    \
+            ds4[idx] += pos ? 0.f : u.comp * dh;                                  \
+            db4[idx] += du.comp;                                                  \
+          }
+          RAAE_DU(x, 0) RAAE_DU(y, 1) RAAE_DU(z, 2) RAAE_DU(w, 3)
+#undef RAAE_DU
+        }
+        dur[b + i] = du;
+        tc::split_store(Dhi, Dlo, tc::sw128_chunk_off(r, c4, tc::kABlockBytes), du);
+      }
+    }
+    // 2. the layer's input activations, staged MN-major
+    {
+      float4 uu[kTM / 16];
+#pragma unroll
+      for (int i = 0; i < kTM / 16; ++i) {
+        const int r = ty + 16 * i;
+        uu[i] = r < nv ? *reinterpret_cast<const float4*>(in.src + (size_t)(row0 + r) * kH + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < kTM / 16; ++i) {
+        const int r = ty + 16 * i;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nv) {
+          uint32_t kb = mask_keep4(in.mask, row0 + r, c4);
+          a.x = (kb & 1u) ? (prelu_f(uu[i].x, sl_in.x) - mu_in.x) * is_in.x * in.mask.scale : 0.f;
+          a.y = (kb & 2u) ? (prelu_f(uu[i].y, sl_in.y) - mu_in.y) * is_in.y * in.mask.scale : 0.f;
+          a.z = (kb & 4u) ? (prelu_f(uu[i].z, sl_in.z) - mu_in.z) * is_in.z * in.mask.scale : 0.f;
+          a.w = (kb & 8u) ? (prelu_f(uu[i].w, sl_in.w) - mu_in.w) * is_in.w * in.mask.scale : 0.f;
+        }
+        tc::split_store(Phi, Plo, tc::sw128_32b_chunk_off(r, c4, tc::kABlockBytes), a);
+      }
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm_3xtf32(d_tmem, Dhi, Dlo, Wthi, Wtlo);                              // g_prev = du W
+      tc::mma_commit(mbar);
+    }
+    tc::mbar_wait(mbar, phase);
+    phase ^= 1u;
+    // 3. re-stage du MN-major (the K-major copy has been consumed) and start dW += du^T a
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i)
+      tc::split_store(Dhi, Dlo, tc::sw128_32b_chunk_off(ty + 16 * i, c4, tc::kABlockBytes), dur[i]);
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm_tn_3xtf32(d_tmem + 64, Dhi, Dlo, Phi, Plo, t > 0 ? 1u : 0u);
+      tc::mma_commit(mbar);
+    }
+    tc::fence_after_sync();
+    // 4. g_prev epilogue (overlaps the dW MMAs): dropout mask of the producing layer, BN-backward partial sums, store
+    {
+      float v[32];
+      tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)ecol0, v);
+      if (erow < nv) {
+        float* grow = g_out + (size_t)(row0 + erow) * kH + ecol0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const uint32_t kb = mask_keep4(in.mask, row0 + erow, ecol0 + j);
+          const uint32_t off = tc::sw128_32b_chunk_off(erow, ecol0 + j, tc::kABlockBytes);
+          const float4 ah = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Phi) + off);
+          const float4 al = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Plo) + off);
+          float4 gm;
+          gm.x = (kb & 1u) ? v[j] * in.mask.scale : 0.f;
+          gm.y = (kb & 2u) ? v[j + 1] * in.mask.scale : 0.f;
+          gm.z = (kb & 4u) ? v[j + 2] * in.mask.scale : 0.f;
+          gm.w = (kb & 8u) ? v[j + 3] * in.mask.scale : 0.f;
+          sgv[j] += gm.x; sgv[j + 1] += gm.y; sgv[j + 2] += gm.z; sgv[j + 3] += gm.w;
+          sgxv[j] = fmaf(v[j], ah.x + al.x, sgxv[j]);
+          sgxv[j + 1] = fmaf(v[j + 1], ah.y + al.y, sgxv[j + 1]);
+          sgxv[j + 2] = fmaf(v[j + 2], ah.z + al.z, sgxv[j + 2]);
+          sgxv[j + 3] = fmaf(v[j + 3], ah.w + al.w, sgxv[j + 3]);
+          *reinterpret_cast<float4*>(grow + j) = gm;
+        }
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();               // TMEM reads of this tile are ordered before the next tile's first MMA
+  }
+  tc::mbar_wait(mbar, phase);      // last dW MMAs
+  phase ^= 1u;
+  if (tid == 0) sm->tc_phase = phase;
+  // ---- weight gradient: TMEM columns [64,128), M = 64 layout (row n -> lane 32 (n / 16) + n % 16) ----
+  float* gradW = Phi;                 // dense [64][64]
+  float* gb = Dhi;                    // [64] db | [64] dslope
+  float* colred = Plo;                // [256][33] partial sums (8448 floats: Plo + the start of the W^T tiles)
+  tc::fence_after_sync();
+  __syncthreads();
+  if (warp < 4) {
+    float v[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      tc::tmem_ld32(d_tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(64 + 32 * h), v);
+      if (lane < 16) {
+        const int n = 16 * warp + lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) gradW[n * kH + 32 * h + j] = v[j];
+      }
+    }
+  }
+  tc::fence_before_sync();
+  sm->red[ty][c4 + 0] = db4[0]; sm->red[ty][c4 + 1] = db4[1]; sm->red[ty][c4 + 2] = db4[2]; sm->red[ty][c4 + 3] = db4[3];
+  __syncthreads();
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[tid] = s; }
+  __syncthreads();
+  sm->red[ty][c4 + 0] = ds4[0]; sm->red[ty][c4 + 1] = ds4[1]; sm->red[ty][c4 + 2] = ds4[2]; sm->red[ty][c4 + 3] = ds4[3];
+  __syncthreads();
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[kH + tid] = s; }
+  // column sums of the per-thread (row, 32-column) partials: threads of column block cb are warps 4 cb .. 4 cb + 3
+#pragma unroll
+  for (int j = 0; j < 32; ++j) colred[tid * 33 + j] = sgv[j];
+  __syncthreads();
+  if (tid < kH) {
+    const int cb = tid >> 5, j = tid & 31;
+    float s = 0.f;
+    for (int r = 0; r < 128; ++r) s += colred[(cb * 128 + r) * 33 + j];
+    sm->sg[tid] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) colred[tid * 33 + j] = sgxv[j];
+  __syncthreads();
+  if (tid < kH) {
+    const int cb = tid >> 5, j = tid & 31;
+    float s = 0.f;
+    for (int r = 0; r < 128; ++r) s += colred[(cb * 128 + r) * 33 + j];
+    sm->sgx[tid] = s;
+  }
+  __syncthreads();
+  adam_apply(c, sm, o, net, nl.w_off[l], kH * kH, gradW);
+  adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
+  adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------
 // last encoder layer backward: BN(nstyle) -> Linear(64, nstyle); input gradient for hidden layer L-2
 // ------------------------------------------------------------------------------------------
@@ -1193,8 +1577,12 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c, const LayerIn& in, float
 
 __device__ __forceinline__ void bwd_hidden(const Ctx& c, int net, int l, const LayerIn& in, const float* __restrict__ u_l,
                                            const float* __restrict__ g_in, float* g_out, int o) {
-  if (in.kind == kInHidden && g_out != nullptr) bwd_hidden64(c, net, l, in, u_l, g_in, g_out, o);
-  else bwd_hidden_edge(c, net, l, in, u_l, g_in, g_out, o);
+  if (in.kind == kInHidden && g_out != nullptr) {
+    if (c.p->cfg.tensor_cores & 2) bwd_hidden64_tc(c, net, l, in, u_l, g_in, g_out, o);
+    else bwd_hidden64(c, net, l, in, u_l, g_in, g_out, o);
+  } else {
+    bwd_hidden_edge(c, net, l, in, u_l, g_in, g_out, o);
+  }
 }
 
 // FCEncoder backward from sc.dz; x = the encoder's input rows.  dx_out != null (MI phase): the decoder

@@ -3,6 +3,7 @@ hyper-parameters and the dataset.  PyTorch is used for device memory and streams
 number is produced by the kernels in csrc/ through librankaae_b200.so."""
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -10,6 +11,9 @@ import torch
 from . import _lib as L
 
 ADAMW_DEFAULT_WD = 1e-2
+# bit 0: hidden-block forward, bit 1: hidden-block backward contractions on tcgen05 (3 x TF32, fp32-grade: the parity
+# suite passes in both modes); `tensor_cores: 0` in the config (or RAAE_TENSOR_CORES=0) selects the all-FP32-FMA path
+DEFAULT_TENSOR_CORES = 3
 
 
 def optimizer_hparams(cfg):
@@ -98,7 +102,8 @@ def make_config(cfg, n_trials, max_rows=None):
         n_aux=int(g("n_aux", 0)), n_layers=int(g("n_layers", 3)), dis_layers=int(g("FC_discriminator_layers", 3)),
         batch_size=bs, n_trials=int(n_trials), kendall_activation=int(bool(g("kendall_activation", False))),
         use_flex_spec_target=int(bool(g("use_flex_spec_target", False))), decoder_softplus=int(act == "Softplus"),
-        max_rows=int(max_rows if max_rows is not None else bs), ctas_per_trial=1)
+        max_rows=int(max_rows if max_rows is not None else bs), ctas_per_trial=1,
+        tensor_cores=int(g("tensor_cores", int(os.environ.get("RAAE_TENSOR_CORES", str(DEFAULT_TENSOR_CORES))))))
 
 
 class Engine:

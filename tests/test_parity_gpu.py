@@ -135,11 +135,12 @@ EXAMPLE = dict(
     use_flex_spec_target=True, weight_decay=0.01, kendall_activation=True, epoch_stop_smooth=1500)
 
 
-@pytest.fixture(scope="module")
-def example_engine(torch_cuda):
-    eng = _engine(EXAMPLE, max_rows=1056)
+@pytest.fixture(scope="module", params=[3, 0], ids=["tcgen05", "fp32fma"])
+def example_engine(request, torch_cuda):
+    """Both contraction back ends: tcgen05 3xTF32 (default) and the all-FP32-FMA path."""
+    eng = _engine(dict(EXAMPLE, tensor_cores=request.param), max_rows=1056)
     yield eng
-    PU.dump_report("parity_fullsize.json")
+    PU.dump_report(f"parity_fullsize_tc{request.param}.json")
     eng.close()
 
 
