@@ -261,8 +261,9 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
                 "traffic": None, "launch_ms": train_ms,
-                "note": "parity-mode kernel computes the contractions as FP32 FMA on CUDA cores (B200 FP32 peak "
-                        "~ 148 SM x 128 FMA x 2 x 1.9 GHz = 72 TFLOP/s); frac is against the tensor-core peak"}
+                "note": "hidden 64x64 blocks run on tcgen05 (kind::tf32, 3xTF32 split); 256-wide layers, discriminator and "
+                        "all element-wise stages on CUDA cores; the kernel is latency/issue-bound at 8 warps/SM "
+                        "(profiles/ncu_train_r01.md), frac is against the tensor-core peak"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
