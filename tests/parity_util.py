@@ -64,7 +64,21 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / den) if den > 0 else float(np.linalg.norm(a - b))
 
 
-def compare_phase(engine, trial, cfg, state, opt, x, aux, rnd, epoch, phase, tag):
+def f32_yardstick(cfg, state, x, aux, rnd, epoch, phase, ref):
+    """Error of the SAME oracle code run in float32 against its float64 run: what the reference's own precision
+    (PyTorch float32) costs on this case.  Ill-conditioned cases (deep stacks, tiny batches: BatchNorm divides by
+    sqrt(var + 1e-5)) are judged against this yardstick, as BASELINE.md §4 prescribes."""
+    c32 = lambda v: None if v is None else ([np.float32(m) for m in v] if isinstance(v, list) else np.float32(v))
+    st32 = O.cast_state(state, np.float32)
+    r32 = O.train_step(st32, None, cfg, np.float32(x), np.float32(aux), {k: c32(v) for k, v in rnd.items()}, epoch,
+                       apply_updates=False, phases=(phase,))
+    out = {"loss": abs(float(r32["losses"][phase]) - float(ref["losses"][phase]))}
+    for net in cfg.optimizer_hparams()[phase]["nets"]:
+        out[net] = rel_l2(net_vec(r32["grads"][phase][net], net == "E"), net_vec(ref["grads"][phase][net], net == "E"))
+    return out
+
+
+def compare_phase(engine, trial, cfg, state, opt, x, aux, rnd, epoch, phase, tag, yardstick=False):
     """Runs phase `phase` teacher-forced on both sides (no optimizer update); returns a report dict."""
     p = PHASES.index(phase)
     engine.set_state(trial, state, opt)
@@ -95,16 +109,21 @@ def compare_phase(engine, trial, cfg, state, opt, x, aux, rnd, epoch, phase, tag
                 bn = max(bn, float(np.abs(u - w).max() / max(1.0, np.abs(w).max())))
         rep[f"nbt_{net}"] = [int(got_state[net]["nbt"]), int(st[net]["nbt"])]
     rep["bn_buffer_err"] = bn
+    if yardstick:
+        rep["f32_yardstick"] = f32_yardstick(cfg, state, x, aux, rnd, epoch, phase, ref)
     REPORT.append(rep)
     return rep, got, ref
 
 
 def check_phase_report(rep):
+    """Bands: losses LOSS_TOL, gradients GRAD_TOL; when the report carries a float32 yardstick (ill-conditioned cases) the
+    band widens to 3x what the reference's own float32 arithmetic loses on that case."""
     ph = rep["phase"]
     lo = rep["loss_oracle"]
-    assert abs(rep["loss_cuda"] - lo) <= LOSS_TOL[ph] * max(1.0, abs(lo)), rep
+    ys = rep.get("f32_yardstick", {})
+    assert abs(rep["loss_cuda"] - lo) <= max(LOSS_TOL[ph] * max(1.0, abs(lo)), 3.0 * ys.get("loss", 0.0)), rep
     for net, e in rep["grad_rel_l2"].items():
-        assert e <= GRAD_TOL, (rep["tag"], ph, net, e, rep["grad_rel_l2_tensor"])
+        assert e <= max(GRAD_TOL, 3.0 * ys.get(net, 0.0)), (rep["tag"], ph, net, e, ys, rep["grad_rel_l2_tensor"])
     assert rep["bn_buffer_err"] <= 1e-5, rep
     for net in ("E", "D"):
         assert rep[f"nbt_{net}"][0] == rep[f"nbt_{net}"][1], rep
