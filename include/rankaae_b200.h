@@ -186,6 +186,20 @@ int raae_validate(raae_handle* h, int trial, const raae_val_io* io, void* stream
 int raae_train_epochs(raae_handle* h, int epoch_begin, int n_epochs, const int32_t* perm,
                       float* out_losses, float* out_metrics, void* stream);
 
+/* Split-phase entry points for the single-trial DATA-PARALLEL mode (BASELINE.json configs[3]): every rank
+ * holds the same weights and its own shard of the training rows.  raae_train_phase runs the phases in `phase_mask` of
+ * batch `step` of epoch `epoch` WITHOUT updating, exporting each phase's gradient vector (optimizer parameter order,
+ * [n_trials][raae_layout.opt[o].n]) to grads[o] (device pointers, NULL for phases not in the mask); the caller
+ * all-reduces (mean) the vector across ranks and hands it to raae_apply_adam.  Phase 0 (adversarial) must be launched
+ * first for every batch: that launch also builds the noised batch and runs the P0 forwards (trainer.py:112-114).
+ * BatchNorm statistics and Kendall pairs stay rank-local (DistributedDataParallel semantics).
+ * raae_validate_epoch runs the validation block + scheduler step of every resident trial (what raae_train_epochs
+ * does after the last batch of an epoch). */
+int raae_train_phase(raae_handle* h, int epoch, int step, int phase_mask, const int32_t* perm, float* const* grads,
+                     void* stream);
+int raae_apply_adam(raae_handle* h, int phase, const float* grads, void* stream);
+int raae_validate_epoch(raae_handle* h, int epoch, float* out_losses, float* out_metrics, void* stream);
+
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 int64_t raae_launch_count(const raae_handle* h);
 

@@ -66,7 +66,8 @@ class ValIO(C.Structure):
 
 EXPORTS = ("raae_last_error", "raae_version", "raae_query_layout", "raae_create", "raae_destroy", "raae_bind_state",
            "raae_bind_dataset", "raae_bind_shapiro_weights", "raae_reset_optimizers", "raae_step_debug",
-           "raae_validate", "raae_train_epochs", "raae_launch_count", "raae_set_profile_buffer")
+           "raae_validate", "raae_train_epochs", "raae_launch_count", "raae_set_profile_buffer",
+           "raae_train_phase", "raae_apply_adam", "raae_validate_epoch")
 
 _lib = None
 
@@ -99,6 +100,9 @@ def load():
     lib.raae_launch_count.argtypes = [_p]
     lib.raae_launch_count.restype = C.c_int64
     lib.raae_set_profile_buffer.argtypes = [_p, _p]
+    lib.raae_train_phase.argtypes = [_p, C.c_int, C.c_int, C.c_int, _p, C.POINTER(_p), _p]
+    lib.raae_apply_adam.argtypes = [_p, C.c_int, _p, _p]
+    lib.raae_validate_epoch.argtypes = [_p, C.c_int, _p, _p, _p]
     _lib = lib
     return lib
 

@@ -65,6 +65,11 @@ struct RunArgs {
   float* out_losses;            // [n_trials][12] (production, may be null)
   float* out_metrics;           // [n_trials][6]
   long long* prof;              // optional [n_trials][32] stage cycle counters (raae_set_profile_buffer)
+  // split-phase (data-parallel) launches: one batch `step0`, phases `phase_mask`, gradients exported, no update
+  int split;                    // 1 = split-phase launch
+  int step0;                    // batch index inside the epoch
+  int phase_mask;
+  float* grads_out[RAAE_NUM_PHASES];   // [n_trials][opt[o].n] per phase, optimizer parameter order
   raae_debug_io dbg;
   raae_val_io val;
 };

@@ -61,7 +61,7 @@ __device__ __noinline__ void build_batch(const Ctx& c, const int32_t* __restrict
 }
 
 // One iteration of the batch loop body, trainer.py:112-204 (gradient-reversal branch).
-__device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
+__device__ __forceinline__ void train_step(Ctx& c, int phase_mask, bool run_p0 = true) {
   const KParams& p = *c.p;
   RAAE_SMEM();
   const int tid = threadIdx.x, ns = p.cfg.nstyle;
@@ -72,6 +72,7 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
     for (int i = 0; i < 8; ++i) sm->loss_acc[i] = 0.0;
   }
   __syncthreads();
+  if (!run_p0) phase_mask &= ~(1 << kAdv);       // the adversarial phase back-propagates through the P0 forward
   const LayerIn x = wide_in(c.sc + p.sl.xn, p.sl.xld, p.cfg.dim_in, 0);
   const float* zE = c.sc + p.sl.zE;
   const float* meanZ = sm->mean[kE][LE - 1];
@@ -82,14 +83,16 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
 
   // P0 (trainer.py:113-114): styles = E(x); spec_out = D(styles) is unused, but the decoder's BatchNorm
   // buffers advance, so its hidden blocks run (the output Linear has no side effect and is skipped).
-  encoder_forward(c, x, 0);
-  if (c.a->debug && c.a->dbg.styles) {
-    for (int i = tid; i < c.B * ns; i += kThreads) {
-      int r = i / ns, k = i - r * ns;
-      c.a->dbg.styles[i] = (zE[(size_t)r * kZ + k] - meanZ[k]) * invZ[k];
+  if (run_p0) {
+    encoder_forward(c, x, 0);
+    if (c.a->debug && c.a->dbg.styles) {
+      for (int i = tid; i < c.B * ns; i += kThreads) {
+        int r = i / ns, k = i - r * ns;
+        c.a->dbg.styles[i] = (zE[(size_t)r * kZ + k] - meanZ[k]) * invZ[k];
+      }
     }
+    decoder_forward_hidden(c, zin, 0);
   }
-  decoder_forward_hidden(c, zin, 0);
 
   // P1 adversarial (trainer.py:118-127)
   if (phase_mask & (1 << kAdv)) {
@@ -154,9 +157,12 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask) {
   }
   if (tid == 0) {
     float* misc = c.st + p.lay.misc_off;
-    for (int i = 0; i < RAAE_NUM_PHASES; ++i) misc[i] = (float)sm->loss_acc[i];
-    misc[5] += (float)sm->loss_acc[kMI];
-    misc[6] += 1.f;
+    for (int i = 0; i < RAAE_NUM_PHASES; ++i)
+      if (phase_mask & (1 << i)) misc[i] = (float)sm->loss_acc[i];
+    if (phase_mask & (1 << kMI)) {
+      misc[5] += (float)sm->loss_acc[kMI];
+      misc[6] += 1.f;
+    }
     if (c.a->debug && c.a->dbg.losses)
       for (int i = 0; i < RAAE_NUM_PHASES; ++i) c.a->dbg.losses[i] = (float)sm->loss_acc[i];
   }
@@ -172,6 +178,7 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const KParams& p, const RunArgs
   c.Breal = p.cfg.batch_size;
   c.seed = mix32((uint32_t)(long long)c.hp[RAAE_HP_SEED] * 0x9e3779b9U + (uint32_t)trial * 0x85ebca6bU + 1u);
   c.epoch = a.epoch;
+  c.trial = trial;
   c.apply = 1;
   c.train = 1;
   c.x = c.sc + p.sl.xn;
@@ -220,6 +227,19 @@ raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ Run
   }
   const int bs = p.cfg.batch_size;
   const int32_t* perm = a.perm + (size_t)trial * p.n_train;
+  if (a.split) {
+    // one batch, selected phases, gradients exported instead of applied (data-parallel mode: the host all-reduces
+    // them and raae_adam_kernel applies the update).  The batch and the P0 forward belong to the launch that runs P1.
+    const bool first = (a.phase_mask & (1 << kAdv)) != 0;
+    if (first && a.step0 == 0 && threadIdx.x == 0) { c.st[p.lay.misc_off + 5] = 0.f; c.st[p.lay.misc_off + 6] = 0.f; }
+    c.B = min(bs, p.n_train - a.step0 * bs);
+    c.step_id = (uint32_t)(a.epoch * a.n_steps + a.step0);
+    c.apply = 0;
+    if (first) build_batch(c, perm + a.step0 * bs);
+    train_step(c, a.phase_mask, first);
+    tc_teardown(p, sm);
+    return;
+  }
   if (threadIdx.x == 0) { c.st[p.lay.misc_off + 5] = 0.f; c.st[p.lay.misc_off + 6] = 0.f; }
   for (int s = 0; s < a.n_steps; ++s) {
     c.B = min(bs, p.n_train - s * bs);
@@ -427,6 +447,41 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
     }
   }
   tc_teardown(p, sm);
+}
+
+// AdamW of optimizer `o` from a gradient vector in global memory (data-parallel mode); grid = (blocks, n_trials)
+__global__ void raae_adam_kernel(const __grid_constant__ KParams p, int o, const float* __restrict__ grads) {
+  const int trial = blockIdx.y;
+  float* st = p.state + (size_t)trial * p.lay.state_floats;
+  const double* hp = p.hp + (size_t)trial * RAAE_HP_COUNT;
+  const raae_opt_layout& ol = p.lay.opt[o];
+  const double lr = (double)st[ol.scalar_off + 0], t = (double)st[ol.scalar_off + 1] + 1.0;
+  const double b1 = hp[RAAE_HP_BETA1 + o], b2d = hp[RAAE_HP_BETA2 + o], wd = hp[RAAE_HP_WD + o];
+  const float decay = (float)(1.0 - lr * wd), w1 = (float)(1.0 - b1), b2 = (float)b2d, w2 = (float)(1.0 - b2d),
+              ss = (float)(lr / (1.0 - pow(b1, t))), bc2s = (float)sqrt(1.0 - pow(b2d, t));
+  const float* g = grads + (size_t)trial * ol.n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ol.n; i += gridDim.x * blockDim.x) {
+    int net = -1, rel = 0;
+    for (int k = 0; k < RAAE_NUM_NETS; ++k)
+      if (ol.net_off[k] >= 0 && i >= ol.net_off[k] && i < ol.net_off[k] + p.lay.net[k].n_params) { net = k; rel = i - ol.net_off[k]; }
+    float* P = st + p.lay.net[net].param_off + rel;
+    float* M = st + ol.m_off + i;
+    float* V = st + ol.v_off + i;
+    const float gi = g[i];
+    float pp = *P * decay;
+    float m = *M;
+    m = m + (gi - m) * w1;
+    float v = *V * b2 + (w2 * gi) * gi;
+    float denom = sqrtf(v) / bc2s + kAdamEps;
+    *P = pp - ss * (m / denom);
+    *M = m;
+    *V = v;
+  }
+}
+// step counter of optimizer o, after raae_adam_kernel
+__global__ void raae_adam_tick_kernel(const __grid_constant__ KParams p, int o, int n_trials) {
+  int trial = blockIdx.x * blockDim.x + threadIdx.x;
+  if (trial < n_trials) p.state[(size_t)trial * p.lay.state_floats + p.lay.opt[o].scalar_off + 1] += 1.f;
 }
 
 // lr <- hp, t <- 0, best <- +inf, bad <- 0; misc zeroed

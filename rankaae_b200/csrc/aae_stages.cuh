@@ -45,9 +45,19 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
   float sg4[4] = {0.f, 0.f, 0.f, 0.f}, sgx4[4] = {0.f, 0.f, 0.f, 0.f};
   double loss_a = 0.0, loss_b = 0.0;        // a: reconstruction, b: smoothness
   const float nB = (float)c.B, nN = (float)N;
+  const double inv_B = 1.0 / (double)c.B, inv_BN = 1.0 / ((double)c.B * (double)N);
+  // prefix sums of the (symmetric) taps: P[j] = w[0] + ... + w[j]; the replicate-padding overhang of the adjoint folds
+  // into the end points with these weights (see the smoothness branch below)
+  float tapP[8];
+  {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc += kGauss17[j]; tapP[j] = acc; }
+  }
   const int ntiles = (c.B + kTM - 1) / kTM;
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    const long long q0 = clock64();
     build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
     if (mode != kLastFromDv) {
       for (int n0 = 0; n0 < N; n0 += kH) {
@@ -70,6 +80,7 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
       build_wide_tile(Y, vpanel, vld, N, row0, nv, 0);
     }
     __syncthreads();
+    const long long q1 = clock64();
     if (mode == kLastStoreV) {
       const int cc = (tid & 63) * 4;
       for (int r = tid >> 6; r < nv; r += 4)
@@ -81,6 +92,15 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
       // ---- per-row losses and dL/dv; one warp per row, lane owns 8 consecutive columns ----
       float* ypad = rowbuf;
       float* ezp = rowbuf + 272;
+      const bool need_x = mode == kLastRecon || mode == kLastEval;
+      float xn[8];                  // target row of the NEXT iteration, prefetched one row ahead
+#pragma unroll
+      for (int e = 0; e < 8; ++e) xn[e] = 0.f;
+      if (need_x && warp < nv) {
+        const float* xrow = c.x + (size_t)(row0 + warp) * c.xld;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xn[e] = (lane * 8 + e < N) ? xrow[lane * 8 + e] : 0.f;
+      }
       for (int r = warp; r < kTM; r += kThreads / 32) {
         float* yrow = Y + r * kLDW;
         const int col0 = lane * 8;
@@ -89,6 +109,14 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
           for (int e = 0; e < 8; ++e) yrow[col0 + e] = 0.f;
           continue;
         }
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = xn[e];
+        if (need_x && r + kThreads / 32 < nv) {
+          const float* xrow = c.x + (size_t)(row0 + r + kThreads / 32) * c.xld;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xn[e] = (col0 + e < N) ? xrow[col0 + e] : 0.f;
+        }
         float v[8], y[8], dy[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -96,15 +124,10 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
           y[e] = (col0 + e < N) ? (act == 1 ? softplus2_f(v[e]) : fmaxf(v[e], 0.f)) : 0.f;
           dy[e] = 0.f;
         }
-        if (mode == kLastRecon || mode == kLastEval) {
-          float x[8];
-          const float* xrow = c.x + (size_t)(row0 + r) * c.xld;
+        if (need_x) {
           float sy = 0.f, sx = 0.f;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            x[e] = (col0 + e < N) ? xrow[col0 + e] : 0.f;
-            sy += y[e]; sx += x[e];
-          }
+          for (int e = 0; e < 8; ++e) { sy += y[e]; sx += x[e]; }
           float cc = 1.f, dr = 0.f;
           if (mode == kLastRecon && flex) {
 #pragma unroll
@@ -114,7 +137,7 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
             cc = fminf(fmaxf(rr, 0.7f), 1.3f);
             float sgn = m_out > 0.f ? 1.f : (m_out < 0.f ? -1.f : 0.f);
             dr = (0.2f / nB) * (rr - 1.f) * sgn / (fabsf(m_in) * nN);
-            if (lane == 0) loss_a += 0.1 * (double)((rr - 1.f) * (rr - 1.f)) / (double)nB;
+            if (lane == 0) loss_a += 0.1 * (double)((rr - 1.f) * (rr - 1.f)) * inv_B;
           }
           float sq = 0.f;
 #pragma unroll
@@ -125,7 +148,7 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
               dy[e] = dr + (2.f / (nB * nN)) * d;
             }
           }
-          loss_a += (double)sq / ((double)nB * (double)nN);
+          loss_a += (double)sq * inv_BN;
         }
         if (mode == kLastSmooth || mode == kLastEval) {
           // replicate-padded copy of the row
@@ -156,7 +179,7 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
               }
             }
           }
-          loss_b += (double)sq / ((double)nB * (double)nN);
+          loss_b += (double)sq * inv_BN;
           if (mode == kLastSmooth) {
             // adjoint: zero-padded full correlation of e with the taps, overhang folded into the end points
             if (lane < 16) { ezp[lane] = 0.f; ezp[16 + N + lane] = 0.f; }
@@ -179,15 +202,15 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
                   float kt = 0.f;
 #pragma unroll
                   for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], win[e + k], kt);
-                  if (j == 0) {            // overhang of the left replicate padding folds into y[0]
-                    for (int i = 0; i < 8; ++i)
+                  // overhang of the replicate padding: sum_{i<8} (K^T e)[i] = sum_{m<8} e[m] P[7-m] folds into y[0],
+                  // and by symmetry sum_{q<8} e[N-1-q] P[7-q] into y[N-1]
+                  if (j == 0) {
 #pragma unroll
-                      for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], ezp[16 + i - k], kt);
+                    for (int m = 0; m < 8; ++m) kt = fmaf(tapP[7 - m], ezp[16 + m], kt);
                   }
-                  if (j == N - 1) {        // right overhang folds into y[N-1]
-                    for (int i = N + 8; i < N + 16; ++i)
+                  if (j == N - 1) {
 #pragma unroll
-                      for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], ezp[16 + i - k], kt);
+                    for (int q2 = 0; q2 < 8; ++q2) kt = fmaf(tapP[7 - q2], ezp[16 + N - 1 - q2], kt);
                   }
                   dy[e] = (2.f / (nB * nN)) * (ee[e] - kt);
                 }
@@ -205,6 +228,8 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
       }
       __syncthreads();
     }
+    const long long q2 = clock64();
+    if (tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) { sm->prof[16] += q1 - q0; sm->prof[17 + (mode == kLastSmooth)] += q2 - q1; }
     if (want_bwd) {
       // db, dW += dv^T a, g = (dv @ W) * dropout
       {
@@ -212,7 +237,10 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
         for (int r = 0; r < kTM; ++r) s += Y[r * kLDW + tid];
         dbp = s;
       }
+      const long long q3 = clock64();
       mma_tn8(Y, kLDW, 8 * (tid >> 3), At, kLD, 8 * (tid & 7), 0, kTM, accW);
+      const long long q4 = clock64();
+      if (tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) { sm->prof[19] += q3 - q2; sm->prof[20] += q4 - q3; }
       float acc[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -241,6 +269,7 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
           *reinterpret_cast<float4*>(c.sc + c.p->sl.g[0] + (size_t)(row0 + r) * kH + c4) = gm;
         }
       }
+      if (tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) sm->prof[21] += clock64() - q4;
     }
     __syncthreads();
   }

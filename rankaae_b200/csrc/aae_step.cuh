@@ -60,6 +60,7 @@ struct Ctx {
   int train;          // BN batch statistics + dropout + noise
   int apply;          // apply optimizer updates
   int epoch;
+  int trial;
 };
 
 // Shared memory is always reached through the `extern __shared__` symbol (never through a pointer stored
@@ -254,7 +255,8 @@ __device__ inline void adam_finish(const Ctx& c, int o) {
 __device__ __forceinline__ void adam_apply(const Ctx& c, const SmemFixed* sm, int o, int net, int poff, int n,
                                            const float* __restrict__ g) {
   const raae_opt_layout& ol = c.p->lay.opt[o];
-  float* dbg = c.a->debug ? c.a->dbg.grads[o] : nullptr;
+  float* dbg = c.a->debug ? c.a->dbg.grads[o]
+             : (c.a->grads_out[o] ? c.a->grads_out[o] + (size_t)c.trial * ol.n : nullptr);
   if (dbg && ol.net_off[net] >= 0)
     for (int i = threadIdx.x; i < n; i += kThreads) dbg[ol.net_off[net] + poff + i] = g[i];
   if (!c.apply || ol.net_off[net] < 0) return;
@@ -356,14 +358,9 @@ __device__ __noinline__ void fwd_hidden_edge(const Ctx& c, int net, int l, const
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
       if (in.kind == kInHidden) {
-        long long p0 = clock64();
         build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
-        long long p1 = clock64();
         __syncthreads();
-        long long p2 = clock64();
         mma_nt<kH>(At, kLD, Ws, kLD, acc, ty, tx);
-        long long p3 = clock64();
-        if (tid == 0) { sm->prof[16] += p1 - p0; sm->prof[17] += p2 - p1; sm->prof[18] += p3 - p2; }
       } else {
         for (int k0 = 0; k0 < K; k0 += kH) {
           build_wide_chunk(At, in.src, in.ld, in.dim, k0, row0, nv, in.act);
@@ -377,9 +374,7 @@ __device__ __noinline__ void fwd_hidden_edge(const Ctx& c, int net, int l, const
 #pragma unroll
         for (int j = 0; j < 4; ++j) Ot[(ty + 16 * i) * kLD + tx + 16 * j] = acc[i][j] + sm->bias[tx + 16 * j];
     }
-    long long p4 = clock64();
     __syncthreads();
-    long long p5 = clock64();
     // elementwise epilogue: thread (ty, tx) owns channels 4tx..4tx+3 of rows ty, ty+16, ...
     const int c4 = tx * 4;
     const float4 a_sl = *reinterpret_cast<const float4*>(sm->slope + c4);
@@ -417,9 +412,7 @@ __device__ __noinline__ void fwd_hidden_edge(const Ctx& c, int net, int l, const
         d = prelu_f(uo[i].w, a_sl.w) - sh.w; s1v.w += d; s2v.w = fmaf(d, d, s2v.w);
       }
     }
-    long long p6 = clock64();
     __syncthreads();
-    if (tid == 0 && in.kind == kInHidden) { sm->prof[19] += p5 - p4; sm->prof[20] += p6 - p5; sm->prof[21] += clock64() - p6; }
   }
   if (c.train) {
     const int c4 = tx * 4;

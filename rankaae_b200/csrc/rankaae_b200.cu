@@ -303,6 +303,63 @@ int raae_train_epochs(raae_handle* h, int epoch_begin, int n_epochs, const int32
   return 0;
 }
 
+int raae_train_phase(raae_handle* h, int epoch, int step, int phase_mask, const int32_t* perm, float* const* grads,
+                     void* stream) {
+  if (!h || !perm || !grads) return fail(-1, "null argument");
+  if (!h->bound_state || !h->bound_data) return fail(-1, "state / dataset not bound");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  const int nt = h->kp.cfg.n_trials, bs = h->kp.cfg.batch_size;
+  const int n_steps = (h->kp.n_train + bs - 1) / bs;
+  if (step < 0 || step >= n_steps) return fail(-1, "step out of range");
+  if (h->kp.n_train - (n_steps - 1) * bs < 2) return fail(-1, "last batch has fewer than 2 rows");
+  raae::RunArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.epoch = epoch;
+  a.n_steps = n_steps;
+  a.perm = perm;
+  a.split = 1;
+  a.step0 = step;
+  a.phase_mask = phase_mask;
+  for (int o = 0; o < RAAE_NUM_PHASES; ++o) a.grads_out[o] = grads[o];
+  a.val.avg_mutual_info = -INFINITY;
+  raae::raae_train_kernel<<<nt, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+  RAAE_CUDA(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int raae_apply_adam(raae_handle* h, int phase, const float* grads, void* stream) {
+  if (!h || !grads) return fail(-1, "null argument");
+  if (phase < 0 || phase >= RAAE_NUM_PHASES) return fail(-1, "phase out of range");
+  if (!h->bound_state) return fail(-1, "state not bound");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  const int nt = h->kp.cfg.n_trials;
+  dim3 grid((h->kp.lay.opt[phase].n + 255) / 256, nt);
+  raae::raae_adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->kp, phase, grads);
+  RAAE_CUDA(cudaGetLastError());
+  raae::raae_adam_tick_kernel<<<(nt + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->kp, phase, nt);
+  RAAE_CUDA(cudaGetLastError());
+  h->launches += 2;
+  return 0;
+}
+
+int raae_validate_epoch(raae_handle* h, int epoch, float* out_losses, float* out_metrics, void* stream) {
+  if (!h) return fail(-1, "null handle");
+  if (!h->bound_state || !h->bound_data) return fail(-1, "state / dataset not bound");
+  if (h->kp.n_val < 3 || h->shapiro_n != h->kp.n_val) return fail(-1, "validation split / Shapiro-Wilk weights not bound");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  raae::RunArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.epoch = epoch;
+  a.out_losses = out_losses;
+  a.out_metrics = out_metrics;
+  a.val.avg_mutual_info = -INFINITY;
+  raae::raae_val_kernel<<<h->kp.cfg.n_trials, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+  RAAE_CUDA(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
 int64_t raae_launch_count(const raae_handle* h) { return h ? h->launches : 0; }
 
 int raae_set_profile_buffer(raae_handle* h, long long* prof) {

@@ -1,0 +1,64 @@
+"""End-of-training statistical parity (BASELINE.json north_star: "fixed-seed end-of-training latent/descriptor rank
+correlations must match within a stated band").
+
+Free-running float32 trajectories of two implementations cannot agree step by step, so the comparison is
+between DISTRIBUTIONS over seeds: tests/golden/e2e_band_ref.json holds 24 runs of the unmodified reference trainer
+(oracle/make_e2e_band.py); the fused path trains the same configuration for 32 seeds and, for every metric, the
+difference of the means must lie within
+
+        3 * sqrt(var_ref / n_ref + var_fused / n_fused) + slack
+
+with slack = 0.02 for the correlation-like quantities and 5 % relative for the losses (the stated band)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import aae_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "e2e_band_ref.json")
+
+
+def test_end_of_training_band():
+    import torch
+    from scipy.stats import spearmanr
+    from rankaae_b200.engine import Engine
+    from rankaae_b200.trainer import init_trial_state
+    ref = json.load(open(GOLDEN))
+    cfg = ref["config"]
+    spec, aux = O.synthetic_dataset(ref["n_rows"], O.Config.from_dict(cfg), seed=ref["data_seed"], dtype=np.float32)
+    n_train, n_val = int(ref["n_rows"] * 0.7), int(ref["n_rows"] * 0.15)
+    T = 32
+    eng = Engine(cfg, n_trials=T, device="cuda:0", max_rows=max(cfg["batch_size"], n_val), seeds=list(range(100, 100 + T)))
+    for t in range(T):
+        init_trial_state(eng, t, cfg, seed=100 + t)
+    eng.bind_dataset(spec[:n_train], aux[:n_train], spec[n_train:n_train + n_val], aux[n_train:n_train + n_val])
+    _, mets = eng.train_epochs(0, cfg["max_epoch"])
+    torch.cuda.synchronize()
+    fused_m = mets[-1, :, :5].cpu().numpy().astype(np.float64)
+    fused_rho = np.array([[spearmanr(eng.validate(t, epoch=cfg["max_epoch"] - 1)["z"][:, k], aux[n_train:n_train + n_val, k]).correlation
+                           for k in range(cfg["n_aux"])] for t in range(T)])
+    eng.close()
+    ref_m = np.array([r["metrics"] for r in ref["runs"]])
+    ref_rho = np.array([r["descriptor_spearman"] for r in ref["runs"]])
+    report = {"ref_metrics_mean": ref_m.mean(0).tolist(), "fused_metrics_mean": fused_m.mean(0).tolist(),
+              "ref_metrics_std": ref_m.std(0, ddof=1).tolist(), "fused_metrics_std": fused_m.std(0, ddof=1).tolist(),
+              "ref_rho_mean": ref_rho.mean(0).tolist(), "fused_rho_mean": fused_rho.mean(0).tolist(),
+              "ref_rho_std": ref_rho.std(0, ddof=1).tolist(), "fused_rho_std": fused_rho.std(0, ddof=1).tolist()}
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    json.dump(report, open(os.path.join(out_dir, "e2e_band.json"), "w"), indent=1)
+
+    def inside(a, b, slack_abs, slack_rel):
+        se = np.sqrt(a.var(0, ddof=1) / len(a) + b.var(0, ddof=1) / len(b))
+        return np.abs(a.mean(0) - b.mean(0)) <= 3.0 * se + slack_abs + slack_rel * np.abs(a.mean(0))
+
+    names = ["min Shapiro W", "val recon MSE", "avg MI", "max |Spearman| coupling", "val Kendall"]
+    ok = inside(ref_m, fused_m, np.array([0.02, 0.0, 0.0, 0.02, 0.005]), np.array([0.0, 0.05, 0.05, 0.0, 0.0]))
+    assert ok.all(), (dict(zip(names, ok.tolist())), report)
+    ok_rho = inside(ref_rho, fused_rho, 0.02, 0.0)
+    assert ok_rho.all(), (ok_rho.tolist(), report)
+    # every descriptor is learned by every fused trial (rank correlation of latent k with descriptor k)
+    assert (np.abs(fused_rho) > 0.6).all(), fused_rho

@@ -40,7 +40,8 @@ calls = [1, 6, 34, 4, 6, 4, 21, 3, 4, 2, 1, 1, 1, 1, 1, 1]
 for i, n in enumerate(names):
     v = p[:, i].mean()
     print(f"  {n:22s} {v/1e3:10.1f} kcyc  {100*v/tot:5.1f}%   [{calls[i]:2d} calls, {v/1e3/calls[i]:8.1f} kcyc each]")
-for i, n in enumerate(["fwd64: build_act_tile", "fwd64: sync", "fwd64: mma_nt", "fwd64: Ot store + sync", "fwd64: epilogue", "fwd64: end sync"]):
+for i, n in enumerate(["dec_last: act tile + fwd GEMM", "dec_last: recon loss pass", "dec_last: smooth loss pass", "dec_last: db column sums",
+                       "dec_last: dW (mma_tn8)", "dec_last: g GEMM + epilogue"]):
     v = p[:, 16 + i].mean()
-    print(f"    probe {n:26s} {v/1e3:10.1f} kcyc  per tile {v/240:8.0f} cyc")
+    print(f"    probe {n:30s} {v/1e3:10.1f} kcyc  per tile {v/(8 if 'loss pass' in n else 16):8.0f} cyc")
 print(f"  {'(unaccounted)':22s} {(tot - p[:, :15].sum(1).mean())/1e3:10.1f} kcyc")
