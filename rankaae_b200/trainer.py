@@ -27,7 +27,7 @@ def build_modules(p, seed=None):
         raise NotImplementedError(f"ae_form {ae_form!r} is not implemented by the fused path (FC only)")
     if g("use_cnn_discriminator", False):
         raise NotImplementedError("use_cnn_discriminator: true is not implemented by the fused path")
-    ctx = torch.random.fork_rng() if seed is not None else None
+    ctx = torch.random.fork_rng(devices=[]) if seed is not None else None
     if ctx is not None:
         ctx.__enter__()
         torch.manual_seed(int(seed))
