@@ -16,7 +16,8 @@ enum LastMode { kLastRecon = 0, kLastSmooth = 1, kLastStoreV = 2, kLastFromDv = 
 //   kLastEval  : plain-MSE reconstruction and smoothness losses only (validation, trainer.py:223-239)
 // Losses land in sm->loss_acc[kRecon] / [kSmooth].
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
+__device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int o) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[mode == kLastStoreV ? kStDecLastStoreV : mode == kLastFromDv ? kStDecLastFromDv : kStDecLastLoss]);
   const raae_net_layout& nl = NL(c, kD);
@@ -312,7 +313,8 @@ __device__ __noinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
 // Output: sm->loss_acc[kAdv]; with backward: discriminator gradients (AdamW / export) and
 // sc.dz = -alpha * dL/dstyles for the fake rows.
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void dis_stage(const Ctx& c, int backward, int o, const float* z_real_ptr, uint32_t key_zreal) {
+__device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, const float* z_real_ptr, uint32_t key_zreal) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStDis]);
   const raae_net_layout& nl = NL(c, kS);
@@ -594,7 +596,8 @@ __device__ __noinline__ void dis_stage(const Ctx& c, int backward, int o, const 
 // ------------------------------------------------------------------------------------------
 constexpr int kKendallChunk = 2048;
 
-__device__ __noinline__ void kendall_stage(const Ctx& c, const float* __restrict__ aux, int want_grad) {
+__device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __restrict__ aux, int want_grad) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStKendall]);
   const raae_net_layout& el = NL(c, kE);
@@ -697,7 +700,8 @@ __device__ __noinline__ void kendall_stage(const Ctx& c, const float* __restrict
 }
 
 // MSE between the re-encoded latent and z_sample (mutual_info_loss functions.py:174-192)
-__device__ __noinline__ void mi_mse_stage(const Ctx& c, int want_grad) {
+__device__ __noinline__ void mi_mse_stage(const Ctx& c_ref, int want_grad) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStMiMse]);
   const raae_net_layout& el = NL(c, kE);

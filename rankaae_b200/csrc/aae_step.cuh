@@ -46,6 +46,10 @@ struct StageTimer {
   __device__ __forceinline__ ~StageTimer() { if (threadIdx.x == 0) *slot += clock64() - t0; }
 };
 
+// sub-stage probe: thread 0 adds the cycles since the previous probe to sm->prof[slot]
+#define RAAE_PROBE_INIT() long long probe_t_ = clock64()
+#define RAAE_PROBE(slot) do { if (threadIdx.x == 0) { long long now_ = clock64(); sm->prof[slot] += now_ - probe_t_; probe_t_ = now_; } } while (0)
+
 struct Ctx {
   const KParams* p;
   const RunArgs* a;
@@ -308,7 +312,9 @@ __device__ __forceinline__ void bn_finalize(const Ctx& c, SmemFixed* sm, int net
   rv[ch] = (1.f - kBnMomentum) * rv[ch] + kBnMomentum * unb;
 }
 
-__device__ __noinline__ void fwd_hidden_edge(const Ctx& c, int net, int l, const LayerIn& in, float* __restrict__ u_out) {
+__device__ __noinline__ void fwd_hidden_edge(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[in.kind == kInWide ? kStFwdWide : in.kind == kInHidden ? kStFwdHidden : kStFwdLatent]);
   const raae_net_layout& nl = NL(c, net);
@@ -437,7 +443,9 @@ __device__ __noinline__ void fwd_hidden_edge(const Ctx& c, int net, int l, const
 
 // forward of a hidden block whose input is another hidden block's panel (K = 64): the raw pre-activation tile of
 // tile t+1 is prefetched with cp.async while tile t runs its contraction and epilogue.
-__device__ __noinline__ void fwd_hidden64(const Ctx& c, int net, int l, const LayerIn& in, float* __restrict__ u_out) {
+__device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStFwdHidden]);
   const raae_net_layout& nl = NL(c, net);
@@ -545,7 +553,9 @@ __device__ __noinline__ void fwd_hidden64(const Ctx& c, int net, int l, const La
 }
 
 // fwd_hidden64 with the contraction on the tensor core (tcgen05.mma kind::tf32, 3 x TF32 split, TMEM accumulator)
-__device__ __noinline__ void fwd_hidden64_tc(const Ctx& c, int net, int l, const LayerIn& in, float* __restrict__ u_out) {
+__device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStFwdHidden]);
   const raae_net_layout& nl = NL(c, net);
@@ -584,6 +594,8 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c, int net, int l, const
   __syncthreads();
   float4 s1v = make_float4(0.f, 0.f, 0.f, 0.f), s2v = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t phase = sm->tc_phase;
+  RAAE_PROBE_INIT();
+  RAAE_PROBE(22);
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     float* Rt = Rb[t & 1];
@@ -612,6 +624,7 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c, int net, int l, const
     }
     tc::fence_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
+    RAAE_PROBE(23);
     if (tid == 0) {
       tc::fence_after_sync();
       tc::issue_gemm_3xtf32(d_tmem, Ahi, Alo, Whi, Wlo);
@@ -619,6 +632,160 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c, int net, int l, const
     }
     tc::mbar_wait(mbar, phase);
     phase ^= 1u;
+    tc::fence_after_sync();
+    RAAE_PROBE(24);
+    // accumulator -> Ot (+ bias): warp w owns TMEM lanes 32 (w % 4) .. +31 and columns 32 (w / 4) .. +31
+    {
+      float v[32];
+      const int row = 32 * (warp & 3) + lane, col0 = 32 * (warp >> 2);
+      tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o = make_float4(v[j] + sm->bias[col0 + j], v[j + 1] + sm->bias[col0 + j + 1], v[j + 2] + sm->bias[col0 + j + 2],
+                               v[j + 3] + sm->bias[col0 + j + 3]);
+        *reinterpret_cast<float4*>(Ot + row * kLD + col0 + j) = o;
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    RAAE_PROBE(25);
+    const float4 a_sl = *reinterpret_cast<const float4*>(sm->slope + c4);
+    float4 uo[kTM / 16];
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) uo[i] = *reinterpret_cast<const float4*>(Ot + (ty + 16 * i) * kLD + c4);
+    if (c.train && t == 0) {
+      float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < kTM / 16; ++i)
+        if (ty + 16 * i < nv) {
+          sp.x += prelu_f(uo[i].x, a_sl.x); sp.y += prelu_f(uo[i].y, a_sl.y);
+          sp.z += prelu_f(uo[i].z, a_sl.z); sp.w += prelu_f(uo[i].w, a_sl.w);
+        }
+      *reinterpret_cast<float4*>(&sm->red[ty][c4]) = sp;
+      __syncthreads();
+      if (tid < kH) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sacc += sm->red[i][tid];
+        sm->shift[tid] = sacc / (float)nv;
+      }
+      __syncthreads();
+    }
+    const float4 sh = c.train ? *reinterpret_cast<const float4*>(sm->shift + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      if (r < nv) {
+        *reinterpret_cast<float4*>(u_out + (size_t)(row0 + r) * kH + c4) = uo[i];
+        float d;
+        d = prelu_f(uo[i].x, a_sl.x) - sh.x; s1v.x += d; s2v.x = fmaf(d, d, s2v.x);
+        d = prelu_f(uo[i].y, a_sl.y) - sh.y; s1v.y += d; s2v.y = fmaf(d, d, s2v.y);
+        d = prelu_f(uo[i].z, a_sl.z) - sh.z; s1v.z += d; s2v.z = fmaf(d, d, s2v.z);
+        d = prelu_f(uo[i].w, a_sl.w) - sh.w; s1v.w += d; s2v.w = fmaf(d, d, s2v.w);
+      }
+    }
+    // the next iteration's barrier (after its operand staging) orders these Ot reads before the next Ot writes;
+    // the operand tiles are free again because this iteration waited for its MMAs
+    RAAE_PROBE(26);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  if (tid == 0) sm->tc_phase = phase;
+  if (c.train) {
+    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s1v;
+    __syncthreads();
+    float a1 = 0.f, a2 = 0.f;
+    if (tid < kH) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a1 += sm->red[i][tid];
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s2v;
+    __syncthreads();
+    if (tid < kH) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a2 += sm->red[i][tid];
+      bn_finalize(c, sm, net, l, tid, sm->shift[tid], a1, a2, c.B);
+    }
+  }
+  __syncthreads();
+}
+
+// forward of the 256-wide first encoder block (input = noised spectra, or the decoder output in the MI phase) on the
+// tensor core: K = dim is consumed in 64-column chunks, each chunk staged hi / lo (K-major SWIZZLE_128B) together with
+// the matching weight chunk, 24 MMAs per chunk accumulating in TMEM; the global loads of chunk c+1 are issued before
+// waiting for the MMAs of chunk c.
+__device__ __noinline__ void fwd_wide_tc(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const LayerIn in = in_ref;
+  RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStFwdWide]);
+  const raae_net_layout& nl = NL(c, net);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, warp = tid >> 5, lane = tid & 31;
+  const int K = nl.in_dim[l];
+  const float* Wg = netp(c, net) + nl.w_off[l];
+  float* Ahi = arena;
+  float* Alo = Ahi + tc::kATileFloats;
+  float* Whi = Alo + tc::kATileFloats;
+  float* Wlo = Whi + tc::kBTileFloats;
+  float* Ot = Wlo + tc::kBTileFloats;              // [kTM][kLD]
+  const int ntiles = (c.B + kTM - 1) / kTM, nchunks = (K + kH - 1) / kH;
+  const uint32_t d_tmem = sm->tmem_base;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(&sm->mbar);
+  __syncthreads();
+  if (tid < kH) {
+    sm->bias[tid] = netp(c, net)[nl.b_off[l] + tid];
+    sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
+    if (!c.train) {
+      sm->mean[net][l][tid] = c.st[nl.rm_off[l] + tid];
+      sm->inv[net][l][tid] = 1.f / sqrtf(c.st[nl.rv_off[l] + tid] + kBnEps);
+    }
+  }
+  __syncthreads();
+  float4 s1v = make_float4(0.f, 0.f, 0.f, 0.f), s2v = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t phase = sm->tc_phase;
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    float4 xa[kTM / 16], wa[4];
+    auto load_chunk = [&](int k0) {
+#pragma unroll
+      for (int i = 0; i < kTM / 16; ++i) {
+        const int r = ty + 16 * i;
+        xa[i] = (r < nv && k0 + c4 < in.dim) ? *reinterpret_cast<const float4*>(in.src + (size_t)(row0 + r) * in.ld + k0 + c4)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {            // W[n][k0 .. k0+63], n = ty + 16 i
+        const int n = ty + 16 * i;
+        wa[i] = (k0 + c4 < K) ? *reinterpret_cast<const float4*>(Wg + (size_t)n * K + k0 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load_chunk(0);
+    for (int ck = 0; ck < nchunks; ++ck) {
+      // stage the chunk held in registers (the previous chunk's MMAs have been waited for)
+#pragma unroll
+      for (int i = 0; i < kTM / 16; ++i) {
+        const int r = ty + 16 * i;
+        float4 o = xa[i];
+        if (r < nv && ck * kH + c4 < in.dim) {
+          if (in.act == 1) { o.x = softplus2_f(o.x); o.y = softplus2_f(o.y); o.z = softplus2_f(o.z); o.w = softplus2_f(o.w); }
+          else if (in.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        }
+        tc::split_store(Ahi, Alo, tc::sw128_chunk_off(r, c4, tc::kABlockBytes), o);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tc::split_store(Whi, Wlo, tc::sw128_chunk_off(ty + 16 * i, c4, tc::kBBlockBytes), wa[i]);
+      tc::fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        tc::issue_gemm_3xtf32_acc(d_tmem, Ahi, Alo, Whi, Wlo, ck > 0 ? 1u : 0u);
+        tc::mma_commit(mbar);
+      }
+      if (ck + 1 < nchunks) load_chunk((ck + 1) * kH);     // global loads in flight while the tensor core works
+      tc::mbar_wait(mbar, phase);
+      phase ^= 1u;
+    }
     tc::fence_after_sync();
     // accumulator -> Ot (+ bias): warp w owns TMEM lanes 32 (w % 4) .. +31 and columns 32 (w / 4) .. +31
     {
@@ -669,10 +836,8 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c, int net, int l, const
         d = prelu_f(uo[i].w, a_sl.w) - sh.w; s1v.w += d; s2v.w = fmaf(d, d, s2v.w);
       }
     }
-    // the next iteration's barrier (after its operand staging) orders these Ot reads before the next Ot writes;
-    // the operand tiles are free again because this iteration waited for its MMAs
+    // next tile: its first barrier (after staging) orders these Ot reads before the next Ot writes
   }
-  cp_async_wait<0>();
   __syncthreads();
   if (tid == 0) sm->tc_phase = phase;
   if (c.train) {
@@ -726,7 +891,9 @@ __device__ __forceinline__ void latent_colstats(SmemFixed* sm, const float* __re
 
 // last encoder Linear (64 -> nstyle) + BatchNorm1d(nstyle).  zE receives the PRE-BN output; the BN
 // statistics go to sm->mean/inv[kE][L-1][0..nstyle).
-__device__ __noinline__ void fwd_enc_last(const Ctx& c, const LayerIn& in) {
+__device__ __noinline__ void fwd_enc_last(const Ctx& c_ref, const LayerIn& in_ref) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStFwdEncLast]);
   const raae_net_layout& nl = NL(c, kE);
@@ -787,6 +954,8 @@ __device__ __forceinline__ void fwd_hidden(const Ctx& c, int net, int l, const L
   if (in.kind == kInHidden) {
     if (c.p->cfg.tensor_cores & 1) fwd_hidden64_tc(c, net, l, in, u_out);
     else fwd_hidden64(c, net, l, in, u_out);
+  } else if (in.kind == kInWide && (c.p->cfg.tensor_cores & 4)) {
+    fwd_wide_tc(c, net, l, in, u_out);
   } else {
     fwd_hidden_edge(c, net, l, in, u_out);
   }
@@ -850,8 +1019,10 @@ __device__ __forceinline__ void decoder_forward_hidden(const Ctx& c, const Layer
 //   in.kind == kInWide   : input rows in.src (K = dim);              dx_out (optional) [rows][ld]: receives
 //                           dL/dx * act'(v) IN PLACE of the pre-activation stored there (MI phase)
 //   in.kind == kInLatent : input latent rows;                        dz_out (optional) [rows][kZ]
-__device__ __noinline__ void bwd_hidden_edge(const Ctx& c, int net, int l, const LayerIn& in, const float* __restrict__ u_l,
+__device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, const float* __restrict__ u_l,
                                              const float* __restrict__ g_in, float* g_out, int o) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[in.kind == kInWide ? kStBwdWide : in.kind == kInHidden ? kStBwdHidden : kStBwdLatent]);
   const raae_net_layout& nl = NL(c, net);
@@ -1082,8 +1253,10 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c, int net, int l, const
 
 // backward of a hidden block whose input is another hidden block's panel (K = 64), software-pipelined: the raw
 // g / u / u_prev tiles of tile t+1 are prefetched with cp.async while tile t runs its two contractions.
-__device__ __noinline__ void bwd_hidden64(const Ctx& c, int net, int l, const LayerIn& in, const float* __restrict__ u_l,
+__device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, const float* __restrict__ u_l,
                                           const float* __restrict__ g_in, float* __restrict__ g_out, int o) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStBwdHidden]);
   const raae_net_layout& nl = NL(c, net);
@@ -1243,8 +1416,10 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c, int net, int l, const La
 // du is staged K-major (SWIZZLE_128B) for the first product and, once that product has completed, re-staged from
 // registers MN-major (SWIZZLE_128B_BASE32B, the only MN-major layout of 32-bit operands) into the same buffer for the
 // second; the input activations are staged MN-major only.  The g_prev epilogue overlaps the dW MMAs.
-__device__ __noinline__ void bwd_hidden64_tc(const Ctx& c, int net, int l, const LayerIn& in, const float* __restrict__ u_l,
+__device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, const float* __restrict__ u_l,
                                              const float* __restrict__ g_in, float* __restrict__ g_out, int o) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStBwdHidden]);
   const raae_net_layout& nl = NL(c, net);
@@ -1293,6 +1468,8 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c, int net, int l, const
   for (int j = 0; j < 32; ++j) { sgv[j] = 0.f; sgxv[j] = 0.f; }
   uint32_t phase = sm->tc_phase;
   const int erow = 32 * (warp & 3) + lane, ecol0 = 32 * (warp >> 2);     // epilogue ownership (TMEM lane, column block)
+  RAAE_PROBE_INIT();
+  RAAE_PROBE(27);
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     // the dW MMAs of the previous tile still read both operand buffers
@@ -1335,6 +1512,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c, int net, int l, const
         tc::split_store(Dhi, Dlo, tc::sw128_chunk_off(r, c4, tc::kABlockBytes), du);
       }
     }
+    RAAE_PROBE(28);
     // 2. the layer's input activations, staged MN-major
     {
       float4 uu[kTM / 16];
@@ -1359,6 +1537,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c, int net, int l, const
     }
     tc::fence_async_smem();
     __syncthreads();
+    RAAE_PROBE(29);
     if (tid == 0) {
       tc::fence_after_sync();
       tc::issue_gemm_3xtf32(d_tmem, Dhi, Dlo, Wthi, Wtlo);                              // g_prev = du W
@@ -1366,6 +1545,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c, int net, int l, const
     }
     tc::mbar_wait(mbar, phase);
     phase ^= 1u;
+    RAAE_PROBE(30);
     // 3. re-stage du MN-major (the K-major copy has been consumed) and start dW += du^T a
 #pragma unroll
     for (int i = 0; i < kTM / 16; ++i)
@@ -1406,6 +1586,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c, int net, int l, const
     }
     tc::fence_before_sync();
     __syncthreads();               // TMEM reads of this tile are ordered before the next tile's first MMA
+    RAAE_PROBE(31);
   }
   tc::mbar_wait(mbar, phase);      // last dW MMAs
   phase ^= 1u;
@@ -1457,16 +1638,20 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c, int net, int l, const
     sm->sgx[tid] = s;
   }
   __syncthreads();
+  RAAE_PROBE(27);
   adam_apply(c, sm, o, net, nl.w_off[l], kH * kH, gradW);
   adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
   adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
   __syncthreads();
+  RAAE_PROBE(22);
 }
 
 // ------------------------------------------------------------------------------------------
 // last encoder layer backward: BN(nstyle) -> Linear(64, nstyle); input gradient for hidden layer L-2
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void bwd_enc_last(const Ctx& c, const LayerIn& in, float* __restrict__ g_out, int o) {
+__device__ __noinline__ void bwd_enc_last(const Ctx& c_ref, const LayerIn& in_ref, float* __restrict__ g_out, int o) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStBwdEncLast]);
   const raae_net_layout& nl = NL(c, kE);

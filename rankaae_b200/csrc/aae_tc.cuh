@@ -111,11 +111,11 @@ __device__ __forceinline__ void split_store(float* hi_base, float* lo_base, uint
   *reinterpret_cast<float4*>(reinterpret_cast<char*>(lo_base) + off_bytes) = l;
 }
 
-// D[128 x 64] (TMEM) = A[128 x 64] * B[64 x 64]^T with the 3 x TF32 split; single thread
-__device__ __forceinline__ void issue_gemm_3xtf32(uint32_t d_tmem, const float* a_hi, const float* a_lo, const float* b_hi,
-                                                  const float* b_lo) {
+// D[128 x 64] (TMEM) (+)= A[128 x 64] * B[64 x 64]^T with the 3 x TF32 split; single thread
+__device__ __forceinline__ void issue_gemm_3xtf32_acc(uint32_t d_tmem, const float* a_hi, const float* a_lo, const float* b_hi,
+                                                      const float* b_lo, uint32_t accumulate_first) {
   const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-  uint32_t first = 0;
+  uint32_t first = accumulate_first;
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
     const uint32_t abase = pass == 0 ? al : ah;           // a_lo b_hi, a_hi b_lo, a_hi b_hi (small terms first)
@@ -129,6 +129,11 @@ __device__ __forceinline__ void issue_gemm_3xtf32(uint32_t d_tmem, const float* 
       first = 1;
     }
   }
+}
+
+__device__ __forceinline__ void issue_gemm_3xtf32(uint32_t d_tmem, const float* a_hi, const float* a_lo, const float* b_hi,
+                                                  const float* b_lo) {
+  issue_gemm_3xtf32_acc(d_tmem, a_hi, a_lo, b_hi, b_lo, 0u);
 }
 
 // D[64 x 64] (TMEM, M = 64 layout) (+)= A^T B over the 128 rows of two [128][64] tiles staged MN-major (SW128_32B),

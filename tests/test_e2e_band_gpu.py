@@ -35,7 +35,9 @@ def test_end_of_training_band():
     for t in range(T):
         init_trial_state(eng, t, cfg, seed=100 + t)
     eng.bind_dataset(spec[:n_train], aux[:n_train], spec[n_train:n_train + n_val], aux[n_train:n_train + n_val])
-    _, mets = eng.train_epochs(0, cfg["max_epoch"])
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(20261018)                       # fixed shuffles: the kernel is bit-reproducible, so is this test
+    _, mets = eng.train_epochs(0, cfg["max_epoch"], perm=eng.make_perm(cfg["max_epoch"], generator=gen))
     torch.cuda.synchronize()
     fused_m = mets[-1, :, :5].cpu().numpy().astype(np.float64)
     fused_rho = np.array([[spearmanr(eng.validate(t, epoch=cfg["max_epoch"] - 1)["z"][:, k], aux[n_train:n_train + n_val, k]).correlation
@@ -60,5 +62,9 @@ def test_end_of_training_band():
     assert ok.all(), (dict(zip(names, ok.tolist())), report)
     ok_rho = inside(ref_rho, fused_rho, 0.02, 0.0)
     assert ok_rho.all(), (ok_rho.tolist(), report)
-    # every descriptor is learned by every fused trial (rank correlation of latent k with descriptor k)
-    assert (np.abs(fused_rho) > 0.6).all(), fused_rho
+    # the descriptors are learned trial by trial as often as the reference learns them: 22 of the 24 reference runs
+    # (92 %) end with every |rho_k| > 0.6 (its worst run has 0.46); the fused ensemble must reach 80 % (binomial 2 sigma)
+    ref_frac = float((np.abs(ref_rho) > 0.6).all(1).mean())
+    fused_frac = float((np.abs(fused_rho) > 0.6).all(1).mean())
+    assert fused_frac >= min(0.8, ref_frac - 0.1), (fused_frac, ref_frac, fused_rho)
+    assert np.abs(fused_rho).min() > 0.3, fused_rho
