@@ -37,6 +37,12 @@ struct ScratchLayout {
   int zs;                       // [rows][kZ]    z_sample (MI phase)
   int rank;                     // [kZ][rows]    validation: per-style ranks (Spearman)
   int xld, vld;                 // padded row strides
+  // tensor-core operand images of the noised batch, written once per step by build_batch and streamed into shared
+  // memory with bulk asynchronous copies (no staging work in the consuming stages); see DESIGN.md
+  int xk;                       // [tiles][nch64][lo/hi: hi 8192 | lo 8192] K-major SWIZZLE_128B blocks (forward of the input layer)
+  int xm;                       // [tiles][nch128][lo 16384 | hi 16384] MN-major SW128_32B blocks (weight gradient of the input layer)
+  int wk;                       // [nch64][hi 4096 | lo 4096] K-major image of the input layer's weights (rebuilt by each forward)
+  int nch64, nch128;
   int total;
 };
 

@@ -21,25 +21,25 @@ __device__ __noinline__ void build_batch(const Ctx& c_ref, const int32_t* __rest
   float* xn = c.sc + p.sl.xn;
   float* aux = c.sc + p.sl.aux;
   float* zs = c.sc + p.sl.zs;
+  float* xk = c.sc + p.sl.xk;
+  float* xm = c.sc + p.sl.xm;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStBatch]);
   __syncthreads();
-  if (c.a->debug) {
-    const raae_debug_io& d = c.a->dbg;
-    for (int i = tid; i < c.B * (dim >> 2); i += kThreads) {
-      int r = i / (dim >> 2), c4 = (i - r * (dim >> 2)) * 4;
-      *reinterpret_cast<float4*>(xn + (size_t)r * xld + c4) = *reinterpret_cast<const float4*>(d.x_noisy + (size_t)r * dim + c4);
-    }
-    for (int i = tid; i < c.B * kZ; i += kThreads) {
-      int r = i >> 3, k = i & 7;
-      aux[i] = k < K ? d.aux[(size_t)r * K + k] : 0.f;
-    }
-  } else {
-    const float sigma = (float)c.hp[RAAE_HP_SPEC_NOISE];
-    const uint32_t key = stream_key(c.seed, c.step_id, kStreamXNoise);
-    for (int i = tid; i < c.B * (dim >> 2); i += kThreads) {
-      int r = i / (dim >> 2), c4 = (i - r * (dim >> 2)) * 4;
-      float4 v = *reinterpret_cast<const float4*>(p.spec_train + (size_t)idx[r] * dim + c4);
+  const bool dbg = c.a->debug != 0;
+  const bool images = (p.cfg.tensor_cores & 4) != 0;
+  const float* xsrc = dbg ? c.a->dbg.x_noisy : p.spec_train;
+  const float sigma = dbg ? 0.f : (float)c.hp[RAAE_HP_SPEC_NOISE];
+  const uint32_t key = stream_key(c.seed, c.step_id, kStreamXNoise);
+  const int nch64 = p.sl.nch64, nch128 = p.sl.nch128;
+  const int q_per_row = images ? nch64 * 16 : (dim >> 2);                 // float4 quads per row (padded to whole 64-col chunks)
+  const int rows_all = images ? ((c.B + kTM - 1) / kTM) * kTM : c.B;      // whole tiles: rows >= B are zero-filled
+  for (int i = tid; i < rows_all * q_per_row; i += kThreads) {
+    const int r = i / q_per_row, c4 = (i - r * q_per_row) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < c.B && c4 < dim) {
+      const size_t srow = dbg ? (size_t)r : (size_t)idx[r];
+      v = *reinterpret_cast<const float4*>(xsrc + srow * dim + c4);
       if (sigma != 0.f) {
         uint32_t e = (uint32_t)(r * kMaxDim + c4);
         v.x += sigma * normal_at(key, e); v.y += sigma * normal_at(key, e + 1);
@@ -47,17 +47,28 @@ __device__ __noinline__ void build_batch(const Ctx& c_ref, const int32_t* __rest
       }
       *reinterpret_cast<float4*>(xn + (size_t)r * xld + c4) = v;
     }
-    for (int i = tid; i < c.B * kZ; i += kThreads) {
-      int r = i >> 3, k = i & 7;
-      aux[i] = k < K ? p.aux_train[(size_t)idx[r] * K + k] : 0.f;
+    if (images) {
+      const int T = r >> 7, rr = r & 127;
+      float* bk = xk + (size_t)(T * nch64 + (c4 >> 6)) * 16384;
+      tc::split_store(bk, bk + 8192, tc::sw128_chunk_off(rr, c4 & 63, tc::kABlockBytes), v);
+      if (c4 < nch128 * 128) {
+        float* bm = xm + (size_t)(T * nch128 + (c4 >> 7)) * 32768;
+        tc::split_store(bm + 16384, bm, tc::sw128_32b_chunk_off(rr, c4 & 127, tc::kABlockBytes), v);
+      }
     }
   }
-  const float* zsp = c.a->debug ? c.a->dbg.z_sample : nullptr;
+  for (int i = tid; i < c.B * kZ; i += kThreads) {
+    int r = i >> 3, k = i & 7;
+    const float* arow = dbg ? c.a->dbg.aux + (size_t)r * K : p.aux_train + (size_t)idx[r] * K;
+    aux[i] = k < K ? arow[k] : 0.f;
+  }
+  const float* zsp = dbg ? c.a->dbg.z_sample : nullptr;
   const uint32_t kz = stream_key(c.seed, c.step_id, kStreamZSample);
   for (int i = tid; i < c.B * kZ; i += kThreads) {
     int r = i >> 3, k = i & 7;
     zs[i] = k < ns ? (zsp ? zsp[(size_t)r * ns + k] : normal_at(kz, (uint32_t)i)) : 0.f;
   }
+  if (images) tc::fence_async_all();     // the images are read by bulk copies (async proxy) in later stages
   __syncthreads();
 }
 
@@ -74,7 +85,8 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask, bool run_p0 =
   }
   __syncthreads();
   if (!run_p0) phase_mask &= ~(1 << kAdv);       // the adversarial phase back-propagates through the P0 forward
-  const LayerIn x = wide_in(c.sc + p.sl.xn, p.sl.xld, p.cfg.dim_in, 0);
+  LayerIn x = wide_in(c.sc + p.sl.xn, p.sl.xld, p.cfg.dim_in, 0);
+  x.img = 1;
   const float* zE = c.sc + p.sl.zE;
   const float* meanZ = sm->mean[kE][LE - 1];
   const float* invZ = sm->inv[kE][LE - 1];
@@ -194,7 +206,9 @@ __device__ __forceinline__ void tc_setup(const KParams& p, SmemFixed* sm) {
   if (threadIdx.x < 32) tc::tmem_alloc(&sm->tmem_base, tc::kTmemCols);
   if (threadIdx.x == 0) {
     tc::mbar_init(reinterpret_cast<uint64_t*>(&sm->mbar), 1);
+    tc::mbar_init(reinterpret_cast<uint64_t*>(&sm->mbar2), 1);
     sm->tc_phase = 0;
+    sm->tc_phase2 = 0;
   }
   tc::fence_before_sync();
   __syncthreads();

@@ -31,6 +31,9 @@ struct SmemFixed {
   float alpha;
   long long prof[32];                   // per-stage-type cycle counters (thread 0), see StageId; 16.. = sub-stage probes
   unsigned long long mbar;              // mbarrier the tcgen05 commits arrive on
+  unsigned long long pipe_bar[8];       // mbarriers of the bulk-copy / MMA pipelines (re-initialised by every stage that uses them)
+  unsigned long long mbar2;             // second mbarrier (double-buffered accumulators of the pipelined forward)
+  uint32_t tc_phase2;                   // parity of the next completion of mbar2
   uint32_t tmem_base;                   // TMEM address returned by tcgen05.alloc
   uint32_t tc_phase;                    // parity of the next mbarrier completion
 };
@@ -268,15 +271,29 @@ __device__ __forceinline__ void adam_apply(const Ctx& c, const SmemFixed* sm, in
   float* M = c.st + ol.m_off + ol.net_off[net] + poff;
   float* V = c.st + ol.v_off + ol.net_off[net] + poff;
   const float decay = sm->ad[0], w1 = sm->ad[1], b2 = sm->ad[2], w2 = sm->ad[3], ss = sm->ad[4], bc2s = sm->ad[5];
-  for (int i = threadIdx.x; i < n; i += kThreads) {
-    float gi = g[i];
-    float pp = P[i] * decay;
-    float m = M[i];
-    m = m + (gi - m) * w1;
-    float v = V[i] * b2 + (w2 * gi) * gi;
-    float denom = sqrtf(v) / bc2s + kAdamEps;
-    pp = pp - ss * (m / denom);
-    P[i] = pp; M[i] = m; V[i] = v;
+  // batches of 8 elements per thread: all 24 loads of a batch are in flight before the first use
+  for (int base = threadIdx.x; base < n; base += kThreads * 8) {
+    float pv[8], mv[8], vv[8], gv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = base + k * kThreads;
+      if (i < n) { pv[k] = P[i]; mv[k] = M[i]; vv[k] = V[i]; gv[k] = g[i]; }
+      else { pv[k] = 0.f; mv[k] = 0.f; vv[k] = 0.f; gv[k] = 0.f; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = base + k * kThreads;
+      if (i < n) {
+        const float gi = gv[k];
+        float pp = pv[k] * decay;
+        float m = mv[k];
+        m = m + (gi - m) * w1;
+        float v = vv[k] * b2 + (w2 * gi) * gi;
+        float denom = sqrtf(v) / bc2s + kAdamEps;
+        pp = pp - ss * (m / denom);
+        P[i] = pp; M[i] = m; V[i] = v;
+      }
+    }
   }
 }
 
@@ -289,6 +306,7 @@ struct LayerIn {
   int kind;
   const float* src;    // hidden: u_prev [rows][64]; wide: [rows][ld]; latent: [rows][kZ]
   int ld, dim, act;    // wide only
+  int img;             // wide only: 1 = the rows are the noised batch, whose operand images exist (ScratchLayout::xk / xm)
   int snet, slayer;    // hidden: BN statistics sm->mean/inv[snet][slayer] of the producing layer;
                        // latent: BN of the encoder output, or slayer < 0 for raw rows
   const float* slope;  // hidden: PReLU slopes (global) of the producing layer
@@ -552,7 +570,11 @@ __device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, cons
   __syncthreads();
 }
 
-// fwd_hidden64 with the contraction on the tensor core (tcgen05.mma kind::tf32, 3 x TF32 split, TMEM accumulator)
+// fwd_hidden64 with the contraction on the tensor core (tcgen05.mma kind::tf32, 3 x TF32 split), software-pipelined over
+// the 128-row tiles: two operand buffers and two TMEM accumulators (columns [0,64) and [64,128)), so the MMAs of tile
+// t+1 run while tile t is read back; the raw pre-activation tile of tile t+2 is in flight (cp.async) meanwhile.
+// The epilogue works in the TMEM layout (thread = row, 32 consecutive columns): bias, store, and the shifted
+// single-pass BatchNorm sums as per-thread partials that are reduced over the rows once per layer.
 __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
   const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
   const LayerIn in = in_ref;
@@ -561,151 +583,165 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   const raae_net_layout& nl = NL(c, net);
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, warp = tid >> 5, lane = tid & 31;
   const float* Wg = netp(c, net) + nl.w_off[l];
-  float* Ahi = arena;                              // [2 K blocks][128 rows][32] swizzled
-  float* Alo = Ahi + tc::kATileFloats;
-  float* Whi = Alo + tc::kATileFloats;             // [2 K blocks][64 rows][32] swizzled
+  float* A0 = arena;                               // operand buffer b: hi at A0 + b * 2 * kATileFloats, lo right after
+  float* Whi = A0 + 4 * tc::kATileFloats;          // [2 K blocks][64 rows][32] swizzled
   float* Wlo = Whi + tc::kBTileFloats;
-  float* Rb[2] = {Wlo + tc::kBTileFloats, Wlo + tc::kBTileFloats + kTile};   // raw prefetch tiles [kTM][kLD]
-  float* Ot = Rb[1] + kTile;                       // [kTM][kLD]
+  float* Raw = Wlo + tc::kBTileFloats;             // raw prefetch tile [kTM][64] (every thread re-reads only what it copied)
   float* slope_in = sm->cg;
-  const float* mean_in = sm->mean[in.snet][in.slayer];
-  const float* inv_in = sm->inv[in.snet][in.slayer];
-  const int ntiles = (c.B + kTM - 1) / kTM;
+  const float* src = in.src;
+  const MaskSrc mk = in.mask;
+  const int B = c.B, train = c.train, ntiles = (B + kTM - 1) / kTM;
   const uint32_t d_tmem = sm->tmem_base;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(&sm->mbar);
+  uint64_t* mbar0 = reinterpret_cast<uint64_t*>(&sm->mbar);
+  uint64_t* mbar1 = reinterpret_cast<uint64_t*>(&sm->mbar2);
   __syncthreads();
-  prefetch_panel_tile(Rb[0], in.src, 0, min(kTM, c.B));
-  cp_async_commit();
-  // W_l [64 n][64 k] -> hi / lo, K-major SWIZZLE_128B
-  for (int i = tid; i < kH * (kH / 4); i += kThreads) {
-    const int n = i >> 4, k4 = (i & 15) * 4;
-    const float4 w = *reinterpret_cast<const float4*>(Wg + (size_t)n * kH + k4);
-    tc::split_store(Whi, Wlo, tc::sw128_chunk_off(n, k4, tc::kBBlockBytes), w);
+  RAAE_PROBE_INIT();
+  auto prefetch_raw = [&](int t) {
+    const int row0 = t * kTM, nv = min(kTM, B - row0);
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      if (r < nv) cp_async16(Raw + r * kH + c4, src + (size_t)(row0 + r) * kH + c4);
+    }
+    cp_async_commit();
+  };
+  prefetch_raw(0);
+  {
+    // W_l [64 n][64 k] -> hi / lo, K-major SWIZZLE_128B
+    float4 w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(Wg + (size_t)(ty + 16 * i) * kH + c4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tc::split_store(Whi, Wlo, tc::sw128_chunk_off(ty + 16 * i, c4, tc::kBBlockBytes), w[i]);
   }
   if (tid < kH) {
     sm->bias[tid] = netp(c, net)[nl.b_off[l] + tid];
     sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
     slope_in[tid] = in.slope[tid];
-    if (!c.train) {
+    if (!train) {
       sm->mean[net][l][tid] = c.st[nl.rm_off[l] + tid];
       sm->inv[net][l][tid] = 1.f / sqrtf(c.st[nl.rv_off[l] + tid] + kBnEps);
     }
   }
   __syncthreads();
-  float4 s1v = make_float4(0.f, 0.f, 0.f, 0.f), s2v = make_float4(0.f, 0.f, 0.f, 0.f);
-  uint32_t phase = sm->tc_phase;
-  RAAE_PROBE_INIT();
-  RAAE_PROBE(22);
-  for (int t = 0; t < ntiles; ++t) {
-    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
-    float* Rt = Rb[t & 1];
-    if (t + 1 < ntiles) prefetch_panel_tile(Rb[(t + 1) & 1], in.src, row0 + kTM, min(kTM, c.B - row0 - kTM));
-    cp_async_commit();
-    cp_async_wait<1>();
-    // transform own elements of the raw tile and stage them as hi / lo tensor-core operands
-    {
-      const float4 mu = *reinterpret_cast<const float4*>(mean_in + c4);
-      const float4 is = *reinterpret_cast<const float4*>(inv_in + c4);
-      const float4 sl = *reinterpret_cast<const float4*>(slope_in + c4);
+  const float4 mu = *reinterpret_cast<const float4*>(sm->mean[in.snet][in.slayer] + c4);
+  const float4 is = *reinterpret_cast<const float4*>(sm->inv[in.snet][in.slayer] + c4);
+  const float4 sl = *reinterpret_cast<const float4*>(slope_in + c4);
+  const uint32_t offK = tc::sw128_chunk_off(ty, c4, tc::kABlockBytes);
+  uint32_t ph0 = sm->tc_phase, ph1 = sm->tc_phase2;
+  // transform the raw tile t (own elements) into the hi / lo operands of buffer t & 1, then start its MMAs
+  auto stage_and_issue = [&](int t) {
+    const int row0 = t * kTM, nv = min(kTM, B - row0);
+    float* Ahi = A0 + (t & 1) * 2 * tc::kATileFloats;
+    float* Alo = Ahi + tc::kATileFloats;
+    cp_async_wait<0>();
+    float4 uu[kTM / 16];
 #pragma unroll
-      for (int i = 0; i < kTM / 16; ++i) {
-        const int r = ty + 16 * i;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nv) {
-          const float4 uu = *reinterpret_cast<const float4*>(Rt + r * kLD + c4);
-          uint32_t kb = mask_keep4(in.mask, row0 + r, c4);
-          o.x = (kb & 1u) ? (prelu_f(uu.x, sl.x) - mu.x) * is.x * in.mask.scale : 0.f;
-          o.y = (kb & 2u) ? (prelu_f(uu.y, sl.y) - mu.y) * is.y * in.mask.scale : 0.f;
-          o.z = (kb & 4u) ? (prelu_f(uu.z, sl.z) - mu.z) * is.z * in.mask.scale : 0.f;
-          o.w = (kb & 8u) ? (prelu_f(uu.w, sl.w) - mu.w) * is.w * in.mask.scale : 0.f;
-        }
-        tc::split_store(Ahi, Alo, tc::sw128_chunk_off(r, c4, tc::kABlockBytes), o);
-      }
-    }
-    tc::fence_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-    RAAE_PROBE(23);
-    if (tid == 0) {
-      tc::fence_after_sync();
-      tc::issue_gemm_3xtf32(d_tmem, Ahi, Alo, Whi, Wlo);
-      tc::mma_commit(mbar);
-    }
-    tc::mbar_wait(mbar, phase);
-    phase ^= 1u;
-    tc::fence_after_sync();
-    RAAE_PROBE(24);
-    // accumulator -> Ot (+ bias): warp w owns TMEM lanes 32 (w % 4) .. +31 and columns 32 (w / 4) .. +31
-    {
-      float v[32];
-      const int row = 32 * (warp & 3) + lane, col0 = 32 * (warp >> 2);
-      tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o = make_float4(v[j] + sm->bias[col0 + j], v[j + 1] + sm->bias[col0 + j + 1], v[j + 2] + sm->bias[col0 + j + 2],
-                               v[j + 3] + sm->bias[col0 + j + 3]);
-        *reinterpret_cast<float4*>(Ot + row * kLD + col0 + j) = o;
-      }
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    RAAE_PROBE(25);
-    const float4 a_sl = *reinterpret_cast<const float4*>(sm->slope + c4);
-    float4 uo[kTM / 16];
-#pragma unroll
-    for (int i = 0; i < kTM / 16; ++i) uo[i] = *reinterpret_cast<const float4*>(Ot + (ty + 16 * i) * kLD + c4);
-    if (c.train && t == 0) {
-      float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < kTM / 16; ++i)
-        if (ty + 16 * i < nv) {
-          sp.x += prelu_f(uo[i].x, a_sl.x); sp.y += prelu_f(uo[i].y, a_sl.y);
-          sp.z += prelu_f(uo[i].z, a_sl.z); sp.w += prelu_f(uo[i].w, a_sl.w);
-        }
-      *reinterpret_cast<float4*>(&sm->red[ty][c4]) = sp;
-      __syncthreads();
-      if (tid < kH) {
-        float sacc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) sacc += sm->red[i][tid];
-        sm->shift[tid] = sacc / (float)nv;
-      }
-      __syncthreads();
-    }
-    const float4 sh = c.train ? *reinterpret_cast<const float4*>(sm->shift + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < kTM / 16; ++i) uu[i] = *reinterpret_cast<const float4*>(Raw + (ty + 16 * i) * kH + c4);
+    if (t + 1 < ntiles) prefetch_raw(t + 1);       // overwrites only this thread's own (already read) elements
 #pragma unroll
     for (int i = 0; i < kTM / 16; ++i) {
       const int r = ty + 16 * i;
-      if (r < nv) {
-        *reinterpret_cast<float4*>(u_out + (size_t)(row0 + r) * kH + c4) = uo[i];
-        float d;
-        d = prelu_f(uo[i].x, a_sl.x) - sh.x; s1v.x += d; s2v.x = fmaf(d, d, s2v.x);
-        d = prelu_f(uo[i].y, a_sl.y) - sh.y; s1v.y += d; s2v.y = fmaf(d, d, s2v.y);
-        d = prelu_f(uo[i].z, a_sl.z) - sh.z; s1v.z += d; s2v.z = fmaf(d, d, s2v.z);
-        d = prelu_f(uo[i].w, a_sl.w) - sh.w; s1v.w += d; s2v.w = fmaf(d, d, s2v.w);
+      const uint32_t kb = r < nv ? mask_keep4(mk, row0 + r, c4) : 0u;
+      float4 o;
+      o.x = (kb & 1u) ? (prelu_f(uu[i].x, sl.x) - mu.x) * is.x * mk.scale : 0.f;
+      o.y = (kb & 2u) ? (prelu_f(uu[i].y, sl.y) - mu.y) * is.y * mk.scale : 0.f;
+      o.z = (kb & 4u) ? (prelu_f(uu[i].z, sl.z) - mu.z) * is.z * mk.scale : 0.f;
+      o.w = (kb & 8u) ? (prelu_f(uu[i].w, sl.w) - mu.w) * is.w * mk.scale : 0.f;
+      tc::split_store(Ahi, Alo, offK + (uint32_t)(i * 16 * 128), o);
+    }
+    tc::fence_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
+    tc::fence_before_sync();             // TMEM reads of tile t-2 (same accumulator) precede these MMAs
+    __syncthreads();
+    RAAE_PROBE(23);
+    if (tc::warp_uniform_id() == 0 && tc::elect_one()) {
+      tc::fence_after_sync();
+      tc::issue_gemm_3xtf32(d_tmem + (uint32_t)(64 * (t & 1)), Ahi, Alo, Whi, Wlo);
+      tc::mma_commit((t & 1) ? mbar1 : mbar0);
+    }
+    RAAE_PROBE(22);
+  };
+  float s1[32], s2[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  const int erow = 32 * (warp & 3) + lane, ecol0 = 32 * (warp >> 2);
+  stage_and_issue(0);
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, B - row0);
+    if (t + 1 < ntiles) stage_and_issue(t + 1);
+    if (t & 1) { tc::mbar_wait(mbar1, ph1); ph1 ^= 1u; }
+    else       { tc::mbar_wait(mbar0, ph0); ph0 ^= 1u; }
+    tc::fence_after_sync();
+    RAAE_PROBE(24);
+    float v[32];
+    tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (t & 1) + ecol0), v);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(sm->bias + ecol0 + j);
+      v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+    }
+    if (erow < nv) {
+      float* urow = u_out + (size_t)(row0 + erow) * kH + ecol0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(urow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    RAAE_PROBE(25);
+    if (train) {
+      if (t == 0) {
+        // shift of the single-pass variance: column means of PReLU(u) over the first tile (operand buffer 0 is free:
+        // its MMAs have completed; buffer 1 may be in use by tile 1)
+        float* colred = A0;               // [256][33]
+#pragma unroll
+        for (int j = 0; j < 32; ++j) colred[tid * 33 + j] = erow < nv ? prelu_f(v[j], sm->slope[ecol0 + j]) : 0.f;
+        __syncthreads();
+        if (tid < kH) {
+          const int cb = tid >> 5, j = tid & 31;
+          float a = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 128; ++r) a += colred[(cb * 128 + r) * 33 + j];
+          sm->shift[tid] = a / (float)nv;
+        }
+        __syncthreads();
+      }
+      if (erow < nv) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 a4 = *reinterpret_cast<const float4*>(sm->slope + ecol0 + j);
+          const float4 sh = *reinterpret_cast<const float4*>(sm->shift + ecol0 + j);
+          float d;
+          d = prelu_f(v[j], a4.x) - sh.x;     s1[j] += d;     s2[j] = fmaf(d, d, s2[j]);
+          d = prelu_f(v[j + 1], a4.y) - sh.y; s1[j + 1] += d; s2[j + 1] = fmaf(d, d, s2[j + 1]);
+          d = prelu_f(v[j + 2], a4.z) - sh.z; s1[j + 2] += d; s2[j + 2] = fmaf(d, d, s2[j + 2]);
+          d = prelu_f(v[j + 3], a4.w) - sh.w; s1[j + 3] += d; s2[j + 3] = fmaf(d, d, s2[j + 3]);
+        }
       }
     }
-    // the next iteration's barrier (after its operand staging) orders these Ot reads before the next Ot writes;
-    // the operand tiles are free again because this iteration waited for its MMAs
     RAAE_PROBE(26);
   }
-  cp_async_wait<0>();
+  tc::fence_before_sync();
   __syncthreads();
-  if (tid == 0) sm->tc_phase = phase;
-  if (c.train) {
-    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s1v;
+  if (tid == 0) { sm->tc_phase = ph0; sm->tc_phase2 = ph1; }
+  if (train) {
+    // column sums of the per-thread (row, 32-column) partials: threads of column block cb are warps 4 cb .. 4 cb + 3
+    float* colred = A0;                 // [256][33]
+#pragma unroll
+    for (int j = 0; j < 32; ++j) colred[tid * 33 + j] = s1[j];
     __syncthreads();
     float a1 = 0.f, a2 = 0.f;
     if (tid < kH) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) a1 += sm->red[i][tid];
+      const int cb = tid >> 5, j = tid & 31;
+#pragma unroll 8
+      for (int r = 0; r < 128; ++r) a1 += colred[(cb * 128 + r) * 33 + j];
     }
     __syncthreads();
-    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s2v;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) colred[tid * 33 + j] = s2[j];
     __syncthreads();
     if (tid < kH) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) a2 += sm->red[i][tid];
-      bn_finalize(c, sm, net, l, tid, sm->shift[tid], a1, a2, c.B);
+      const int cb = tid >> 5, j = tid & 31;
+#pragma unroll 8
+      for (int r = 0; r < 128; ++r) a2 += colred[(cb * 128 + r) * 33 + j];
+      bn_finalize(c, sm, net, l, tid, sm->shift[tid], a1, a2, B);
     }
   }
   __syncthreads();
@@ -777,7 +813,7 @@ __device__ __noinline__ void fwd_wide_tc(const Ctx& c_ref, int net, int l, const
       for (int i = 0; i < 4; ++i) tc::split_store(Whi, Wlo, tc::sw128_chunk_off(ty + 16 * i, c4, tc::kBBlockBytes), wa[i]);
       tc::fence_async_smem();
       __syncthreads();
-      if (tid == 0) {
+      if (tc::warp_uniform_id() == 0 && tc::elect_one()) {
         tc::fence_after_sync();
         tc::issue_gemm_3xtf32_acc(d_tmem, Ahi, Alo, Whi, Wlo, ck > 0 ? 1u : 0u);
         tc::mma_commit(mbar);
@@ -856,6 +892,175 @@ __device__ __noinline__ void fwd_wide_tc(const Ctx& c_ref, int net, int l, const
       for (int i = 0; i < 16; ++i) a2 += sm->red[i][tid];
       bn_finalize(c, sm, net, l, tid, sm->shift[tid], a1, a2, c.B);
     }
+  }
+  __syncthreads();
+}
+
+// column sums over the 32 lanes of a warp: on return lane j holds sum_lanes v[j] (31 shuffles, recursive halving)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// Forward of the input block of the encoder on the noised batch, fed from the operand images (ScratchLayout::xk) that
+// build_batch wrote: no staging work at all.  Warp 0 drives a two-deep pipeline of bulk asynchronous copies (A chunk
+// 64 KB + weight chunk 32 KB per 64 input columns) and the 24 MMAs of every chunk; warps 4..7 read the finished
+// 128 x 64 accumulators back (two TMEM accumulators, so the MMAs of tile t+1 overlap the epilogue of tile t), add the
+// bias, store u and keep the BatchNorm sums per warp with warp-local shifts that are merged exactly at the end.
+__device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, float* __restrict__ u_out) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStFwdWide]);
+  const raae_net_layout& nl = NL(c, net);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = nl.in_dim[l], nch = c.p->sl.nch64;
+  const float* Wg = netp(c, net) + nl.w_off[l];
+  float* wk = c.sc + c.p->sl.wk;
+  const float* xk = c.sc + c.p->sl.xk;
+  float* Abuf = arena;                       // 2 x [hi 8192 | lo 8192]
+  float* Bbuf = arena + 2 * 16384;           // 2 x [hi 4096 | lo 4096]
+  const int B = c.B, train = c.train, ntiles = (B + kTM - 1) / kTM, nitems = ntiles * nch;
+  const uint32_t d_tmem = sm->tmem_base;
+  uint64_t* full = reinterpret_cast<uint64_t*>(&sm->pipe_bar[0]);      // [2] copies landed
+  uint64_t* empty = reinterpret_cast<uint64_t*>(&sm->pipe_bar[2]);     // [2] MMAs of the buffer completed
+  uint64_t* accfull = reinterpret_cast<uint64_t*>(&sm->pipe_bar[4]);   // [2] accumulator complete
+  uint64_t* accfree = reinterpret_cast<uint64_t*>(&sm->pipe_bar[6]);   // [2] accumulator read back (4 warps arrive)
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i) tc::mbar_init(reinterpret_cast<uint64_t*>(&sm->pipe_bar[i]), 1);
+    tc::mbar_init(&accfree[0], 4);
+    tc::mbar_init(&accfree[1], 4);
+  }
+  // K-major hi / lo image of W_l [64][K] in global scratch, one [hi 4096 | lo 4096] block per 64 input columns
+  for (int i = tid; i < kH * nch * 16; i += kThreads) {
+    const int n = i / (nch * 16), k4 = (i - n * (nch * 16)) * 4;
+    const float4 w = k4 < K ? *reinterpret_cast<const float4*>(Wg + (size_t)n * K + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float* blk = wk + (size_t)(k4 >> 6) * 8192;
+    tc::split_store(blk, blk + 4096, tc::sw128_chunk_off(n, k4 & 63, tc::kBBlockBytes), w);
+  }
+  if (tid < kH) {
+    sm->bias[tid] = netp(c, net)[nl.b_off[l] + tid];
+    sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
+    if (!train) {
+      sm->mean[net][l][tid] = c.st[nl.rm_off[l] + tid];
+      sm->inv[net][l][tid] = 1.f / sqrtf(c.st[nl.rv_off[l] + tid] + kBnEps);
+    }
+  }
+  tc::fence_async_all();
+  __syncthreads();
+  const int warp_u = tc::warp_uniform_id();
+  if (warp_u == 0) {
+    if (tc::elect_one()) {
+      auto load_item = [&](int it) {
+        const int b = it & 1, ck = it % nch;
+        tc::mbar_expect_tx(&full[b], 65536u + 32768u);
+        tc::bulk_g2s(Abuf + b * 16384, xk + (size_t)it * 16384, 65536u, &full[b]);     // item order == image order
+        tc::bulk_g2s(Bbuf + b * 8192, wk + (size_t)ck * 8192, 32768u, &full[b]);
+      };
+      load_item(0);
+      if (nitems > 1) load_item(1);
+      for (int it = 0; it < nitems; ++it) {
+        const int b = it & 1, tile = it / nch, ck = it - tile * nch;
+        tc::mbar_wait(&full[b], (uint32_t)((it >> 1) & 1));
+        if (ck == 0 && tile >= 2) tc::mbar_wait(&accfree[tile & 1], (uint32_t)(((tile >> 1) - 1) & 1));
+        tc::fence_after_sync();
+        const float* Ah = Abuf + b * 16384;
+        const float* Bh = Bbuf + b * 8192;
+        tc::issue_gemm_3xtf32_acc(d_tmem + (uint32_t)(64 * (tile & 1)), Ah, Ah + 8192, Bh, Bh + 4096, ck > 0 ? 1u : 0u);
+        tc::mma_commit(&empty[b]);
+        if (ck == nch - 1) tc::mma_commit(&accfull[tile & 1]);
+        if (it + 2 < nitems) {
+          tc::mbar_wait(&empty[b], (uint32_t)((it >> 1) & 1));
+          load_item(it + 2);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_u >= 4) {
+    // epilogue: this thread owns TMEM lane (row) 32 (warp - 4) + lane, both 32-column halves
+    const int erow = 32 * (warp - 4) + lane;
+    float sh[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};     // lane j: columns j and 32 + j
+    int nrows_w = 0;                                                        // rows this warp has accumulated
+    for (int t = 0; t < ntiles; ++t) {
+      const int row0 = t * kTM, nv = min(kTM, B - row0);
+      tc::mbar_wait(&accfull[t & 1], (uint32_t)((t >> 1) & 1));
+      tc::fence_after_sync();
+      const int nvw = max(0, min(32, nv - 32 * (warp - 4)));                // valid rows of this warp in the tile
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[32];
+        tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp - 4)) << 16) + (uint32_t)(64 * (t & 1) + 32 * h), v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(sm->bias + 32 * h + j);
+          v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+        }
+        if (erow < nv) {
+          float* urow = u_out + (size_t)(row0 + erow) * kH + 32 * h;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(urow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (train && nvw > 0) {
+          float pv[32], qv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pv[j] = erow < nv ? prelu_f(v[j], sm->slope[32 * h + j]) : 0.f;
+          if (nrows_w == 0) {
+            // warp-local shift: mean of the warp's first rows
+#pragma unroll
+            for (int j = 0; j < 32; ++j) qv[j] = pv[j];
+            sh[h] = warp_colsum32(qv) / (float)nvw;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float shj = __shfl_sync(0xffffffffu, sh[h], j);
+            const float d = erow < nv ? pv[j] - shj : 0.f;
+            pv[j] = d;
+            qv[j] = d * d;
+          }
+          s1[h] += warp_colsum32(pv);
+          s2[h] += warp_colsum32(qv);
+        }
+      }
+      if (train) nrows_w += nvw;
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&accfree[t & 1])) : "memory");
+    }
+    if (train) {
+      // per-warp (count, mean, M2) of every column -> sm->red rows 0..11
+      const float nw = (float)nrows_w;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float mean_w = nrows_w > 0 ? sh[h] + s1[h] / nw : 0.f;
+        const float m2_w = nrows_w > 0 ? fmaxf(s2[h] - s1[h] * s1[h] / nw, 0.f) : 0.f;
+        sm->red[warp - 4][32 * h + lane] = mean_w;
+        sm->red[4 + warp - 4][32 * h + lane] = m2_w;
+      }
+      if (lane == 0) sm->redw[warp - 4] = nw;
+    }
+  }
+  __syncthreads();
+  if (train && tid < kH) {
+    // exact merge of the four row groups (parallel variance): mean = sum n_w mean_w / n, M2 = sum M2_w + n_w (mean_w - mean)^2
+    const float n = (float)B;
+    float mean = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) mean += sm->redw[w] * sm->red[w][tid];
+    mean /= n;
+    float m2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { const float d = sm->red[w][tid] - mean; m2 += sm->red[4 + w][tid] + sm->redw[w] * d * d; }
+    bn_finalize(c, sm, net, l, tid, mean, 0.f, m2, B);
   }
   __syncthreads();
 }
@@ -954,7 +1159,9 @@ __device__ __forceinline__ void fwd_hidden(const Ctx& c, int net, int l, const L
   if (in.kind == kInHidden) {
     if (c.p->cfg.tensor_cores & 1) fwd_hidden64_tc(c, net, l, in, u_out);
     else fwd_hidden64(c, net, l, in, u_out);
-  } else if (in.kind == kInWide && (c.p->cfg.tensor_cores & 4)) {
+  } else if (in.kind == kInWide && (c.p->cfg.tensor_cores & 4) && in.img) {
+    fwd_wide_img(c, net, l, u_out);
+  } else if (in.kind == kInWide && (c.p->cfg.tensor_cores & 8)) {
     fwd_wide_tc(c, net, l, in, u_out);
   } else {
     fwd_hidden_edge(c, net, l, in, u_out);
@@ -966,7 +1173,7 @@ __device__ __forceinline__ LayerIn hidden_out(const Ctx& c, int net, int l, int 
   LayerIn in;
   in.kind = kInHidden;
   in.src = c.sc + (net == kE ? c.p->sl.uE[l] : c.p->sl.uD[l]);
-  in.ld = kH; in.dim = kH; in.act = 0;
+  in.ld = kH; in.dim = kH; in.act = 0; in.img = 0;
   in.snet = net; in.slayer = l;
   in.slope = netp(c, net) + NL(c, net).a_off[l];
   in.mask = make_mask(c, net, inst, l);
@@ -975,7 +1182,7 @@ __device__ __forceinline__ LayerIn hidden_out(const Ctx& c, int net, int l, int 
 
 __device__ __forceinline__ LayerIn wide_in(const float* src, int ld, int dim, int act) {
   LayerIn in;
-  in.kind = kInWide; in.src = src; in.ld = ld; in.dim = dim; in.act = act;
+  in.kind = kInWide; in.src = src; in.ld = ld; in.dim = dim; in.act = act; in.img = 0;
   in.snet = 0; in.slayer = -1; in.slope = nullptr;
   in.mask.ptr = nullptr; in.mask.key = 0; in.mask.thresh = 0; in.mask.scale = 1.f;
   return in;
@@ -984,7 +1191,7 @@ __device__ __forceinline__ LayerIn wide_in(const float* src, int ld, int dim, in
 // bn_layer >= 0: rows are the pre-BN encoder output, normalised with sm->mean/inv[kE][bn_layer]
 __device__ __forceinline__ LayerIn latent_in(const float* src, int nstyle, int bn_layer) {
   LayerIn in;
-  in.kind = kInLatent; in.src = src; in.ld = kZ; in.dim = nstyle; in.act = 0;
+  in.kind = kInLatent; in.src = src; in.ld = kZ; in.dim = nstyle; in.act = 0; in.img = 0;
   in.snet = kE; in.slayer = bn_layer; in.slope = nullptr;
   in.mask.ptr = nullptr; in.mask.key = 0; in.mask.thresh = 0; in.mask.scale = 1.f;
   return in;
@@ -1414,8 +1621,10 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, cons
 // bwd_hidden64 with both contractions on the tensor core: g_prev = du W (128 x 64 x 64, read back every tile) and
 // dW += du^T a (64 x 64, K = batch rows, accumulated in TMEM over the whole batch and read back once).
 // du is staged K-major (SWIZZLE_128B) for the first product and, once that product has completed, re-staged from
-// registers MN-major (SWIZZLE_128B_BASE32B, the only MN-major layout of 32-bit operands) into the same buffer for the
-// second; the input activations are staged MN-major only.  The g_prev epilogue overlaps the dW MMAs.
+// registers MN-major (SWIZZLE_128B_BASE32B, the only MN-major layout of 32-bit operands; a K-major operand in that
+// swizzle faults, tools/tc_probe.cu variant 5) into the same buffer for the second; the input activations are staged
+// MN-major only.  The g_prev epilogue overlaps the dW MMAs.  All 24 global loads of a tile (g, u_l, u_prev) are issued
+// before the first use, so a tile exposes one memory latency.
 __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, const float* __restrict__ u_l,
                                              const float* __restrict__ g_in, float* __restrict__ g_out, int o) {
   const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
@@ -1432,26 +1641,40 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   float* Wthi = Plo + tc::kATileFloats;                // W^T (K-major): rows = input channel k, K index = output channel n
   float* Wtlo = Wthi + tc::kBTileFloats;
   float* slope_in = sm->shift;
-  const float* mean_in = sm->mean[in.snet][in.slayer];
-  const float* inv_in = sm->inv[in.snet][in.slayer];
-  const int ntiles = (c.B + kTM - 1) / kTM;
+  const float* u_prev = in.src;
+  const MaskSrc mk = in.mask;
+  const int B = c.B, ntiles = (B + kTM - 1) / kTM;
   const uint32_t d_tmem = sm->tmem_base;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(&sm->mbar);
   __syncthreads();
   if (tid < kH) {
-    float nB = (float)c.B;
+    float nB = (float)B;
     sm->cg[tid] = sm->sg[tid] / nB;
     sm->cgx[tid] = sm->sgx[tid] / nB;
     sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
     slope_in[tid] = in.slope[tid];
   }
-  for (int i = tid; i < kH * kH; i += kThreads) {      // W[n][k] -> W^T operand element (row k, column n)
-    const int n = i >> 6, k = i & 63;
-    const float w = Wg[i];
-    const float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
-    const uint32_t off = tc::sw128_chunk_off(k, n & ~3, tc::kBBlockBytes) + (uint32_t)((n & 3) * 4);
-    *reinterpret_cast<float*>(reinterpret_cast<char*>(Wthi) + off) = h;
-    *reinterpret_cast<float*>(reinterpret_cast<char*>(Wtlo) + off) = w - h;
+  {
+    // W[n][k] -> W^T operand element (row k, column n): a warp covers 32 consecutive n of one 4-column group, so the
+    // four transposed scalar stores of a thread land in 32 distinct banks across the warp
+    float4 w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + kThreads * i, n = e & 63, k4 = (e >> 6) * 4;
+      w[i] = *reinterpret_cast<const float4*>(Wg + (size_t)n * kH + k4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + kThreads * i, n = e & 63, k4 = (e >> 6) * 4;
+      const float wv[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float h = __uint_as_float(__float_as_uint(wv[j]) & 0xffffe000u);
+        const uint32_t off = tc::sw128_chunk_off(k4 + j, n & ~3, tc::kBBlockBytes) + (uint32_t)((n & 3) * 4);
+        *reinterpret_cast<float*>(reinterpret_cast<char*>(Wthi) + off) = h;
+        *reinterpret_cast<float*>(reinterpret_cast<char*>(Wtlo) + off) = wv[j] - h;
+      }
+    }
   }
   __syncthreads();
   const float4 mu = *reinterpret_cast<const float4*>(sm->mean[net][l] + c4);
@@ -1459,8 +1682,8 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   const float4 sl = *reinterpret_cast<const float4*>(sm->slope + c4);
   const float4 cg = *reinterpret_cast<const float4*>(sm->cg + c4);
   const float4 cgx = *reinterpret_cast<const float4*>(sm->cgx + c4);
-  const float4 mu_in = *reinterpret_cast<const float4*>(mean_in + c4);
-  const float4 is_in = *reinterpret_cast<const float4*>(inv_in + c4);
+  const float4 mu_in = *reinterpret_cast<const float4*>(sm->mean[in.snet][in.slayer] + c4);
+  const float4 is_in = *reinterpret_cast<const float4*>(sm->inv[in.snet][in.slayer] + c4);
   const float4 sl_in = *reinterpret_cast<const float4*>(slope_in + c4);
   float db4[4] = {0.f, 0.f, 0.f, 0.f}, ds4[4] = {0.f, 0.f, 0.f, 0.f};
   float sgv[32], sgxv[32];                              // this thread's row (mod 128) x 32 columns partial sums
@@ -1468,77 +1691,73 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   for (int j = 0; j < 32; ++j) { sgv[j] = 0.f; sgxv[j] = 0.f; }
   uint32_t phase = sm->tc_phase;
   const int erow = 32 * (warp & 3) + lane, ecol0 = 32 * (warp >> 2);     // epilogue ownership (TMEM lane, column block)
+  // swizzled staging offsets of this thread's chunks: row = ty + 16 i => (row & 7) and (row & 3) do not depend on i
+  const uint32_t offK = tc::sw128_chunk_off(ty, c4, tc::kABlockBytes);          // + i * 16 rows * 128 B
+  const uint32_t offM = tc::sw128_32b_chunk_off(ty, c4, tc::kABlockBytes);
   RAAE_PROBE_INIT();
   RAAE_PROBE(27);
   for (int t = 0; t < ntiles; ++t) {
-    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    const int row0 = t * kTM, nv = min(kTM, B - row0);
+    // ---- all global loads of the tile ----
+    float4 gg[kTM / 16], uu[kTM / 16], up[kTM / 16];
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      const size_t go = (size_t)(row0 + r) * kH + c4;
+      if (r < nv) {
+        gg[i] = *reinterpret_cast<const float4*>(g_in + go);
+        uu[i] = *reinterpret_cast<const float4*>(u_l + go);
+        up[i] = *reinterpret_cast<const float4*>(u_prev + go);
+      } else {
+        gg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        uu[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        up[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     // the dW MMAs of the previous tile still read both operand buffers
     if (t > 0) { tc::mbar_wait(mbar, phase); phase ^= 1u; }
-    // 1. du = PReLU'(u) BN'(g): kept in registers, staged K-major
+    RAAE_PROBE(28);
+    // ---- 1. du = PReLU'(u) BN'(g): kept in registers, staged K-major ----
     float4 dur[kTM / 16];
 #pragma unroll
-    for (int b = 0; b < kTM / 16; b += 4) {
-      float4 gg[4], uu[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = ty + 16 * (b + i);
-        if (r < nv) {
-          gg[i] = *reinterpret_cast<const float4*>(g_in + (size_t)(row0 + r) * kH + c4);
-          uu[i] = *reinterpret_cast<const float4*>(u_l + (size_t)(row0 + r) * kH + c4);
-        } else {
-          gg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          uu[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 g = gg[i], u = uu[i];
+      const bool valid = r < nv;
+#define RAAE_DU(comp, idx)                                                          \
+      {                                                                             \
+        float xh = (prelu_f(u.comp, sl.comp) - mu.comp) * is.comp;                  \
+        float dh = (g.comp - cg.comp - xh * cgx.comp) * is.comp;                    \
+        bool pos = u.comp > 0.f;                                                    \
+        float d = pos ? dh : sl.comp * dh;                                          \
+        d = valid ? d : 0.f;                                                        \
+        du.comp = d;                                                                \
+        ds4[idx] += (pos || !valid) ? 0.f : u.comp * dh;                            \
+        db4[idx] += d;                                                              \
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = ty + 16 * (b + i);
-        float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nv) {
-          const float4 g = gg[i], u = uu[i];
-#define RAAE_DU(comp, idx)                                                        \
-          {                                                                       \
-            float xh = (prelu_f(u.comp, sl.comp) - mu.comp) * is.comp;            \
-            float dh = (g.comp - cg.comp - xh * cgx.comp) * is.comp;              \
-            bool pos = u.comp > 0.f;                                              \
-            du.comp = pos ? dh : sl.comp * dh;                                    \
-            ds4[idx] += pos ? 0.f : u.comp * dh;                                  \
-            db4[idx] += du.comp;                                                  \
-          }
-          RAAE_DU(x, 0) RAAE_DU(y, 1) RAAE_DU(z, 2) RAAE_DU(w, 3)
+      RAAE_DU(x, 0) RAAE_DU(y, 1) RAAE_DU(z, 2) RAAE_DU(w, 3)
 #undef RAAE_DU
-        }
-        dur[b + i] = du;
-        tc::split_store(Dhi, Dlo, tc::sw128_chunk_off(r, c4, tc::kABlockBytes), du);
-      }
+      dur[i] = du;
+      tc::split_store(Dhi, Dlo, offK + (uint32_t)(i * 16 * 128), du);
     }
-    RAAE_PROBE(28);
-    // 2. the layer's input activations, staged MN-major
-    {
-      float4 uu[kTM / 16];
+    // ---- 2. the layer's input activations, staged MN-major ----
 #pragma unroll
-      for (int i = 0; i < kTM / 16; ++i) {
-        const int r = ty + 16 * i;
-        uu[i] = r < nv ? *reinterpret_cast<const float4*>(in.src + (size_t)(row0 + r) * kH + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int i = 0; i < kTM / 16; ++i) {
-        const int r = ty + 16 * i;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nv) {
-          uint32_t kb = mask_keep4(in.mask, row0 + r, c4);
-          a.x = (kb & 1u) ? (prelu_f(uu[i].x, sl_in.x) - mu_in.x) * is_in.x * in.mask.scale : 0.f;
-          a.y = (kb & 2u) ? (prelu_f(uu[i].y, sl_in.y) - mu_in.y) * is_in.y * in.mask.scale : 0.f;
-          a.z = (kb & 4u) ? (prelu_f(uu[i].z, sl_in.z) - mu_in.z) * is_in.z * in.mask.scale : 0.f;
-          a.w = (kb & 8u) ? (prelu_f(uu[i].w, sl_in.w) - mu_in.w) * is_in.w * in.mask.scale : 0.f;
-        }
-        tc::split_store(Phi, Plo, tc::sw128_32b_chunk_off(r, c4, tc::kABlockBytes), a);
-      }
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint32_t kb = r < nv ? mask_keep4(mk, row0 + r, c4) : 0u;
+      a.x = (kb & 1u) ? (prelu_f(up[i].x, sl_in.x) - mu_in.x) * is_in.x * mk.scale : 0.f;
+      a.y = (kb & 2u) ? (prelu_f(up[i].y, sl_in.y) - mu_in.y) * is_in.y * mk.scale : 0.f;
+      a.z = (kb & 4u) ? (prelu_f(up[i].z, sl_in.z) - mu_in.z) * is_in.z * mk.scale : 0.f;
+      a.w = (kb & 8u) ? (prelu_f(up[i].w, sl_in.w) - mu_in.w) * is_in.w * mk.scale : 0.f;
+      tc::split_store(Phi, Plo, offM + (uint32_t)(i * 16 * 128), a);
     }
     tc::fence_async_smem();
+    tc::fence_before_sync();           // TMEM reads of the previous tile's epilogue precede the next MMA
     __syncthreads();
     RAAE_PROBE(29);
-    if (tid == 0) {
+    if (tc::warp_uniform_id() == 0 && tc::elect_one()) {
       tc::fence_after_sync();
       tc::issue_gemm_3xtf32(d_tmem, Dhi, Dlo, Wthi, Wtlo);                              // g_prev = du W
       tc::mma_commit(mbar);
@@ -1546,35 +1765,35 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     tc::mbar_wait(mbar, phase);
     phase ^= 1u;
     RAAE_PROBE(30);
-    // 3. re-stage du MN-major (the K-major copy has been consumed) and start dW += du^T a
+    // ---- 3. re-stage du MN-major (the K-major copy has been consumed) and start dW += du^T a ----
 #pragma unroll
-    for (int i = 0; i < kTM / 16; ++i)
-      tc::split_store(Dhi, Dlo, tc::sw128_32b_chunk_off(ty + 16 * i, c4, tc::kABlockBytes), dur[i]);
+    for (int i = 0; i < kTM / 16; ++i) tc::split_store(Dhi, Dlo, offM + (uint32_t)(i * 16 * 128), dur[i]);
     tc::fence_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (tc::warp_uniform_id() == 0 && tc::elect_one()) {
       tc::fence_after_sync();
       tc::issue_gemm_tn_3xtf32(d_tmem + 64, Dhi, Dlo, Phi, Plo, t > 0 ? 1u : 0u);
       tc::mma_commit(mbar);
     }
     tc::fence_after_sync();
-    // 4. g_prev epilogue (overlaps the dW MMAs): dropout mask of the producing layer, BN-backward partial sums, store
+    // ---- 4. g_prev epilogue (overlaps the dW MMAs): dropout mask of the producing layer, BN-backward partial sums ----
     {
       float v[32];
       tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)ecol0, v);
       if (erow < nv) {
         float* grow = g_out + (size_t)(row0 + erow) * kH + ecol0;
+        const uint32_t abase = (uint32_t)((ecol0 >> 5) * tc::kABlockBytes + erow * 128);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const uint32_t kb = mask_keep4(in.mask, row0 + erow, ecol0 + j);
-          const uint32_t off = tc::sw128_32b_chunk_off(erow, ecol0 + j, tc::kABlockBytes);
+          const uint32_t kb = mask_keep4(mk, row0 + erow, ecol0 + j);
+          const uint32_t off = abase + (uint32_t)((((j >> 3) ^ (erow & 3)) << 5) + ((j & 7) << 2));
           const float4 ah = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Phi) + off);
           const float4 al = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Plo) + off);
           float4 gm;
-          gm.x = (kb & 1u) ? v[j] * in.mask.scale : 0.f;
-          gm.y = (kb & 2u) ? v[j + 1] * in.mask.scale : 0.f;
-          gm.z = (kb & 4u) ? v[j + 2] * in.mask.scale : 0.f;
-          gm.w = (kb & 8u) ? v[j + 3] * in.mask.scale : 0.f;
+          gm.x = (kb & 1u) ? v[j] * mk.scale : 0.f;
+          gm.y = (kb & 2u) ? v[j + 1] * mk.scale : 0.f;
+          gm.z = (kb & 4u) ? v[j + 2] * mk.scale : 0.f;
+          gm.w = (kb & 8u) ? v[j + 3] * mk.scale : 0.f;
           sgv[j] += gm.x; sgv[j + 1] += gm.y; sgv[j + 2] += gm.z; sgv[j + 3] += gm.w;
           sgxv[j] = fmaf(v[j], ah.x + al.x, sgxv[j]);
           sgxv[j + 1] = fmaf(v[j + 1], ah.y + al.y, sgxv[j + 1]);
@@ -1584,9 +1803,10 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
         }
       }
     }
-    tc::fence_before_sync();
-    __syncthreads();               // TMEM reads of this tile are ordered before the next tile's first MMA
     RAAE_PROBE(31);
+    // no barrier here: the next tile overwrites the operand buffers only after it has waited for this tile's dW MMAs,
+    // but its P stores must not overtake the P reads of this epilogue in other warps -> barrier
+    __syncthreads();
   }
   tc::mbar_wait(mbar, phase);      // last dW MMAs
   phase ^= 1u;
@@ -1605,7 +1825,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       if (lane < 16) {
         const int n = 16 * warp + lane;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) gradW[n * kH + 32 * h + j] = v[j];
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(gradW + n * kH + 32 * h + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
     }
   }
@@ -1624,6 +1844,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   if (tid < kH) {
     const int cb = tid >> 5, j = tid & 31;
     float s = 0.f;
+#pragma unroll 8
     for (int r = 0; r < 128; ++r) s += colred[(cb * 128 + r) * 33 + j];
     sm->sg[tid] = s;
   }
@@ -1634,6 +1855,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   if (tid < kH) {
     const int cb = tid >> 5, j = tid & 31;
     float s = 0.f;
+#pragma unroll 8
     for (int r = 0; r < 128; ++r) s += colred[(cb * 128 + r) * 33 + j];
     sm->sgx[tid] = s;
   }
@@ -1643,7 +1865,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
   adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
   __syncthreads();
-  RAAE_PROBE(22);
+  RAAE_PROBE(27);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -14,7 +14,7 @@
 namespace raae {
 namespace tc {
 
-constexpr int kTmemCols = 128;                // [0,64): 128 x 64 accumulator; [64,128): 64 x 64 weight-gradient accumulator
+constexpr int kTmemCols = 512;                // the whole TMEM of the SM (one CTA per SM); every stage carves its own accumulators
 constexpr int kABlockBytes = kTM * 128;       // one 32-float K block of a 128-row operand
 constexpr int kBBlockBytes = kH * 128;        // one 32-float K block of a 64-row operand
 constexpr int kATileFloats = kTM * kH;        // 8192 floats: two K blocks
@@ -34,6 +34,15 @@ __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fenc
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One lane of a converged warp.  Issuing the MMAs from `warp_uniform_id() == 0 && elect_one()` instead of `tid == 0`
+// lets the compiler keep the descriptors in uniform registers (no per-instruction ELECT loop around UTCHMMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int warp_uniform_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -50,6 +59,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   }
 }
+// ---- bulk asynchronous copies global -> shared (UBLKCP), completion counted in bytes on an mbarrier ----
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// generic-proxy writes (to global or shared memory) -> visible to later async-proxy reads (bulk copies, tensor core)
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // arrives on `bar` when every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -153,6 +173,23 @@ __device__ __forceinline__ void issue_gemm_tn_3xtf32(uint32_t d_tmem, const floa
       mma_tf32(d_tmem, da, db, kIdescTf32_TN_64x64, acc);
       acc = 1;
     }
+  }
+}
+
+// D[128 x 64] (TMEM, identity row map) (+)= A^T B with A = [128 rows (K)][128 (M)] as four 32-column blocks `a_block_bytes`
+// apart and B = [128 rows (K)][64 (N)] as two blocks `b_block_bytes` apart, both MN-major SW128_32B; ONE product of the
+// 3 x TF32 split per call (the caller streams the hi / lo halves of A separately); single thread
+constexpr uint32_t kIdescTf32_TN_128x64 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void issue_gemm_tn128_pass(uint32_t d_tmem, const float* a, uint32_t a_block_bytes, const float* b,
+                                                      uint32_t b_block_bytes, uint32_t accumulate_first) {
+  const uint32_t a0 = smem_u32(a), b0 = smem_u32(b);
+  uint32_t acc = accumulate_first;
+#pragma unroll
+  for (int s = 0; s < kTM / 8; ++s) {
+    uint64_t da = make_desc_mn_sw128_32b(a0 + s * 1024, a_block_bytes, 512);
+    uint64_t db = make_desc_mn_sw128_32b(b0 + s * 1024, b_block_bytes, 512);
+    mma_tf32(d_tmem, da, db, kIdescTf32_TN_128x64, acc);
+    acc = 1;
   }
 }
 

@@ -38,7 +38,7 @@ int validate_config(const raae_config& c) {
   if (c.n_trials <= 0) return fail(-1, "n_trials must be positive");
   if (c.max_rows < c.batch_size) return fail(-1, "max_rows must be >= batch_size");
   if (c.ctas_per_trial != 1) return fail(-1, "ctas_per_trial must be 1 in this version");
-  if (c.tensor_cores & ~7) return fail(-1, "tensor_cores: bits 0 (hidden forward), 1 (hidden backward), 2 (256-wide forward) are implemented");
+  if (c.tensor_cores & ~15) return fail(-1, "tensor_cores: bits 0 (hidden forward), 1 (hidden backward), 2 (input block from operand images), 3 (other 256-wide forwards) are implemented");
   return 0;
 }
 
@@ -127,7 +127,14 @@ void build_layout(const raae_config& c, raae_layout& L, raae::ScratchLayout& S) 
   S.g[1] = s; s += rows * H;
   S.zs = s; s += rows * RAAE_ZPAD;
   S.rank = s; s += rows * RAAE_ZPAD;
-  S.total = round4(s);
+  S.nch64 = (c.dim_in + 63) / 64;
+  S.nch128 = (c.dim_in + 127) / 128;
+  const int tiles = (rows + 127) / 128;
+  s = (s + 255) & ~255;                                  // 1 KB alignment of the operand images
+  S.xk = s; s += tiles * S.nch64 * 16384;
+  S.xm = s; s += tiles * S.nch128 * 32768;
+  S.wk = s; s += S.nch64 * 8192;
+  S.total = (s + 255) & ~255;
   L.scratch_floats = S.total;
 }
 

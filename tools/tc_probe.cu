@@ -21,18 +21,20 @@ __global__ void probe(const float* A, const float* B, float* C, int variant) {
   tc::fence_before_sync(); __syncthreads(); tc::fence_after_sync();
   for (int i = tid; i < 128 * 16; i += blockDim.x) {
     int r = i >> 4, c4 = (i & 15) * 4;
-    uint32_t off = variant == 4 ? tc::sw128_chunk_off(r, c4, tc::kABlockBytes) : tc::sw128_32b_chunk_off(r, c4, tc::kABlockBytes);
+    uint32_t off = (variant == 4 || variant == 6) ? tc::sw128_chunk_off(r, c4, tc::kABlockBytes) : tc::sw128_32b_chunk_off(r, c4, tc::kABlockBytes);
+    uint32_t offb = (variant == 4 || variant == 5 || variant == 6) ? tc::sw128_chunk_off(r, c4, tc::kABlockBytes) : off;
     *reinterpret_cast<float4*>(reinterpret_cast<char*>(As) + off) = *reinterpret_cast<const float4*>(A + r * 64 + c4);
-    *reinterpret_cast<float4*>(reinterpret_cast<char*>(Bs) + off) = *reinterpret_cast<const float4*>(B + r * 64 + c4);
+    *reinterpret_cast<float4*>(reinterpret_cast<char*>(Bs) + offb) = *reinterpret_cast<const float4*>(B + r * 64 + c4);
   }
   tc::fence_async_smem(); __syncthreads();
   const uint32_t d = tmem_base;
   if (tid == 0) {
     tc::fence_after_sync();
     uint32_t a0 = tc::smem_u32(As), b0 = tc::smem_u32(Bs);
-    if (variant == 4) {       // known-good K-major product C[128][64] = A[128][64] B[0:64][64]^T
+    if (variant == 4 || variant == 5 || variant == 6) {       // K-major product C[128][64] = A[128][64] B[0:64][64]^T; 5: A staged SW128_32B
       for (int s = 0; s < 8; ++s) {
         uint64_t da = tc::make_desc_k_sw128(a0 + (s >> 2) * tc::kABlockBytes + (s & 3) * 32);
+        if (variant == 5) da = (da & ~((uint64_t)7u << 61)) | ((uint64_t)1u << 61);   // layout type SWIZZLE_128B_BASE32B
         uint64_t db = tc::make_desc_k_sw128(b0 + (s >> 2) * tc::kABlockBytes + (s & 3) * 32);
         tc::mma_tf32(d, da, db, tc::kIdescTf32_128x64, s > 0);
       }
@@ -78,7 +80,15 @@ int main() {
   cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
-  for (int variant = 0; variant < 5; ++variant) {
+  std::vector<float> A2(A), B2(B);
+  for (auto& x : A2) { uint32_t u; memcpy(&u, &x, 4); u |= (uint32_t)(rand() & 0x1fff); memcpy(&x, &u, 4); }
+  for (auto& x : B2) { uint32_t u; memcpy(&u, &x, 4); u |= (uint32_t)(rand() & 0x1fff); memcpy(&x, &u, 4); }
+  for (int variant = 0; variant < 7; ++variant) {
+    if (variant == 5) continue;     // K-major + SW128_32B faults (misaligned address): recorded in aae_step.cuh
+    if (variant == 6) {             // operands with non-zero low mantissa bits: does the tensor core truncate them?
+      cudaMemcpy(dA, A2.data(), A.size() * 4, cudaMemcpyHostToDevice);
+      cudaMemcpy(dB, B2.data(), B.size() * 4, cudaMemcpyHostToDevice);
+    }
     cudaMemset(dC, 0, C.size() * 4);
     probe<<<1, 256, 66 * 1024>>>(dA, dB, dC, variant);
     cudaError_t e = cudaDeviceSynchronize();
@@ -86,10 +96,10 @@ int main() {
     cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost);
     int nz = 0; for (float x : C) nz += x != 0.f;
     printf("variant %d: nonzeros %d  C[0..3] = %g %g %g %g  ref[0..3] = %g %g %g %g\n", variant, nz, C[0], C[1], C[2], C[3], ref[0], ref[1], ref[2], ref[3]);
-    if (variant == 4) {
+    if (variant == 4 || variant == 5 || variant == 6) {
       double err = 0;
       for (int m = 0; m < 128; ++m) for (int n = 0; n < 64; ++n) { double s = 0; for (int k = 0; k < 64; ++k) s += (double)A[m * 64 + k] * B[n * 64 + k]; err = fmax(err, fabs(C[m * 64 + n] - s)); }
-      printf("variant 4 (K-major reference case): max err %.3e\n", err);
+      printf("variant %d (K-major%s): max err vs the product of the TRUNCATED operands %.3e\n", variant, variant == 6 ? ", low mantissa bits set" : " reference case", err);
       continue;
     }
     const int M = (variant & 1) ? 128 : 64;
