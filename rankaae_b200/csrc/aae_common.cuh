@@ -39,9 +39,10 @@ struct ScratchLayout {
   int xld, vld;                 // padded row strides
   // tensor-core operand images of the noised batch, written once per step by build_batch and streamed into shared
   // memory with bulk asynchronous copies (no staging work in the consuming stages); see DESIGN.md
-  int xk;                       // [tiles][nch64][lo/hi: hi 8192 | lo 8192] K-major SWIZZLE_128B blocks (forward of the input layer)
-  int xm;                       // [tiles][nch128][lo 16384 | hi 16384] MN-major SW128_32B blocks (weight gradient of the input layer)
+  int xk;                       // [tiles][nch64][8192] fp32 (batch - xref), K-major SWIZZLE_128B blocks (forward of the input layer)
+  int xm;                       // [tiles][nch128][16384] fp32 (batch - xref), MN-major SW128_32B blocks (weight gradient of the input layer)
   int wk;                       // [nch64][hi 4096 | lo 4096] K-major image of the input layer's weights (rebuilt by each forward)
+  int xref;                     // [kMaxDim] reference row the images are centred on (mean of the first rows of the batch)
   int nch64, nch128;
   int total;
 };

@@ -32,6 +32,35 @@ __device__ __noinline__ void build_batch(const Ctx& c_ref, const int32_t* __rest
   const float sigma = dbg ? 0.f : (float)c.hp[RAAE_HP_SPEC_NOISE];
   const uint32_t key = stream_key(c.seed, c.step_id, kStreamXNoise);
   const int nch64 = p.sl.nch64, nch128 = p.sl.nch128;
+  // Reference row of the operand images: column means over the first (up to 32) rows of the batch.  The tensor core
+  // accumulates with truncation, ~1 ulp of the running sum per MMA; spectra are a large common profile plus small
+  // variations, and BatchNorm then divides by the small spread, so the images hold (row - reference) and the consumers
+  // add reference . W^T (forward) / db (x) reference (weight gradient) back in FP32: exact algebra, 20 x smaller sums.
+  float* xref = c.sc + p.sl.xref;
+  if (images) {
+    const int nref = min(32, c.B), c4 = (tid & 63) * 4, g = tid >> 6;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < dim)
+      for (int r = g; r < nref; r += 4) {
+        const size_t srow = dbg ? (size_t)r : (size_t)idx[r];
+        float4 v = *reinterpret_cast<const float4*>(xsrc + srow * dim + c4);
+        if (sigma != 0.f) {
+          uint32_t e = (uint32_t)(r * kMaxDim + c4);
+          v.x += sigma * normal_at(key, e); v.y += sigma * normal_at(key, e + 1);
+          v.z += sigma * normal_at(key, e + 2); v.w += sigma * normal_at(key, e + 3);
+        }
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    float* red = &sm->red[0][0];                 // [4][256]
+    *reinterpret_cast<float4*>(red + g * 256 + c4) = acc;
+    __syncthreads();
+    {
+      const float s = (red[tid] + red[256 + tid] + red[512 + tid] + red[768 + tid]) / (float)nref;
+      sm->bias[tid] = s;                         // kMaxDim == kThreads == 256
+      xref[tid] = s;
+    }
+    __syncthreads();
+  }
   const int q_per_row = images ? nch64 * 16 : (dim >> 2);                 // float4 quads per row (padded to whole 64-col chunks)
   const int rows_all = images ? ((c.B + kTM - 1) / kTM) * kTM : c.B;      // whole tiles: rows >= B are zero-filled
   for (int i = tid; i < rows_all * q_per_row; i += kThreads) {
@@ -49,11 +78,17 @@ __device__ __noinline__ void build_batch(const Ctx& c_ref, const int32_t* __rest
     }
     if (images) {
       const int T = r >> 7, rr = r & 127;
-      float* bk = xk + (size_t)(T * nch64 + (c4 >> 6)) * 16384;
-      tc::split_store(bk, bk + 8192, tc::sw128_chunk_off(rr, c4 & 63, tc::kABlockBytes), v);
+      if (r < c.B && c4 < dim) {
+        const float4 xr = *reinterpret_cast<const float4*>(sm->bias + c4);
+        v.x -= xr.x; v.y -= xr.y; v.z -= xr.z; v.w -= xr.w;
+      }
+      // raw fp32 in the operand layout: the consumers split it into rounded hi / lo planes in shared memory, so the
+      // batch crosses HBM once per consumer
+      float* bk = xk + (size_t)(T * nch64 + (c4 >> 6)) * 8192;
+      *reinterpret_cast<float4*>(reinterpret_cast<char*>(bk) + tc::sw128_chunk_off(rr, c4 & 63, tc::kABlockBytes)) = v;
       if (c4 < nch128 * 128) {
-        float* bm = xm + (size_t)(T * nch128 + (c4 >> 7)) * 32768;
-        tc::split_store(bm + 16384, bm, tc::sw128_32b_chunk_off(rr, c4 & 127, tc::kABlockBytes), v);
+        float* bm = xm + (size_t)(T * nch128 + (c4 >> 7)) * 16384;
+        *reinterpret_cast<float4*>(reinterpret_cast<char*>(bm) + tc::sw128_32b_chunk_off(rr, c4 & 127, tc::kABlockBytes)) = v;
       }
     }
   }

@@ -31,7 +31,7 @@ struct SmemFixed {
   float alpha;
   long long prof[32];                   // per-stage-type cycle counters (thread 0), see StageId; 16.. = sub-stage probes
   unsigned long long mbar;              // mbarrier the tcgen05 commits arrive on
-  unsigned long long pipe_bar[8];       // mbarriers of the bulk-copy / MMA pipelines (re-initialised by every stage that uses them)
+  unsigned long long pipe_bar[12];       // mbarriers of the bulk-copy / MMA pipelines (re-initialised by every stage that uses them)
   unsigned long long mbar2;             // second mbarrier (double-buffered accumulators of the pipelined forward)
   uint32_t tc_phase2;                   // parity of the next completion of mbar2
   uint32_t tmem_base;                   // TMEM address returned by tcgen05.alloc
@@ -323,6 +323,9 @@ __device__ __forceinline__ void bn_finalize(const Ctx& c, SmemFixed* sm, int net
   float var = fmaxf(s2 / n - d * d, 0.f);
   sm->mean[net][l][ch] = mean;
   sm->inv[net][l][ch] = 1.f / sqrtf(var + kBnEps);
+#ifdef RAAE_DEBUG_STATS
+  if (net == kE && l == 0) { float* dd = c.sc + c.p->sl.rank; dd[ch] = mean; dd[64 + ch] = var; }
+#endif
   float* rm = c.st + nl.rm_off[l];
   float* rv = c.st + nl.rv_off[l];
   float unb = nrows > 1 ? var * (n / (n - 1.f)) : var;
@@ -595,7 +598,6 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   uint64_t* mbar0 = reinterpret_cast<uint64_t*>(&sm->mbar);
   uint64_t* mbar1 = reinterpret_cast<uint64_t*>(&sm->mbar2);
   __syncthreads();
-  RAAE_PROBE_INIT();
   auto prefetch_raw = [&](int t) {
     const int row0 = t * kTM, nv = min(kTM, B - row0);
 #pragma unroll
@@ -653,13 +655,11 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     tc::fence_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
     tc::fence_before_sync();             // TMEM reads of tile t-2 (same accumulator) precede these MMAs
     __syncthreads();
-    RAAE_PROBE(23);
     if (tc::warp_uniform_id() == 0 && tc::elect_one()) {
       tc::fence_after_sync();
       tc::issue_gemm_3xtf32(d_tmem + (uint32_t)(64 * (t & 1)), Ahi, Alo, Whi, Wlo);
       tc::mma_commit((t & 1) ? mbar1 : mbar0);
     }
-    RAAE_PROBE(22);
   };
   float s1[32], s2[32];
 #pragma unroll
@@ -672,7 +672,6 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     if (t & 1) { tc::mbar_wait(mbar1, ph1); ph1 ^= 1u; }
     else       { tc::mbar_wait(mbar0, ph0); ph0 ^= 1u; }
     tc::fence_after_sync();
-    RAAE_PROBE(24);
     float v[32];
     tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (t & 1) + ecol0), v);
 #pragma unroll
@@ -685,7 +684,6 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
 #pragma unroll
       for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(urow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
-    RAAE_PROBE(25);
     if (train) {
       if (t == 0) {
         // shift of the single-pass variance: column means of PReLU(u) over the first tile (operand buffer 0 is free:
@@ -716,7 +714,6 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
         }
       }
     }
-    RAAE_PROBE(26);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -912,11 +909,13 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
   return v[0];
 }
 
-// Forward of the input block of the encoder on the noised batch, fed from the operand images (ScratchLayout::xk) that
-// build_batch wrote: no staging work at all.  Warp 0 drives a two-deep pipeline of bulk asynchronous copies (A chunk
-// 64 KB + weight chunk 32 KB per 64 input columns) and the 24 MMAs of every chunk; warps 4..7 read the finished
-// 128 x 64 accumulators back (two TMEM accumulators, so the MMAs of tile t+1 overlap the epilogue of tile t), add the
-// bias, store u and keep the BatchNorm sums per warp with warp-local shifts that are merged exactly at the end.
+// Forward of the input block of the encoder on the noised batch, fed from the raw K-major operand image
+// (ScratchLayout::xk) that build_batch wrote.  Warp 0 drives a two-deep pipeline of bulk asynchronous copies (raw A chunk
+// 32 KB + weight chunk hi/lo 32 KB per 64 input columns) and the 24 MMAs of every chunk; warps 1..3 split every raw
+// A chunk into its rounded hi (in place) and lo planes in shared memory;
+// warps 4..7 read the finished 128 x 64 accumulators back (two TMEM accumulators, so the MMAs of tile t+1 overlap the
+// epilogue of tile t), add the bias, store u and keep the BatchNorm sums per warp with warp-local shifts that are
+// merged exactly at the end.  HBM traffic: the batch once (the hi/lo split never leaves the SM).
 __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, float* __restrict__ u_out) {
   const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
   RAAE_SMEM();
@@ -927,19 +926,23 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, floa
   const float* Wg = netp(c, net) + nl.w_off[l];
   float* wk = c.sc + c.p->sl.wk;
   const float* xk = c.sc + c.p->sl.xk;
-  float* Abuf = arena;                       // 2 x [hi 8192 | lo 8192]
-  float* Bbuf = arena + 2 * 16384;           // 2 x [hi 4096 | lo 4096]
+  float* Araw = arena;                       // 2 x [8192] raw chunk (= hi operand)
+  float* Alo = arena + 2 * 8192;             // 2 x [8192] lo plane
+  float* Bbuf = arena + 4 * 8192;            // 2 x [hi 4096 | lo 4096]
   const int B = c.B, train = c.train, ntiles = (B + kTM - 1) / kTM, nitems = ntiles * nch;
   const uint32_t d_tmem = sm->tmem_base;
   uint64_t* full = reinterpret_cast<uint64_t*>(&sm->pipe_bar[0]);      // [2] copies landed
   uint64_t* empty = reinterpret_cast<uint64_t*>(&sm->pipe_bar[2]);     // [2] MMAs of the buffer completed
   uint64_t* accfull = reinterpret_cast<uint64_t*>(&sm->pipe_bar[4]);   // [2] accumulator complete
   uint64_t* accfree = reinterpret_cast<uint64_t*>(&sm->pipe_bar[6]);   // [2] accumulator read back (4 warps arrive)
+  uint64_t* conv = reinterpret_cast<uint64_t*>(&sm->pipe_bar[8]);      // [2] lo plane of the buffer written
   __syncthreads();
   if (tid == 0) {
     for (int i = 0; i < 6; ++i) tc::mbar_init(reinterpret_cast<uint64_t*>(&sm->pipe_bar[i]), 1);
     tc::mbar_init(&accfree[0], 4);
     tc::mbar_init(&accfree[1], 4);
+    tc::mbar_init(&conv[0], 1);
+    tc::mbar_init(&conv[1], 1);
   }
   // K-major hi / lo image of W_l [64][K] in global scratch, one [hi 4096 | lo 4096] block per 64 input columns
   for (int i = tid; i < kH * nch * 16; i += kThreads) {
@@ -948,8 +951,21 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, floa
     float* blk = wk + (size_t)(k4 >> 6) * 8192;
     tc::split_store(blk, blk + 4096, tc::sw128_chunk_off(n, k4 & 63, tc::kBBlockBytes), w);
   }
+  {
+    // effective bias: b + W xref (the images are centred on xref); 4 threads per output channel, float64 partial sums
+    const float* xref = c.sc + c.p->sl.xref;
+    const int n = tid >> 2, part = tid & 3;
+    double acc = 0.0;
+    for (int k = part * 4; k < K; k += 16) {
+      const float4 w = *reinterpret_cast<const float4*>(Wg + (size_t)n * K + k);
+      const float4 xr = *reinterpret_cast<const float4*>(xref + k);
+      acc += (double)w.x * xr.x + (double)w.y * xr.y + (double)w.z * xr.z + (double)w.w * xr.w;
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (part == 0) sm->bias[n] = (float)((double)netp(c, net)[nl.b_off[l] + n] + acc);
+  }
   if (tid < kH) {
-    sm->bias[tid] = netp(c, net)[nl.b_off[l] + tid];
     sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
     if (!train) {
       sm->mean[net][l][tid] = c.st[nl.rm_off[l] + tid];
@@ -963,29 +979,62 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, floa
     if (tc::elect_one()) {
       auto load_item = [&](int it) {
         const int b = it & 1, ck = it % nch;
-        tc::mbar_expect_tx(&full[b], 65536u + 32768u);
-        tc::bulk_g2s(Abuf + b * 16384, xk + (size_t)it * 16384, 65536u, &full[b]);     // item order == image order
+        tc::mbar_expect_tx(&full[b], 32768u + 32768u);
+        tc::bulk_g2s(Araw + b * 8192, xk + (size_t)it * 8192, 32768u, &full[b]);       // item order == image order
         tc::bulk_g2s(Bbuf + b * 8192, wk + (size_t)ck * 8192, 32768u, &full[b]);
       };
+      RAAE_PROBE_INIT();
       load_item(0);
       if (nitems > 1) load_item(1);
       for (int it = 0; it < nitems; ++it) {
         const int b = it & 1, tile = it / nch, ck = it - tile * nch;
-        tc::mbar_wait(&full[b], (uint32_t)((it >> 1) & 1));
+        RAAE_PROBE(22);
+        tc::mbar_wait(&conv[b], (uint32_t)((it >> 1) & 1));                             // raw landed and lo derived
+        RAAE_PROBE(23);
         if (ck == 0 && tile >= 2) tc::mbar_wait(&accfree[tile & 1], (uint32_t)(((tile >> 1) - 1) & 1));
         tc::fence_after_sync();
-        const float* Ah = Abuf + b * 16384;
+        RAAE_PROBE(24);
         const float* Bh = Bbuf + b * 8192;
-        tc::issue_gemm_3xtf32_acc(d_tmem + (uint32_t)(64 * (tile & 1)), Ah, Ah + 8192, Bh, Bh + 4096, ck > 0 ? 1u : 0u);
+        tc::issue_gemm_3xtf32_acc(d_tmem + (uint32_t)(64 * (tile & 1)), Araw + b * 8192, Alo + b * 8192, Bh, Bh + 4096,
+                                  ck > 0 ? 1u : 0u);
         tc::mma_commit(&empty[b]);
         if (ck == nch - 1) tc::mma_commit(&accfull[tile & 1]);
+        RAAE_PROBE(25);
         if (it + 2 < nitems) {
           tc::mbar_wait(&empty[b], (uint32_t)((it >> 1) & 1));
           load_item(it + 2);
         }
+        RAAE_PROBE(26);
       }
     }
     __syncwarp();
+  } else if (warp_u < 4) {
+    // converters (96 threads): round-to-nearest hi / lo split, element for element in the swizzled layout
+    const int ctid = tid - 32;
+    for (int it = 0; it < nitems; ++it) {
+      const int b = it & 1;
+      tc::mbar_wait(&full[b], (uint32_t)((it >> 1) & 1));
+      float4* src = reinterpret_cast<float4*>(Araw + b * 8192);     // rounded in place: becomes the hi plane
+      float4* dst = reinterpret_cast<float4*>(Alo + b * 8192);
+      for (int q0 = ctid; q0 < 2048; q0 += 96 * 4) {
+        float4 x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int q = q0 + 96 * k; x[k] = q < 2048 ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int q = q0 + 96 * k;
+          float4 hi, lo;
+          tc::tf32_split(x[k].x, hi.x, lo.x);
+          tc::tf32_split(x[k].y, hi.y, lo.y);
+          tc::tf32_split(x[k].z, hi.z, lo.z);
+          tc::tf32_split(x[k].w, hi.w, lo.w);
+          if (q < 2048) { src[q] = hi; dst[q] = lo; }
+        }
+      }
+      tc::fence_async_smem();
+      asm volatile("bar.sync 2, 96;" ::: "memory");
+      if (ctid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&conv[b])) : "memory");
+    }
   } else if (warp_u >= 4) {
     // epilogue: this thread owns TMEM lane (row) 32 (warp - 4) + lane, both 32-column halves
     const int erow = 32 * (warp - 4) + lane;
@@ -1669,10 +1718,11 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       const float wv[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float h = __uint_as_float(__float_as_uint(wv[j]) & 0xffffe000u);
+        float h, lo;
+        tc::tf32_split(wv[j], h, lo);
         const uint32_t off = tc::sw128_chunk_off(k4 + j, n & ~3, tc::kBBlockBytes) + (uint32_t)((n & 3) * 4);
         *reinterpret_cast<float*>(reinterpret_cast<char*>(Wthi) + off) = h;
-        *reinterpret_cast<float*>(reinterpret_cast<char*>(Wtlo) + off) = wv[j] - h;
+        *reinterpret_cast<float*>(reinterpret_cast<char*>(Wtlo) + off) = lo;
       }
     }
   }

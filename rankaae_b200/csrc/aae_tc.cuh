@@ -121,12 +121,26 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t 
 __device__ __forceinline__ uint32_t sw128_chunk_off(int row, int k, int block_bytes) {
   return (uint32_t)((k >> 5) * block_bytes + row * 128 + ((((k & 31) >> 2) ^ (row & 7)) << 4));
 }
+// Round-to-nearest TF32 split x = hi + lo (+ <= 2^-24 |x|): hi = rna_tf32(x), lo = rna_tf32(x - hi).  The tensor core
+// TRUNCATES the 13 low mantissa bits of its operands (tools/tc_probe.cu variant 6); splitting by truncation leaves a
+// one-sided error of ~2^-21 |x| per operand that adds up coherently over K (measured: 2e-6 absolute on the K = 256
+// input layer, 50 x the FP32-FMA error, enough to fail gradient parity on its low-variance channels), whereas both
+// rounded halves are exact TF32 numbers, so nothing is truncated and the residual has a random sign.
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  hi = tf32_rna(x);
+  lo = tf32_rna(x - hi);
+}
 __device__ __forceinline__ void split_store(float* hi_base, float* lo_base, uint32_t off_bytes, float4 v) {
   float4 h, l;
-  h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-  h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-  h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-  h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+  tf32_split(v.x, h.x, l.x);
+  tf32_split(v.y, h.y, l.y);
+  tf32_split(v.z, h.z, l.z);
+  tf32_split(v.w, h.w, l.w);
   *reinterpret_cast<float4*>(reinterpret_cast<char*>(hi_base) + off_bytes) = h;
   *reinterpret_cast<float4*>(reinterpret_cast<char*>(lo_base) + off_bytes) = l;
 }

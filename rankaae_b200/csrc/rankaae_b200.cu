@@ -131,9 +131,10 @@ void build_layout(const raae_config& c, raae_layout& L, raae::ScratchLayout& S) 
   S.nch128 = (c.dim_in + 127) / 128;
   const int tiles = (rows + 127) / 128;
   s = (s + 255) & ~255;                                  // 1 KB alignment of the operand images
-  S.xk = s; s += tiles * S.nch64 * 16384;
-  S.xm = s; s += tiles * S.nch128 * 32768;
+  S.xk = s; s += tiles * S.nch64 * 8192;
+  S.xm = s; s += tiles * S.nch128 * 16384;
   S.wk = s; s += S.nch64 * 8192;
+  S.xref = s; s += 256;
   S.total = (s + 255) & ~255;
   L.scratch_floats = S.total;
 }

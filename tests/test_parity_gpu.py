@@ -3,6 +3,7 @@
 All tests here need a B200 (`-m gpu`).  Sizes: the committed golden fixtures (B = 200 / 80 with
 batch_size 200, example architecture) and seeded full-size batches (B = 1024 and the ragged 804 of
 the 7000-row example dataset)."""
+import zlib
 import numpy as np
 import pytest
 
@@ -135,7 +136,7 @@ EXAMPLE = dict(
     use_flex_spec_target=True, weight_decay=0.01, kendall_activation=True, epoch_stop_smooth=1500)
 
 
-@pytest.fixture(scope="module", params=[3, 0], ids=["tcgen05", "fp32fma"])
+@pytest.fixture(scope="module", params=[7, 0], ids=["tcgen05", "fp32fma"])
 def example_engine(request, torch_cuda):
     """Both contraction back ends: tcgen05 3xTF32 (default) and the all-FP32-FMA path."""
     eng = _engine(dict(EXAMPLE, tensor_cores=request.param), max_rows=1056)
@@ -263,7 +264,7 @@ def test_config_variants_parity(torch_cuda, name, rows):
     float32 yardstick (parity_util.f32_yardstick)."""
     cfgd = dict(EXAMPLE, batch_size=512, **VARIANTS[name])
     cfg = O.Config.from_dict(cfgd)
-    rng = np.random.default_rng(hash(name) % 1000 + rows)
+    rng = np.random.default_rng(zlib.crc32(name.encode()) % 1000 + rows)   # stable across processes (str hash is salted)
     state = PU.f32_state(O.init_state(cfg, rng))
     for net in ("E", "D", "S"):
         state[net]["a"] = [np.float32(a + rng.uniform(-0.005, 0.3, a.shape)).astype(np.float64) for a in state[net]["a"]]

@@ -44,11 +44,11 @@ for i, n in enumerate(["dec_last: act tile + fwd GEMM", "dec_last: recon loss pa
                        "dec_last: dW (mma_tn8)", "dec_last: g GEMM + epilogue"]):
     v = p[:, 16 + i].mean()
     print(f"    probe {n:30s} {v/1e3:10.1f} kcyc  per tile {v/(8 if 'loss pass' in n else 16):8.0f} cyc")
-for i, n in [(23, "fwd64tc: wait raw + transform + stage (per tile)"), (24, "fwd64tc: MMA issue..complete"), (25, "fwd64tc: TMEM -> Ot"),
-             (26, "fwd64tc: epilogue (store u, stats)"), (28, "bwd64tc: wait prev dW + du pass"), (29, "bwd64tc: act staging"),
-             (30, "bwd64tc: g_prev MMA"), (31, "bwd64tc: restage + dW issue + g epilogue"), (27, "bwd64tc: tail reductions + adam (per call x8)"),
-             (22, "fwd64tc: MMA issue (thread 0)")]:
+for i, n in [(23, "wideimg driver: wait conv (copy + split)"), (24, "wideimg driver: wait accfree"), (25, "wideimg driver: MMA issue"),
+             (26, "wideimg driver: wait empty + next load"), (22, "wideimg driver: loop overhead"),
+             (28, "bwd64tc: wait prev dW + du pass"), (29, "bwd64tc: act staging"),
+             (30, "bwd64tc: g_prev MMA"), (31, "bwd64tc: restage + dW issue + g epilogue"), (27, "bwd64tc: tail reductions + adam (per call x8)")]:
     v = p[:, i].mean()
-    calls_tiles = (34 if 22 <= i < 27 else 21) * 8
-    print(f"    probe {n:50s} {v/1e3:10.1f} kcyc  per tile {v/calls_tiles:8.0f} cyc")
+    calls_tiles = (5 * 32 if 22 <= i < 27 else 21 * 8)
+    print(f"    probe {n:50s} {v/1e3:10.1f} kcyc  per item/tile {v/calls_tiles:8.0f} cyc")
 print(f"  {'(unaccounted)':22s} {(tot - p[:, :15].sum(1).mean())/1e3:10.1f} kcyc")
