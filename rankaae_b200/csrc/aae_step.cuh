@@ -1918,6 +1918,187 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   RAAE_PROBE(27);
 }
 
+// Backward of the input block of the encoder on the noised batch (no input gradient): du = PReLU'(u) BN'(g) per tile,
+// staged MN-major as the A operand; the batch comes from the centred MN-major operand image (ScratchLayout::xm) in
+// 64-column chunks (bulk copy 32 KB, rounded hi / lo split in shared memory), and dW[:, chunk] += du^T x accumulates in
+// four TMEM accumulators (M = 64 layout) over the whole batch.  dW = dWc + db (x) xref undoes the centring.
+__device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, const float* __restrict__ u_l,
+                                          const float* __restrict__ g_in, int o) {
+  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStBwdWide]);
+  const raae_net_layout& nl = NL(c, net);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, warp = tid >> 5, lane = tid & 31;
+  const int K = nl.in_dim[l], nch = c.p->sl.nch64, nch128 = c.p->sl.nch128;
+  const float* xm = c.sc + c.p->sl.xm;
+  float* Dhi = arena;                        // du tile, MN-major
+  float* Dlo = Dhi + 8192;
+  float* Xb = Dlo + 8192;                    // 2 x [hi 8192 | lo 8192] batch chunk, MN-major
+  const int B = c.B, ntiles = (B + kTM - 1) / kTM;
+  const uint32_t d_tmem = sm->tmem_base;
+  uint64_t* full = reinterpret_cast<uint64_t*>(&sm->pipe_bar[0]);      // [2] chunk landed
+  uint64_t* done = reinterpret_cast<uint64_t*>(&sm->pipe_bar[2]);      // [2] MMAs reading the chunk buffer completed
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) tc::mbar_init(reinterpret_cast<uint64_t*>(&sm->pipe_bar[i]), 1);
+  }
+  if (tid < kH) {
+    float nB = (float)B;
+    sm->cg[tid] = sm->sg[tid] / nB;
+    sm->cgx[tid] = sm->sgx[tid] / nB;
+    sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
+  }
+  __syncthreads();
+  const float4 mu = *reinterpret_cast<const float4*>(sm->mean[net][l] + c4);
+  const float4 is = *reinterpret_cast<const float4*>(sm->inv[net][l] + c4);
+  const float4 sl = *reinterpret_cast<const float4*>(sm->slope + c4);
+  const float4 cg = *reinterpret_cast<const float4*>(sm->cg + c4);
+  const float4 cgx = *reinterpret_cast<const float4*>(sm->cgx + c4);
+  float db4[4] = {0.f, 0.f, 0.f, 0.f}, ds4[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t offM = tc::sw128_32b_chunk_off(ty, c4, tc::kABlockBytes);
+  const bool leader = tc::warp_uniform_id() == 0;
+  uint32_t nfull[2] = {0u, 0u}, ndone[2] = {0u, 0u};      // completed phases seen per barrier (parity = count & 1)
+  auto load_chunk = [&](int t, int ck) {                   // elected thread only
+    const int b = ck & 1;
+    tc::mbar_expect_tx(&full[b], 32768u);
+    tc::bulk_g2s(Xb + b * 16384, xm + (size_t)t * nch128 * 16384 + (size_t)ck * 8192, 32768u, &full[b]);
+  };
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, B - row0);
+    if (leader) {
+      if (tc::elect_one()) { load_chunk(t, 0); if (nch > 1) load_chunk(t, 1); }
+      __syncwarp();
+    }
+    // ---- du = PReLU'(u) BN'(g) -> MN-major hi / lo ----
+    float4 gg[kTM / 16], uu[kTM / 16];
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      const size_t go = (size_t)(row0 + r) * kH + c4;
+      if (r < nv) {
+        gg[i] = *reinterpret_cast<const float4*>(g_in + go);
+        uu[i] = *reinterpret_cast<const float4*>(u_l + go);
+      } else {
+        gg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        uu[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 g = gg[i], u = uu[i];
+      const bool valid = r < nv;
+#define RAAE_DU(comp, idx)                                                          \
+      {                                                                             \
+        float xh = (prelu_f(u.comp, sl.comp) - mu.comp) * is.comp;                  \
+        float dh = (g.comp - cg.comp - xh * cgx.comp) * is.comp;                    \
+        bool pos = u.comp > 0.f;                                                    \
+        float d = pos ? dh : sl.comp * dh;                                          \
+        d = valid ? d : 0.f;                                                        \
+        du.comp = d;                                                                \
+        ds4[idx] += (pos || !valid) ? 0.f : u.comp * dh;                            \
+        db4[idx] += d;                                                              \
+      }
+      RAAE_DU(x, 0) RAAE_DU(y, 1) RAAE_DU(z, 2) RAAE_DU(w, 3)
+#undef RAAE_DU
+      tc::split_store(Dhi, Dlo, offM + (uint32_t)(i * 16 * 128), du);
+    }
+    // ---- chunks of 64 input columns ----
+    for (int ck = 0; ck < nch; ++ck) {
+      const int b = ck & 1;
+      tc::mbar_wait(&full[b], nfull[b] & 1u);
+      ++nfull[b];
+      {
+        float4* X = reinterpret_cast<float4*>(Xb + b * 16384);
+        float4 x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = X[tid + kThreads * k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float4 hi, lo;
+          tc::tf32_split(x[k].x, hi.x, lo.x);
+          tc::tf32_split(x[k].y, hi.y, lo.y);
+          tc::tf32_split(x[k].z, hi.z, lo.z);
+          tc::tf32_split(x[k].w, hi.w, lo.w);
+          X[tid + kThreads * k] = hi;
+          X[2048 + tid + kThreads * k] = lo;
+        }
+      }
+      tc::fence_async_smem();
+      __syncthreads();
+      if (leader) {
+        if (tc::elect_one()) {
+          tc::fence_after_sync();
+          const float* Xh = Xb + b * 16384;
+          tc::issue_gemm_tn_3xtf32(d_tmem + (uint32_t)(64 * ck), Dhi, Dlo, Xh, Xh + 8192, t > 0 ? 1u : 0u);
+          tc::mma_commit(&done[b]);
+          // refill the OTHER buffer's successor: chunk ck + 1 is already loaded (or loading); chunk ck + 2 reuses buffer b
+          // once these MMAs have completed, which is waited for at the start of the next chunk of the same parity
+        }
+        __syncwarp();
+      }
+      if (ck + 2 < nch) {
+        // buffer b is needed for chunk ck + 2: wait for the MMAs just issued, then start the copy
+        tc::mbar_wait(&done[b], ndone[b] & 1u);
+        ++ndone[b];
+        if (leader) {
+          if (tc::elect_one()) load_chunk(t, ck + 2);
+          __syncwarp();
+        }
+      }
+    }
+    // all MMAs of the tile must have completed before du is re-staged and the chunk buffers are reloaded
+    for (int ck = max(0, nch - 2); ck < nch; ++ck) {
+      const int b = ck & 1;
+      tc::mbar_wait(&done[b], ndone[b] & 1u);
+      ++ndone[b];
+    }
+  }
+  // ---- weight gradient from the TMEM accumulators (M = 64 layout: row n -> lane 32 (n / 16) + n % 16) ----
+  float* gradW = Xb;                  // dense [64][K]
+  float* gb = Dhi;                    // [64] db | [64] dslope
+  tc::fence_after_sync();
+  __syncthreads();
+  sm->red[ty][c4 + 0] = db4[0]; sm->red[ty][c4 + 1] = db4[1]; sm->red[ty][c4 + 2] = db4[2]; sm->red[ty][c4 + 3] = db4[3];
+  __syncthreads();
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[tid] = s; }
+  __syncthreads();
+  sm->red[ty][c4 + 0] = ds4[0]; sm->red[ty][c4 + 1] = ds4[1]; sm->red[ty][c4 + 2] = ds4[2]; sm->red[ty][c4 + 3] = ds4[3];
+  __syncthreads();
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[kH + tid] = s; }
+  __syncthreads();
+  if (warp < 4) {
+    const float* xref = c.sc + c.p->sl.xref;
+    const int n = 16 * warp + (lane & 15);
+    const float dbn = gb[n];
+    for (int ck = 0; ck < nch; ++ck) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[32];
+        tc::tmem_ld32(d_tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(64 * ck + 32 * h), v);
+        if (lane < 16) {
+          const int k0 = 64 * ck + 32 * h;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (k0 + j < K) {
+              const float4 xr = *reinterpret_cast<const float4*>(xref + k0 + j);
+              *reinterpret_cast<float4*>(gradW + n * K + k0 + j) =
+                  make_float4(fmaf(dbn, xr.x, v[j]), fmaf(dbn, xr.y, v[j + 1]), fmaf(dbn, xr.z, v[j + 2]), fmaf(dbn, xr.w, v[j + 3]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  adam_apply(c, sm, o, net, nl.w_off[l], kH * K, gradW);
+  adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
+  adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------
 // last encoder layer backward: BN(nstyle) -> Linear(64, nstyle); input gradient for hidden layer L-2
 // ------------------------------------------------------------------------------------------
@@ -2030,6 +2211,8 @@ __device__ __forceinline__ void bwd_hidden(const Ctx& c, int net, int l, const L
   if (in.kind == kInHidden && g_out != nullptr) {
     if (c.p->cfg.tensor_cores & 2) bwd_hidden64_tc(c, net, l, in, u_l, g_in, g_out, o);
     else bwd_hidden64(c, net, l, in, u_l, g_in, g_out, o);
+  } else if (in.kind == kInWide && in.img && g_out == nullptr && (c.p->cfg.tensor_cores & 4)) {
+    bwd_wide_img(c, net, l, u_l, g_in, o);
   } else {
     bwd_hidden_edge(c, net, l, in, u_l, g_in, g_out, o);
   }
