@@ -105,6 +105,22 @@ __device__ inline MaskSrc make_mask(const Ctx& c, int net, int inst, int layer) 
   return m;
 }
 
+// column sums over the 32 lanes of a warp: on return lane j holds sum_lanes v[j] (31 shuffles, recursive halving)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
 // ------------------------------------------------------------------------------------------
 // tile builders (global -> transformed smem tile, zero-filled beyond `nv` rows)
 // ------------------------------------------------------------------------------------------
@@ -632,7 +648,7 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   const uint32_t offK = tc::sw128_chunk_off(ty, c4, tc::kABlockBytes);
   uint32_t ph0 = sm->tc_phase, ph1 = sm->tc_phase2;
   // transform the raw tile t (own elements) into the hi / lo operands of buffer t & 1, then start its MMAs
-  auto stage_and_issue = [&](int t) {
+  auto stage = [&](int t) {
     const int row0 = t * kTM, nv = min(kTM, B - row0);
     float* Ahi = A0 + (t & 1) * 2 * tc::kATileFloats;
     float* Alo = Ahi + tc::kATileFloats;
@@ -653,11 +669,12 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       tc::split_store(Ahi, Alo, offK + (uint32_t)(i * 16 * 128), o);
     }
     tc::fence_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
-    tc::fence_before_sync();             // TMEM reads of tile t-2 (same accumulator) precede these MMAs
-    __syncthreads();
+  };
+  auto issue = [&](int t) {              // after a barrier that follows stage(t) and every TMEM read of tile t-2
     if (tc::warp_uniform_id() == 0 && tc::elect_one()) {
+      float* Ahi = A0 + (t & 1) * 2 * tc::kATileFloats;
       tc::fence_after_sync();
-      tc::issue_gemm_3xtf32(d_tmem + (uint32_t)(64 * (t & 1)), Ahi, Alo, Whi, Wlo);
+      tc::issue_gemm_3xtf32(d_tmem + (uint32_t)(64 * (t & 1)), Ahi, Ahi + tc::kATileFloats, Whi, Wlo);
       tc::mma_commit((t & 1) ? mbar1 : mbar0);
     }
   };
@@ -665,15 +682,23 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
 #pragma unroll
   for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   const int erow = 32 * (warp & 3) + lane, ecol0 = 32 * (warp >> 2);
-  stage_and_issue(0);
+  stage(0);
+  __syncthreads();
+  issue(0);
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, B - row0);
-    if (t + 1 < ntiles) stage_and_issue(t + 1);
+    // operands of tile t+1 are staged while the MMAs of tile t run; the accumulator of tile t is read back BEFORE the
+    // MMAs of tile t+1 are queued (a tcgen05.ld issued behind a queued MMA batch waits for it), and the epilogue
+    // arithmetic then overlaps them
+    if (t + 1 < ntiles) stage(t + 1);
     if (t & 1) { tc::mbar_wait(mbar1, ph1); ph1 ^= 1u; }
     else       { tc::mbar_wait(mbar0, ph0); ph0 ^= 1u; }
     tc::fence_after_sync();
     float v[32];
     tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (t & 1) + ecol0), v);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (t + 1 < ntiles) issue(t + 1);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 bb = *reinterpret_cast<const float4*>(sm->bias + ecol0 + j);
@@ -893,22 +918,6 @@ __device__ __noinline__ void fwd_wide_tc(const Ctx& c_ref, int net, int l, const
   __syncthreads();
 }
 
-// column sums over the 32 lanes of a warp: on return lane j holds sum_lanes v[j] (31 shuffles, recursive halving)
-__device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
 // Forward of the input block of the encoder on the noised batch, fed from the raw K-major operand image
 // (ScratchLayout::xk) that build_batch wrote.  Warp 0 drives a two-deep pipeline of bulk asynchronous copies (raw A chunk
 // 32 KB + weight chunk hi/lo 32 KB per 64 input columns) and the 24 MMAs of every chunk; warps 1..3 split every raw
@@ -983,28 +992,22 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, floa
         tc::bulk_g2s(Araw + b * 8192, xk + (size_t)it * 8192, 32768u, &full[b]);       // item order == image order
         tc::bulk_g2s(Bbuf + b * 8192, wk + (size_t)ck * 8192, 32768u, &full[b]);
       };
-      RAAE_PROBE_INIT();
       load_item(0);
       if (nitems > 1) load_item(1);
       for (int it = 0; it < nitems; ++it) {
         const int b = it & 1, tile = it / nch, ck = it - tile * nch;
-        RAAE_PROBE(22);
         tc::mbar_wait(&conv[b], (uint32_t)((it >> 1) & 1));                             // raw landed and lo derived
-        RAAE_PROBE(23);
         if (ck == 0 && tile >= 2) tc::mbar_wait(&accfree[tile & 1], (uint32_t)(((tile >> 1) - 1) & 1));
         tc::fence_after_sync();
-        RAAE_PROBE(24);
         const float* Bh = Bbuf + b * 8192;
         tc::issue_gemm_3xtf32_acc(d_tmem + (uint32_t)(64 * (tile & 1)), Araw + b * 8192, Alo + b * 8192, Bh, Bh + 4096,
                                   ck > 0 ? 1u : 0u);
         tc::mma_commit(&empty[b]);
         if (ck == nch - 1) tc::mma_commit(&accfull[tile & 1]);
-        RAAE_PROBE(25);
         if (it + 2 < nitems) {
           tc::mbar_wait(&empty[b], (uint32_t)((it >> 1) & 1));
           load_item(it + 2);
         }
-        RAAE_PROBE(26);
       }
     }
     __syncwarp();
@@ -1746,10 +1749,11 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   const uint32_t offM = tc::sw128_32b_chunk_off(ty, c4, tc::kABlockBytes);
   RAAE_PROBE_INIT();
   RAAE_PROBE(27);
-  for (int t = 0; t < ntiles; ++t) {
+  // g / u_l of tile t+1 are loaded into registers before the epilogue of tile t (their latency hides behind it);
+  // u_prev of tile t is loaded at the top of the tile and consumed after the du pass
+  float4 gg[kTM / 16], uu[kTM / 16];
+  auto load_gu = [&](int t) {
     const int row0 = t * kTM, nv = min(kTM, B - row0);
-    // ---- all global loads of the tile ----
-    float4 gg[kTM / 16], uu[kTM / 16], up[kTM / 16];
 #pragma unroll
     for (int i = 0; i < kTM / 16; ++i) {
       const int r = ty + 16 * i;
@@ -1757,12 +1761,20 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       if (r < nv) {
         gg[i] = *reinterpret_cast<const float4*>(g_in + go);
         uu[i] = *reinterpret_cast<const float4*>(u_l + go);
-        up[i] = *reinterpret_cast<const float4*>(u_prev + go);
       } else {
         gg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         uu[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        up[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    }
+  };
+  load_gu(0);
+  for (int t = 0; t < ntiles; ++t) {
+    const int row0 = t * kTM, nv = min(kTM, B - row0);
+    float4 up[kTM / 16];
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      up[i] = r < nv ? *reinterpret_cast<const float4*>(u_prev + (size_t)(row0 + r) * kH + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     // the dW MMAs of the previous tile still read both operand buffers
     if (t > 0) { tc::mbar_wait(mbar, phase); phase ^= 1u; }
@@ -1815,41 +1827,51 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     tc::mbar_wait(mbar, phase);
     phase ^= 1u;
     RAAE_PROBE(30);
-    // ---- 3. re-stage du MN-major (the K-major copy has been consumed) and start dW += du^T a ----
+    // ---- 3. read the g_prev accumulator back FIRST (a tcgen05.ld issued behind a queued MMA batch waits for it), then
+    //         re-stage du MN-major (the K-major copy has been consumed) and start dW += du^T a ----
+    float v[32];
+    tc::fence_after_sync();
+    tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)ecol0, v);
+    tc::fence_before_sync();
 #pragma unroll
     for (int i = 0; i < kTM / 16; ++i) tc::split_store(Dhi, Dlo, offM + (uint32_t)(i * 16 * 128), dur[i]);
     tc::fence_async_smem();
     __syncthreads();
+    RAAE_PROBE(22);
     if (tc::warp_uniform_id() == 0 && tc::elect_one()) {
       tc::fence_after_sync();
       tc::issue_gemm_tn_3xtf32(d_tmem + 64, Dhi, Dlo, Phi, Plo, t > 0 ? 1u : 0u);
       tc::mma_commit(mbar);
     }
-    tc::fence_after_sync();
+    RAAE_PROBE(23);
+    if (t + 1 < ntiles) load_gu(t + 1);
     // ---- 4. g_prev epilogue (overlaps the dW MMAs): dropout mask of the producing layer, BN-backward partial sums ----
     {
-      float v[32];
-      tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)ecol0, v);
       if (erow < nv) {
         float* grow = g_out + (size_t)(row0 + erow) * kH + ecol0;
         const uint32_t abase = (uint32_t)((ecol0 >> 5) * tc::kABlockBytes + erow * 128);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const uint32_t kb = mask_keep4(mk, row0 + erow, ecol0 + j);
-          const uint32_t off = abase + (uint32_t)((((j >> 3) ^ (erow & 3)) << 5) + ((j & 7) << 2));
-          const float4 ah = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Phi) + off);
-          const float4 al = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Plo) + off);
-          float4 gm;
-          gm.x = (kb & 1u) ? v[j] * mk.scale : 0.f;
-          gm.y = (kb & 2u) ? v[j + 1] * mk.scale : 0.f;
-          gm.z = (kb & 4u) ? v[j + 2] * mk.scale : 0.f;
-          gm.w = (kb & 8u) ? v[j + 3] * mk.scale : 0.f;
-          sgv[j] += gm.x; sgv[j + 1] += gm.y; sgv[j + 2] += gm.z; sgv[j + 3] += gm.w;
-          sgxv[j] = fmaf(v[j], ah.x + al.x, sgxv[j]);
-          sgxv[j + 1] = fmaf(v[j + 1], ah.y + al.y, sgxv[j + 1]);
-          sgxv[j + 2] = fmaf(v[j + 2], ah.z + al.z, sgxv[j + 2]);
-          sgxv[j + 3] = fmaf(v[j + 3], ah.w + al.w, sgxv[j + 3]);
-          *reinterpret_cast<float4*>(grow + j) = gm;
+        for (int j = 0; j < 32; j += 8) {
+          float gm8[8];
+#pragma unroll
+          for (int q = 0; q < 8; q += 4) {
+            const int jj = j + q;
+            const uint32_t kb = mask_keep4(mk, row0 + erow, ecol0 + jj);
+            const uint32_t off = abase + (uint32_t)((((jj >> 3) ^ (erow & 3)) << 5) + ((jj & 7) << 2));
+            const float4 ah = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Phi) + off);
+            const float4 al = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Plo) + off);
+            gm8[q] = (kb & 1u) ? v[jj] * mk.scale : 0.f;
+            gm8[q + 1] = (kb & 2u) ? v[jj + 1] * mk.scale : 0.f;
+            gm8[q + 2] = (kb & 4u) ? v[jj + 2] * mk.scale : 0.f;
+            gm8[q + 3] = (kb & 8u) ? v[jj + 3] * mk.scale : 0.f;
+            sgv[jj] += gm8[q]; sgv[jj + 1] += gm8[q + 1]; sgv[jj + 2] += gm8[q + 2]; sgv[jj + 3] += gm8[q + 3];
+            sgxv[jj] = fmaf(v[jj], ah.x + al.x, sgxv[jj]);
+            sgxv[jj + 1] = fmaf(v[jj + 1], ah.y + al.y, sgxv[jj + 1]);
+            sgxv[jj + 2] = fmaf(v[jj + 2], ah.z + al.z, sgxv[jj + 2]);
+            sgxv[jj + 3] = fmaf(v[jj + 3], ah.w + al.w, sgxv[jj + 3]);
+          }
+          *reinterpret_cast<float4*>(grow + j) = make_float4(gm8[0], gm8[1], gm8[2], gm8[3]);
+          *reinterpret_cast<float4*>(grow + j + 4) = make_float4(gm8[4], gm8[5], gm8[6], gm8[7]);
         }
       }
     }
@@ -1864,7 +1886,6 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   // ---- weight gradient: TMEM columns [64,128), M = 64 layout (row n -> lane 32 (n / 16) + n % 16) ----
   float* gradW = Phi;                 // dense [64][64]
   float* gb = Dhi;                    // [64] db | [64] dslope
-  float* colred = Plo;                // [256][33] partial sums (8448 floats: Plo + the start of the W^T tiles)
   tc::fence_after_sync();
   __syncthreads();
   if (warp < 4) {
@@ -1887,27 +1908,19 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   sm->red[ty][c4 + 0] = ds4[0]; sm->red[ty][c4 + 1] = ds4[1]; sm->red[ty][c4 + 2] = ds4[2]; sm->red[ty][c4 + 3] = ds4[3];
   __syncthreads();
   if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[kH + tid] = s; }
-  // column sums of the per-thread (row, 32-column) partials: threads of column block cb are warps 4 cb .. 4 cb + 3
-#pragma unroll
-  for (int j = 0; j < 32; ++j) colred[tid * 33 + j] = sgv[j];
-  __syncthreads();
-  if (tid < kH) {
-    const int cb = tid >> 5, j = tid & 31;
-    float s = 0.f;
-#pragma unroll 8
-    for (int r = 0; r < 128; ++r) s += colred[(cb * 128 + r) * 33 + j];
-    sm->sg[tid] = s;
+  // column sums of the per-thread (row, 32-column) partials: warp-level transposing reduction, then the four row
+  // quarters of every column block (warps 4 cb .. 4 cb + 3) are added
+  {
+    const float a = warp_colsum32(sgv);
+    const float b2 = warp_colsum32(sgxv);
+    __syncthreads();                                   // sm->red was read by the slope-gradient reduction above
+    sm->red[warp & 3][ecol0 + lane] = a;
+    sm->red[4 + (warp & 3)][ecol0 + lane] = b2;
   }
   __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 32; ++j) colred[tid * 33 + j] = sgxv[j];
-  __syncthreads();
   if (tid < kH) {
-    const int cb = tid >> 5, j = tid & 31;
-    float s = 0.f;
-#pragma unroll 8
-    for (int r = 0; r < 128; ++r) s += colred[(cb * 128 + r) * 33 + j];
-    sm->sgx[tid] = s;
+    sm->sg[tid] = sm->red[0][tid] + sm->red[1][tid] + sm->red[2][tid] + sm->red[3][tid];
+    sm->sgx[tid] = sm->red[4][tid] + sm->red[5][tid] + sm->red[6][tid] + sm->red[7][tid];
   }
   __syncthreads();
   RAAE_PROBE(27);
