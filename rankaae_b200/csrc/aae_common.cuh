@@ -111,6 +111,18 @@ __device__ __forceinline__ float normal_at(uint32_t key, uint32_t idx) {
   return (idx & 1u) ? r * s : r * c;
 }
 
+// both normals of pair `pair` of a stream: elements 2 pair and 2 pair + 1 of normal_at
+__device__ __forceinline__ void normal_pair(uint32_t key, uint32_t pair, float& n0, float& n1) {
+  uint32_t h1 = hash2(key, 2u * pair), h2 = hash2(key, 2u * pair + 1u);
+  float u1 = ((h1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  float u2 = ((h2 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.28318530717958647692f * u2, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+
 struct MaskSrc {
   const uint8_t* ptr;   // explicit keep-mask [rows][64] or null
   uint32_t key;

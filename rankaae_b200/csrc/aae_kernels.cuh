@@ -46,8 +46,10 @@ __device__ __noinline__ void build_batch(const Ctx& c_ref, const int32_t* __rest
         float4 v = *reinterpret_cast<const float4*>(xsrc + srow * dim + c4);
         if (sigma != 0.f) {
           uint32_t e = (uint32_t)(r * kMaxDim + c4);
-          v.x += sigma * normal_at(key, e); v.y += sigma * normal_at(key, e + 1);
-          v.z += sigma * normal_at(key, e + 2); v.w += sigma * normal_at(key, e + 3);
+          float n0, n1, n2, n3;                    // e is a multiple of 4: two whole Box-Muller pairs
+          normal_pair(key, e >> 1, n0, n1);
+          normal_pair(key, (e >> 1) + 1u, n2, n3);
+          v.x += sigma * n0; v.y += sigma * n1; v.z += sigma * n2; v.w += sigma * n3;
         }
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
@@ -71,8 +73,10 @@ __device__ __noinline__ void build_batch(const Ctx& c_ref, const int32_t* __rest
       v = *reinterpret_cast<const float4*>(xsrc + srow * dim + c4);
       if (sigma != 0.f) {
         uint32_t e = (uint32_t)(r * kMaxDim + c4);
-        v.x += sigma * normal_at(key, e); v.y += sigma * normal_at(key, e + 1);
-        v.z += sigma * normal_at(key, e + 2); v.w += sigma * normal_at(key, e + 3);
+        float n0, n1, n2, n3;
+        normal_pair(key, e >> 1, n0, n1);
+        normal_pair(key, (e >> 1) + 1u, n2, n3);
+        v.x += sigma * n0; v.y += sigma * n1; v.z += sigma * n2; v.w += sigma * n3;
       }
       *reinterpret_cast<float4*>(xn + (size_t)r * xld + c4) = v;
     }

@@ -596,6 +596,40 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
 // ------------------------------------------------------------------------------------------
 constexpr int kKendallChunk = 2048;
 
+// pair loop of one row i against the staged rows j, K descriptors (compile-time so that the loop is branch-free).
+// Per (pair, k): t = sign(d_i - d_j), p = (s_i - s_j) t; accumulated: counts and the sum over the p > 0 pairs, the row's
+// A = sum [p > 0] t and T = sum t.  The p < 0 sums follow from sum_j p = s_i T_i - sum_j s_j t_ij, see the caller.
+template <int K>
+__device__ __forceinline__ void kendall_row(const float* __restrict__ Ss, const float* __restrict__ Ds, int nj, const float (&si)[kZ],
+                                            const float (&di)[kZ], float (&A)[kZ], float (&T)[kZ], float (&fp)[kZ], float (&fa)[kZ],
+                                            int (&cs)[kZ], int (&co)[kZ]) {
+#pragma unroll 2
+  for (int j = 0; j < nj; ++j) {
+    const float4 s0 = *reinterpret_cast<const float4*>(Ss + j * kZ);
+    const float4 d0 = *reinterpret_cast<const float4*>(Ds + j * kZ);
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (K > 4) {
+      s1 = *reinterpret_cast<const float4*>(Ss + j * kZ + 4);
+      d1 = *reinterpret_cast<const float4*>(Ds + j * kZ + 4);
+    }
+    const float sj[kZ] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float dj[kZ] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float dd = di[k] - dj[k];
+      const float tt = dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f);
+      const float p = (si[k] - sj[k]) * tt;
+      const bool pos = p > 0.f, neg = p < 0.f;
+      cs[k] += pos ? 1 : 0;
+      co[k] += neg ? 1 : 0;
+      fp[k] += pos ? p : 0.f;
+      fa[k] += p;
+      A[k] += pos ? tt : 0.f;
+      T[k] += tt;
+    }
+  }
+}
+
 __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __restrict__ aux, int want_grad) {
   const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
   RAAE_SMEM();
@@ -627,44 +661,33 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
     }
     __syncthreads();
     for (int i = tid; i < B; i += kThreads) {
-      float si[kZ], di[kZ], A[kZ], Bn[kZ], fp[kZ], fn[kZ];
+      float si[kZ], di[kZ], A[kZ], T[kZ], fp[kZ], fa[kZ];
 #pragma unroll
       for (int k = 0; k < kZ; ++k) {
         si[k] = k < K ? (zE[(size_t)i * kZ + k] - sm->mean[kE][lE][k]) * sm->inv[kE][lE][k] : 0.f;
         di[k] = k < K ? aux[(size_t)i * kZ + k] : 0.f;
-        A[k] = 0.f; Bn[k] = 0.f; fp[k] = 0.f; fn[k] = 0.f;
+        A[k] = 0.f; T[k] = 0.f; fp[k] = 0.f; fa[k] = 0.f;
       }
-      if (ck > 0 && want_grad) {
+      switch (K) {
+        case 1: kendall_row<1>(Ss, Ds, nj, si, di, A, T, fp, fa, cs, co); break;
+        case 2: kendall_row<2>(Ss, Ds, nj, si, di, A, T, fp, fa, cs, co); break;
+        case 3: kendall_row<3>(Ss, Ds, nj, si, di, A, T, fp, fa, cs, co); break;
+        case 4: kendall_row<4>(Ss, Ds, nj, si, di, A, T, fp, fa, cs, co); break;
+        case 5: kendall_row<5>(Ss, Ds, nj, si, di, A, T, fp, fa, cs, co); break;
+        case 6: kendall_row<6>(Ss, Ds, nj, si, di, A, T, fp, fa, cs, co); break;
+        case 7: kendall_row<7>(Ss, Ds, nj, si, di, A, T, fp, fa, cs, co); break;
+        default: kendall_row<8>(Ss, Ds, nj, si, di, A, T, fp, fa, cs, co); break;
+      }
 #pragma unroll
-        for (int k = 0; k < kZ; ++k) { A[k] = kacc[(size_t)i * 16 + k]; Bn[k] = kacc[(size_t)i * 16 + 8 + k]; }
-      }
-      for (int j = 0; j < nj; ++j) {
-        const float4 s0 = *reinterpret_cast<const float4*>(Ss + j * kZ);
-        const float4 s1 = *reinterpret_cast<const float4*>(Ss + j * kZ + 4);
-        const float4 d0 = *reinterpret_cast<const float4*>(Ds + j * kZ);
-        const float4 d1 = *reinterpret_cast<const float4*>(Ds + j * kZ + 4);
-        const float sj[kZ] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        const float dj[kZ] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      for (int k = 0; k < kZ; ++k) { sp[k] += (double)fp[k]; sn[k] += (double)fa[k] - (double)fp[k]; }
+      if (want_grad) {
+        // A = sum [p > 0] t, Bn = sum [p <= 0] t = T - A, accumulated over the chunks of a large batch
 #pragma unroll
         for (int k = 0; k < kZ; ++k) {
-          if (k >= K) break;
-          float dd = di[k] - dj[k];
-          float tt = dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f);
-          float p = (si[k] - sj[k]) * tt;
-          bool pos = p > 0.f, neg = p < 0.f;
-          cs[k] += pos ? 1 : 0;
-          co[k] += neg ? 1 : 0;
-          fp[k] += pos ? p : 0.f;
-          fn[k] += neg ? p : 0.f;
-          A[k] += pos ? tt : 0.f;
-          Bn[k] += pos ? 0.f : tt;
+          float a = A[k], bn = T[k] - A[k];
+          if (ck > 0) { a += kacc[(size_t)i * 16 + k]; bn += kacc[(size_t)i * 16 + 8 + k]; }
+          kacc[(size_t)i * 16 + k] = a; kacc[(size_t)i * 16 + 8 + k] = bn;
         }
-      }
-#pragma unroll
-      for (int k = 0; k < kZ; ++k) { sp[k] += (double)fp[k]; sn[k] += (double)fn[k]; }
-      if (want_grad) {
-#pragma unroll
-        for (int k = 0; k < kZ; ++k) { kacc[(size_t)i * 16 + k] = A[k]; kacc[(size_t)i * 16 + 8 + k] = Bn[k]; }
       }
     }
   }
