@@ -1121,7 +1121,13 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, floa
 __device__ __forceinline__ void latent_colstats(SmemFixed* sm, const float* __restrict__ z, int nrows) {
   const int tid = threadIdx.x, k = tid & 7, g = tid >> 3;
   float s = 0.f;
-  for (int r = g; r < nrows; r += 32) s += z[(size_t)r * kZ + k];
+  for (int r0 = g; r0 < nrows; r0 += 32 * 8) {            // 8 loads in flight per thread
+    float zv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int r = r0 + 32 * u; zv[u] = r < nrows ? z[(size_t)r * kZ + k] : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += zv[u];
+  }
   float* red = &sm->red[0][0];
   __syncthreads();
   red[tid] = s;
@@ -1134,7 +1140,13 @@ __device__ __forceinline__ void latent_colstats(SmemFixed* sm, const float* __re
   __syncthreads();
   const float mu = sm->zs[0][k];
   s = 0.f;
-  for (int r = g; r < nrows; r += 32) { float d = z[(size_t)r * kZ + k] - mu; s = fmaf(d, d, s); }
+  for (int r0 = g; r0 < nrows; r0 += 32 * 8) {
+    float zv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int r = r0 + 32 * u; zv[u] = r < nrows ? z[(size_t)r * kZ + k] : mu; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const float d = zv[u] - mu; s = fmaf(d, d, s); }
+  }
   __syncthreads();
   red[tid] = s;
   __syncthreads();
@@ -2135,11 +2147,19 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
     const int k = tid & 7, g = tid >> 3;
     const float mu = sm->mean[kE][l][k], is = sm->inv[kE][l][k];
     float s0 = 0.f, s1 = 0.f;
-    for (int r = g; r < c.B; r += 32) {
-      float d = dz[(size_t)r * kZ + k];
-      float zh = (zE[(size_t)r * kZ + k] - mu) * is;
-      s0 += d;
-      s1 = fmaf(d, zh, s1);
+    for (int r0 = g; r0 < c.B; r0 += 32 * 8) {          // 16 loads in flight per thread
+      float dv[8], zv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + 32 * u;
+        dv[u] = r < c.B ? dz[(size_t)r * kZ + k] : 0.f;
+        zv[u] = r < c.B ? zE[(size_t)r * kZ + k] : mu;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        s0 += dv[u];
+        s1 = fmaf(dv[u], (zv[u] - mu) * is, s1);
+      }
     }
     float* red = &sm->red[0][0];
     red[tid] = s0;
@@ -2157,63 +2177,79 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
     Ws[n * kLD + k] = n < ns ? netp(c, kE)[nl.w_off[l] + n * kH + k] : 0.f;
   }
   __syncthreads();
-  float accW[2] = {0.f, 0.f};
+  float accW8[kZ];
+  float wcol[kZ];                      // W[n][ch], n < 8
+#pragma unroll
+  for (int n = 0; n < kZ; ++n) { accW8[n] = 0.f; wcol[n] = Ws[n * kLD + ch]; }
   float accB = 0.f, sgp = 0.f, sgxp = 0.f;
   const int ntiles = (c.B + kTM - 1) / kTM;
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
-    for (int i = tid; i < kTM * kZ; i += kThreads) {
-      int r = i >> 3, k = i & 7;
-      float v = 0.f;
-      if (r < nv && k < ns) {
-        float is = sm->inv[kE][l][k];
-        float zh = (zE[(size_t)(row0 + r) * kZ + k] - sm->mean[kE][l][k]) * is;
-        v = (dz[(size_t)(row0 + r) * kZ + k] - sm->zs[2][k] - zh * sm->zs[3][k]) * is;
+    {
+      // one float4 of zE and of dz per thread (row tid / 2, columns 4 (tid & 1) ..): a single memory latency per tile
+      const int r = tid >> 1, k0 = (tid & 1) * 4;
+      float4 zz = make_float4(0.f, 0.f, 0.f, 0.f), dd = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nv) {
+        zz = *reinterpret_cast<const float4*>(zE + (size_t)(row0 + r) * kZ + k0);
+        dd = *reinterpret_cast<const float4*>(dz + (size_t)(row0 + r) * kZ + k0);
       }
-      D5[i] = v;
+      const float zv[4] = {zz.x, zz.y, zz.z, zz.w}, dv[4] = {dd.x, dd.y, dd.z, dd.w};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k0 + e;
+        const float is = sm->inv[kE][l][k];
+        const float zh = (zv[e] - sm->mean[kE][l][k]) * is;
+        o[e] = (r < nv && k < ns) ? (dv[e] - sm->zs[2][k] - zh * sm->zs[3][k]) * is : 0.f;
+      }
+      *reinterpret_cast<float4*>(D5 + r * kZ + k0) = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {          // dW[n][k], n < 8, k < 64
-      int oo = tid + kThreads * e, n = oo >> 6, k = oo & 63;
-      float s = accW[e];
-      for (int r = 0; r < kTM; ++r) s = fmaf(D5[r * kZ + n], At[r * kLD + k], s);
-      accW[e] = s;
-    }
-    if (tid < kZ) {
-      float s = accB;
-      for (int r = 0; r < kTM; ++r) s += D5[r * kZ + tid];
-      accB = s;
-    }
+    // dW[n][ch] over rows q, q + 4, ...: one activation load and one broadcast row of D5 per 8 FMAs
+    // g_prev[r][ch] = sum_n D5[r][n] W[n][ch] with this thread's weight column held in registers
     for (int i = 0; i < kTM / 4; ++i) {
-      int r = q + 4 * i;
-      if (r < nv) {
-        float gg = 0.f;
+      const int r = q + 4 * i;
+      const float4 d0 = *reinterpret_cast<const float4*>(D5 + r * kZ);
+      const float4 d1 = *reinterpret_cast<const float4*>(D5 + r * kZ + 4);
+      const float dr[kZ] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      const float av = At[r * kLD + ch];
+      float gg = 0.f;
 #pragma unroll
-        for (int n = 0; n < kZ; ++n) gg = fmaf(D5[r * kZ + n], Ws[n * kLD + ch], gg);
+      for (int n = 0; n < kZ; ++n) {
+        accW8[n] = fmaf(dr[n], av, accW8[n]);
+        gg = fmaf(dr[n], wcol[n], gg);
+      }
+      if (ch < kZ) accB += D5[r * kZ + ch];
+      if (r < nv) {
         bool keep = mask_keep(in.mask, row0 + r, ch);
         float gm = keep ? gg * in.mask.scale : 0.f;
         sgp += gm;
-        sgxp = fmaf(gg, At[r * kLD + ch], sgxp);
+        sgxp = fmaf(gg, av, sgxp);
         g_out[(size_t)(row0 + r) * kH + ch] = gm;
       }
     }
     __syncthreads();
   }
+  // reduce the four row groups: dW partials [4][8][64] and bias partials in the At / D5 area (free now)
+  float* part = At;                      // [4][kZ][64]
+#pragma unroll
+  for (int n = 0; n < kZ; ++n) part[(q * kZ + n) * kH + ch] = accW8[n];
   sm->red[q][ch] = sgp;
   sm->red[4 + q][ch] = sgxp;
+  if (ch < kZ) sm->red[8 + q][ch] = accB;
+  __syncthreads();
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     int oo = tid + kThreads * e, n = oo >> 6, k = oo & 63;
-    if (n < ns) gradW[n * kH + k] = accW[e];
+    if (n < ns) gradW[n * kH + k] = part[(0 * kZ + n) * kH + k] + part[(1 * kZ + n) * kH + k] + part[(2 * kZ + n) * kH + k] + part[(3 * kZ + n) * kH + k];
   }
-  if (tid < ns) gradW[kZ * kH + tid] = accB;
-  __syncthreads();
+  if (tid < ns) gradW[kZ * kH + tid] = sm->red[8][tid] + sm->red[9][tid] + sm->red[10][tid] + sm->red[11][tid];
   if (q == 0) {
     sm->sg[ch] = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
     sm->sgx[ch] = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
   }
+  __syncthreads();
   adam_apply(c, sm, o, kE, nl.w_off[l], ns * kH, gradW);
   adam_apply(c, sm, o, kE, nl.b_off[l], ns, gradW + kZ * kH);
   __syncthreads();
