@@ -1,6 +1,8 @@
 // Loss-side stages of the fused AAE step: decoder output layer (+ reconstruction / smoothness losses),
 // style discriminator (+ BCE through the gradient-reversal layer), Kendall rank constraint, latent MSE.
 #pragma once
+#include <type_traits>
+
 #include "aae_step.cuh"
 
 namespace raae {
@@ -28,6 +30,7 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
   float* Y = arena;                         // [kTM][kLDW]
   float* At = Y + kWideTile;                // [kTM][kLD]
   float* Wc = At + kTile;                   // [64][kLD]
+  float* Wc2 = Wc + kWTile;                 // second weight-chunk buffer; aliases the row buffers (loss pass only)
   float* rowbuf = Wc + kWTile + warp * 576; // per warp: ypad[272] | ezp[288]
   float* vpanel = c.sc + c.p->sl.v;
   const int vld = c.p->sl.vld;
@@ -61,16 +64,21 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
     const long long q0 = clock64();
     build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
     if (mode != kLastFromDv) {
-      for (int n0 = 0; n0 < N; n0 += kH) {
+      // weight chunks double-buffered with cp.async (second buffer = the per-warp row buffers, unused during the GEMMs):
+      // the copy of chunk c+1 overlaps the contraction of chunk c, one barrier per chunk
+      prefetch_w_rows64(Wc, kLD, Wg, 0, N);
+      cp_async_commit();
+      for (int n0 = 0, ci = 0; n0 < N; n0 += kH, ++ci) {
+        float* Wcur = (ci & 1) ? Wc2 : Wc;
+        cp_async_wait<0>();
         __syncthreads();
-        load_w_rows(Wc, kLD, Wg, kH, n0, N);
-        __syncthreads();
+        if (n0 + kH < N) { prefetch_w_rows64((ci & 1) ? Wc : Wc2, kLD, Wg, n0 + kH, N); cp_async_commit(); }
         float acc[8][4];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        mma_nt<kH>(At, kLD, Wc, kLD, acc, ty, tx);
+        mma_nt<kH>(At, kLD, Wcur, kLD, acc, ty, tx);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -90,142 +98,165 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
       continue;
     }
     if (mode != kLastFromDv) {
-      // ---- per-row losses and dL/dv; one warp per row, lane owns 8 consecutive columns ----
+      // ---- per-row losses and dL/dv; one warp per row, lane owns 8 consecutive columns.  The row loop is specialised on
+      // (mode, activation, full 256-column rows) so that its unrolled bodies carry no run-time branches ----
+      auto row_pass = [&](auto mode_c, auto act_c, auto full_c) {
+        constexpr int MODE = decltype(mode_c)::value;
+        constexpr int ACT = decltype(act_c)::value;
+        constexpr bool FULL = decltype(full_c)::value;
       float* ypad = rowbuf;
-      float* ezp = rowbuf + 272;
-      const bool need_x = mode == kLastRecon || mode == kLastEval;
-      float xn[8];                  // target row of the NEXT iteration, prefetched one row ahead
+        float* ezp = rowbuf + 272;
+        const bool need_x = (MODE == kLastRecon) || (MODE == kLastEval);
+        float xn[8];                  // target row of the NEXT iteration, prefetched one row ahead
 #pragma unroll
-      for (int e = 0; e < 8; ++e) xn[e] = 0.f;
-      if (need_x && warp < nv) {
-        const float* xrow = c.x + (size_t)(row0 + warp) * c.xld;
+        for (int e = 0; e < 8; ++e) xn[e] = 0.f;
+        if (need_x && warp < nv) {
+          const float* xrow = c.x + (size_t)(row0 + warp) * c.xld;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) xn[e] = (lane * 8 + e < N) ? xrow[lane * 8 + e] : 0.f;
-      }
-      for (int r = warp; r < kTM; r += kThreads / 32) {
-        float* yrow = Y + r * kLDW;
-        const int col0 = lane * 8;
-        if (r >= nv) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) yrow[col0 + e] = 0.f;
-          continue;
+          for (int e = 0; e < 8; ++e) xn[e] = (FULL || lane * 8 + e < N) ? xrow[lane * 8 + e] : 0.f;
         }
-        float x[8];
+        for (int r = warp; r < kTM; r += kThreads / 32) {
+          float* yrow = Y + r * kLDW;
+          const int col0 = lane * 8;
+          if (r >= nv) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = xn[e];
-        if (need_x && r + kThreads / 32 < nv) {
-          const float* xrow = c.x + (size_t)(row0 + r + kThreads / 32) * c.xld;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) xn[e] = (col0 + e < N) ? xrow[col0 + e] : 0.f;
-        }
-        float v[8], y[8], dy[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          v[e] = yrow[col0 + e];
-          y[e] = (col0 + e < N) ? (act == 1 ? softplus2_f(v[e]) : fmaxf(v[e], 0.f)) : 0.f;
-          dy[e] = 0.f;
-        }
-        if (need_x) {
-          float sy = 0.f, sx = 0.f;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { sy += y[e]; sx += x[e]; }
-          float cc = 1.f, dr = 0.f;
-          if (mode == kLastRecon && flex) {
-#pragma unroll
-            for (int of = 16; of > 0; of >>= 1) { sy += __shfl_xor_sync(0xffffffffu, sy, of); sx += __shfl_xor_sync(0xffffffffu, sx, of); }
-            float m_out = sy / nN, m_in = sx / nN;
-            float rr = fabsf(m_out) / fabsf(m_in);
-            cc = fminf(fmaxf(rr, 0.7f), 1.3f);
-            float sgn = m_out > 0.f ? 1.f : (m_out < 0.f ? -1.f : 0.f);
-            dr = (0.2f / nB) * (rr - 1.f) * sgn / (fabsf(m_in) * nN);
-            if (lane == 0) loss_a += 0.1 * (double)((rr - 1.f) * (rr - 1.f)) * inv_B;
+            for (int e = 0; e < 8; ++e) yrow[col0 + e] = 0.f;
+            continue;
           }
-          float sq = 0.f;
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = xn[e];
+          if (need_x && r + kThreads / 32 < nv) {
+            const float* xrow = c.x + (size_t)(row0 + r + kThreads / 32) * c.xld;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xn[e] = (FULL || col0 + e < N) ? xrow[col0 + e] : 0.f;
+          }
+          float v[8], y[8], dy[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            if (col0 + e < N) {
-              float d = y[e] - x[e] * cc;
-              sq = fmaf(d, d, sq);
-              dy[e] = dr + (2.f / (nB * nN)) * d;
-            }
+            v[e] = yrow[col0 + e];
+            y[e] = (FULL || col0 + e < N) ? ((ACT == 1) ? softplus2_f(v[e]) : fmaxf(v[e], 0.f)) : 0.f;
+            dy[e] = 0.f;
           }
-          loss_a += (double)sq * inv_BN;
-        }
-        if (mode == kLastSmooth || mode == kLastEval) {
-          // replicate-padded copy of the row
+          if (need_x) {
+            float sy = 0.f, sx = 0.f;
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (col0 + e < N) ypad[8 + col0 + e] = y[e];
-          __syncwarp();
-          if (lane < 8) { ypad[lane] = ypad[8]; ypad[8 + N + lane] = ypad[8 + N - 1]; }
-          __syncwarp();
-          float ee[8], sq = 0.f;
-          {
-            // sliding window in registers: ypad[col0 .. col0 + 24)
-            float win[24];
+            for (int e = 0; e < 8; ++e) { sy += y[e]; sx += x[e]; }
+            float cc = 1.f, dr = 0.f;
+            if ((MODE == kLastRecon) && flex) {
 #pragma unroll
-            for (int q4 = 0; q4 < 6; ++q4) {
-              float4 t4 = *reinterpret_cast<const float4*>(ypad + col0 + 4 * q4);
-              win[4 * q4] = t4.x; win[4 * q4 + 1] = t4.y; win[4 * q4 + 2] = t4.z; win[4 * q4 + 3] = t4.w;
+              for (int of = 16; of > 0; of >>= 1) { sy += __shfl_xor_sync(0xffffffffu, sy, of); sx += __shfl_xor_sync(0xffffffffu, sx, of); }
+              float m_out = sy / nN, m_in = sx / nN;
+              float rr = fabsf(m_out) / fabsf(m_in);
+              cc = fminf(fmaxf(rr, 0.7f), 1.3f);
+              float sgn = m_out > 0.f ? 1.f : (m_out < 0.f ? -1.f : 0.f);
+              dr = (0.2f / nB) * (rr - 1.f) * sgn / (fabsf(m_in) * nN);
+              if (lane == 0) loss_a += 0.1 * (double)((rr - 1.f) * (rr - 1.f)) * inv_B;
             }
+            float sq = 0.f;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              ee[e] = 0.f;
-              if (col0 + e < N) {
-                float s = 0.f;
-#pragma unroll
-                for (int k = 0; k < 17; ++k) s = fmaf(kGauss17[k], win[e + k], s);
-                ee[e] = y[e] - s;
-                sq = fmaf(ee[e], ee[e], sq);
+              if (FULL || col0 + e < N) {
+                float d = y[e] - x[e] * cc;
+                sq = fmaf(d, d, sq);
+                dy[e] = dr + (2.f / (nB * nN)) * d;
               }
             }
+            loss_a += (double)sq * inv_BN;
           }
-          loss_b += (double)sq * inv_BN;
-          if (mode == kLastSmooth) {
-            // adjoint: zero-padded full correlation of e with the taps, overhang folded into the end points
-            if (lane < 16) { ezp[lane] = 0.f; ezp[16 + N + lane] = 0.f; }
+          if ((MODE == kLastSmooth) || (MODE == kLastEval)) {
+            // replicate-padded copy of the row
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              if (col0 + e < N) ezp[16 + col0 + e] = ee[e];
+              if (FULL || col0 + e < N) ypad[8 + col0 + e] = y[e];
             __syncwarp();
+            if (lane < 8) { ypad[lane] = ypad[8]; ypad[8 + N + lane] = ypad[8 + N - 1]; }
+            __syncwarp();
+            float ee[8], sq = 0.f;
             {
-              // (K^T e)[j + 8] = sum_t w[t] e[j + 8 - t] = sum_m w[m] ezp[j + 8 + m]  (taps symmetric, ezp[16 + i] = e[i])
+              // sliding window in registers: ypad[col0 .. col0 + 24)
               float win[24];
 #pragma unroll
               for (int q4 = 0; q4 < 6; ++q4) {
-                float4 t4 = *reinterpret_cast<const float4*>(ezp + col0 + 8 + 4 * q4);
+                float4 t4 = *reinterpret_cast<const float4*>(ypad + col0 + 4 * q4);
                 win[4 * q4] = t4.x; win[4 * q4 + 1] = t4.y; win[4 * q4 + 2] = t4.z; win[4 * q4 + 3] = t4.w;
               }
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const int j = col0 + e;
-                if (j < N) {
-                  float kt = 0.f;
+                ee[e] = 0.f;
+                if (FULL || col0 + e < N) {
+                  float s = 0.f;
 #pragma unroll
-                  for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], win[e + k], kt);
-                  // overhang of the replicate padding: sum_{i<8} (K^T e)[i] = sum_{m<8} e[m] P[7-m] folds into y[0],
-                  // and by symmetry sum_{q<8} e[N-1-q] P[7-q] into y[N-1]
-                  if (j == 0) {
-#pragma unroll
-                    for (int m = 0; m < 8; ++m) kt = fmaf(tapP[7 - m], ezp[16 + m], kt);
-                  }
-                  if (j == N - 1) {
-#pragma unroll
-                    for (int q2 = 0; q2 < 8; ++q2) kt = fmaf(tapP[7 - q2], ezp[16 + N - 1 - q2], kt);
-                  }
-                  dy[e] = (2.f / (nB * nN)) * (ee[e] - kt);
+                  for (int k = 0; k < 17; ++k) s = fmaf(kGauss17[k], win[e + k], s);
+                  ee[e] = y[e] - s;
+                  sq = fmaf(ee[e], ee[e], sq);
                 }
               }
             }
-          }
-          __syncwarp();
-        }
+            loss_b += (double)sq * inv_BN;
+            if ((MODE == kLastSmooth)) {
+              // adjoint: zero-padded full correlation of e with the taps, overhang folded into the end points
+              if (lane < 16) { ezp[lane] = 0.f; ezp[16 + N + lane] = 0.f; }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float g = 0.f;
-          if (col0 + e < N) g = dy[e] * (act == 1 ? softplus2_grad_f(v[e]) : (v[e] > 0.f ? 1.f : 0.f));
-          yrow[col0 + e] = g;
+              for (int e = 0; e < 8; ++e)
+                if (FULL || col0 + e < N) ezp[16 + col0 + e] = ee[e];
+              __syncwarp();
+              {
+                // (K^T e)[j + 8] = sum_t w[t] e[j + 8 - t] = sum_m w[m] ezp[j + 8 + m]  (taps symmetric, ezp[16 + i] = e[i])
+                float win[24];
+#pragma unroll
+                for (int q4 = 0; q4 < 6; ++q4) {
+                  float4 t4 = *reinterpret_cast<const float4*>(ezp + col0 + 8 + 4 * q4);
+                  win[4 * q4] = t4.x; win[4 * q4 + 1] = t4.y; win[4 * q4 + 2] = t4.z; win[4 * q4 + 3] = t4.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int j = col0 + e;
+                  if (FULL || j < N) {
+                    float kt = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], win[e + k], kt);
+                    // overhang of the replicate padding: sum_{i<8} (K^T e)[i] = sum_{m<8} e[m] P[7-m] folds into y[0],
+                    // and by symmetry sum_{q<8} e[N-1-q] P[7-q] into y[N-1]
+                    if (j == 0) {
+#pragma unroll
+                      for (int m = 0; m < 8; ++m) kt = fmaf(tapP[7 - m], ezp[16 + m], kt);
+                    }
+                    if (j == N - 1) {
+#pragma unroll
+                      for (int q2 = 0; q2 < 8; ++q2) kt = fmaf(tapP[7 - q2], ezp[16 + N - 1 - q2], kt);
+                    }
+                    dy[e] = (2.f / (nB * nN)) * (ee[e] - kt);
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float g = 0.f;
+            if (FULL || col0 + e < N) g = dy[e] * ((ACT == 1) ? softplus2_grad_f(v[e]) : (v[e] > 0.f ? 1.f : 0.f));
+            yrow[col0 + e] = g;
+          }
         }
+      };
+      {
+        using I0 = std::integral_constant<int, kLastRecon>;
+        using I1 = std::integral_constant<int, kLastSmooth>;
+        using I4 = std::integral_constant<int, kLastEval>;
+        using A1 = std::integral_constant<int, 1>;
+        using A2 = std::integral_constant<int, 2>;
+        using BT = std::integral_constant<bool, true>;
+        using BF = std::integral_constant<bool, false>;
+        const bool full = N == kMaxDim;
+#define RAAE_ROWPASS(M)                                                     \
+        if (act == 1) { if (full) row_pass(M{}, A1{}, BT{}); else row_pass(M{}, A1{}, BF{}); } \
+        else          { if (full) row_pass(M{}, A2{}, BT{}); else row_pass(M{}, A2{}, BF{}); }
+        if (mode == kLastRecon) { RAAE_ROWPASS(I0) }
+        else if (mode == kLastSmooth) { RAAE_ROWPASS(I1) }
+        else { RAAE_ROWPASS(I4) }
+#undef RAAE_ROWPASS
       }
       __syncthreads();
     }
@@ -247,11 +278,14 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-      for (int n0 = 0; n0 < N; n0 += kH) {
+      prefetch_w_rows64(Wc, kLD, Wg, 0, N);
+      cp_async_commit();
+      for (int n0 = 0, ci = 0; n0 < N; n0 += kH, ++ci) {
+        float* Wcur = (ci & 1) ? Wc2 : Wc;
+        cp_async_wait<0>();
         __syncthreads();
-        load_w_rows(Wc, kLD, Wg, kH, n0, N);
-        __syncthreads();
-        mma_nn<kH>(Y + n0, kLDW, Wc, kLD, acc, ty, tx);
+        if (n0 + kH < N) { prefetch_w_rows64((ci & 1) ? Wc : Wc2, kLD, Wg, n0 + kH, N); cp_async_commit(); }
+        mma_nn<kH>(Y + n0, kLDW, Wcur, kLD, acc, ty, tx);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {

@@ -242,11 +242,34 @@ __device__ __forceinline__ void build_latent_tile(float* __restrict__ Zt, const 
 __device__ __forceinline__ void load_w_rows(float* __restrict__ Ws, int ld, const float* __restrict__ W, int K, int n0,
                                             int n_rows) {
   const int k4n = (K + 3) >> 2;  // K is a multiple of 4 for every wide/hidden layer
-  for (int o = threadIdx.x; o < kH * (ld >> 2); o += kThreads) {
-    int n = o / (ld >> 2), k4 = o - n * (ld >> 2);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n0 + n < n_rows && k4 < k4n) v = *reinterpret_cast<const float4*>(W + (size_t)(n0 + n) * K + 4 * k4);
-    *reinterpret_cast<float4*>(Ws + n * ld + 4 * k4) = v;
+  const int per_row = ld >> 2, total = kH * per_row;
+  // batches of 4 float4 per thread: all loads of a batch are in flight before the first store
+  for (int o0 = threadIdx.x; o0 < total; o0 += kThreads * 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int o = o0 + kThreads * u;
+      const int n = o / per_row, k4 = o - n * per_row;
+      v[u] = (o < total && n0 + n < n_rows && k4 < k4n) ? *reinterpret_cast<const float4*>(W + (size_t)(n0 + n) * K + 4 * k4)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int o = o0 + kThreads * u;
+      const int n = o / per_row, k4 = o - n * per_row;
+      if (o < total) *reinterpret_cast<float4*>(Ws + n * ld + 4 * k4) = v[u];
+    }
+  }
+}
+
+// asynchronous variant for 64-column weight rows: rows [n0, n0+64) x [0, 64) -> smem [64][ld] with cp.async (rows beyond
+// n_rows are zero-filled with plain stores); the caller commits / waits
+__device__ __forceinline__ void prefetch_w_rows64(float* __restrict__ Ws, int ld, const float* __restrict__ W, int n0, int n_rows) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int o = threadIdx.x + kThreads * u, n = o >> 4, k4 = (o & 15) * 4;
+    if (n0 + n < n_rows) cp_async16(Ws + n * ld + k4, W + (size_t)(n0 + n) * kH + k4);
+    else *reinterpret_cast<float4*>(Ws + n * ld + k4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
