@@ -1012,8 +1012,11 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, floa
       auto load_item = [&](int it) {
         const int b = it & 1, ck = it % nch;
         tc::mbar_expect_tx(&full[b], 32768u + 32768u);
-        tc::bulk_g2s(Araw + b * 8192, xk + (size_t)it * 8192, 32768u, &full[b]);       // item order == image order
-        tc::bulk_g2s(Bbuf + b * 8192, wk + (size_t)ck * 8192, 32768u, &full[b]);
+#pragma unroll
+        for (int part = 0; part < 4; ++part) {                                          // item order == image order
+          tc::bulk_g2s(Araw + b * 8192 + part * 2048, xk + (size_t)it * 8192 + part * 2048, 8192u, &full[b]);
+          tc::bulk_g2s(Bbuf + b * 8192 + part * 2048, wk + (size_t)ck * 8192 + part * 2048, 8192u, &full[b]);
+        }
       };
       load_item(0);
       if (nitems > 1) load_item(1);
@@ -1872,13 +1875,11 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     for (int i = 0; i < kTM / 16; ++i) tc::split_store(Dhi, Dlo, offM + (uint32_t)(i * 16 * 128), dur[i]);
     tc::fence_async_smem();
     __syncthreads();
-    RAAE_PROBE(22);
     if (tc::warp_uniform_id() == 0 && tc::elect_one()) {
       tc::fence_after_sync();
       tc::issue_gemm_tn_3xtf32(d_tmem + 64, Dhi, Dlo, Phi, Plo, t > 0 ? 1u : 0u);
       tc::mma_commit(mbar);
     }
-    RAAE_PROBE(23);
     if (t + 1 < ntiles) load_gu(t + 1);
     // ---- 4. g_prev epilogue (overlaps the dW MMAs): dropout mask of the producing layer, BN-backward partial sums ----
     {
@@ -1967,9 +1968,10 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
 }
 
 // Backward of the input block of the encoder on the noised batch (no input gradient): du = PReLU'(u) BN'(g) per tile,
-// staged MN-major as the A operand; the batch comes from the centred MN-major operand image (ScratchLayout::xm) in
-// 64-column chunks (bulk copy 32 KB, rounded hi / lo split in shared memory), and dW[:, chunk] += du^T x accumulates in
-// four TMEM accumulators (M = 64 layout) over the whole batch.  dW = dWc + db (x) xref undoes the centring.
+// staged MN-major as the B operand (N = 64 output channels); the batch comes from the centred MN-major operand image
+// (ScratchLayout::xm) in 128-column chunks (bulk copy 64 KB, rounded hi / lo split in shared memory) as the A operand
+// (M = 128 input columns), and dW^T[chunk] += x^T du accumulates in TMEM over the whole batch (M = 128: full-rate MMAs,
+// half as many as with M = 64).  dW = dWc + db (x) xref undoes the centring.
 __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, const float* __restrict__ u_l,
                                           const float* __restrict__ g_in, int o) {
   const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
@@ -1977,18 +1979,20 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
   StageTimer timer_(&sm->prof[kStBwdWide]);
   const raae_net_layout& nl = NL(c, net);
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, warp = tid >> 5, lane = tid & 31;
-  const int K = nl.in_dim[l], nch = c.p->sl.nch64, nch128 = c.p->sl.nch128;
+  const int K = nl.in_dim[l], nch = c.p->sl.nch128;
   const float* xm = c.sc + c.p->sl.xm;
-  float* Dhi = arena;                        // du tile, MN-major
+  float* Dhi = arena;                        // du tile, MN-major [2 blocks][128 rows][32]
   float* Dlo = Dhi + 8192;
-  float* Xb = Dlo + 8192;                    // 2 x [hi 8192 | lo 8192] batch chunk, MN-major
+  float* Xhi = Dlo + 8192;                   // batch chunk, MN-major [4 blocks][128 rows][32]: raw, rounded in place
+  float* Xlo = Xhi + 16384;
   const int B = c.B, ntiles = (B + kTM - 1) / kTM;
   const uint32_t d_tmem = sm->tmem_base;
-  uint64_t* full = reinterpret_cast<uint64_t*>(&sm->pipe_bar[0]);      // [2] chunk landed
-  uint64_t* done = reinterpret_cast<uint64_t*>(&sm->pipe_bar[2]);      // [2] MMAs reading the chunk buffer completed
+  uint64_t* full = reinterpret_cast<uint64_t*>(&sm->pipe_bar[0]);      // chunk landed
+  uint64_t* done = reinterpret_cast<uint64_t*>(&sm->pipe_bar[1]);      // MMAs of the chunk completed
   __syncthreads();
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) tc::mbar_init(reinterpret_cast<uint64_t*>(&sm->pipe_bar[i]), 1);
+    tc::mbar_init(full, 1);
+    tc::mbar_init(done, 1);
   }
   if (tid < kH) {
     float nB = (float)B;
@@ -2005,16 +2009,20 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
   float db4[4] = {0.f, 0.f, 0.f, 0.f}, ds4[4] = {0.f, 0.f, 0.f, 0.f};
   const uint32_t offM = tc::sw128_32b_chunk_off(ty, c4, tc::kABlockBytes);
   const bool leader = tc::warp_uniform_id() == 0;
-  uint32_t nfull[2] = {0u, 0u}, ndone[2] = {0u, 0u};      // completed phases seen per barrier (parity = count & 1)
+  uint32_t nfull = 0u, ndone = 0u;                       // completed phases seen (parity = count & 1)
   auto load_chunk = [&](int t, int ck) {                   // elected thread only
-    const int b = ck & 1;
-    tc::mbar_expect_tx(&full[b], 32768u);
-    tc::bulk_g2s(Xb + b * 16384, xm + (size_t)t * nch128 * 16384 + (size_t)ck * 8192, 32768u, &full[b]);
+    // eight concurrent 8 KB copies: one bulk copy keeps only a few KB in flight and is latency-limited (~7 B/cycle)
+    tc::mbar_expect_tx(full, 65536u);
+    const float* src = xm + ((size_t)t * nch + ck) * 16384;
+#pragma unroll
+    for (int part = 0; part < 8; ++part) tc::bulk_g2s(Xhi + part * 2048, src + part * 2048, 8192u, full);
   };
+  RAAE_PROBE_INIT();
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, B - row0);
+    RAAE_PROBE(26);
     if (leader) {
-      if (tc::elect_one()) { load_chunk(t, 0); if (nch > 1) load_chunk(t, 1); }
+      if (tc::elect_one()) load_chunk(t, 0);               // overlaps the du pass
       __syncwarp();
     }
     // ---- du = PReLU'(u) BN'(g) -> MN-major hi / lo ----
@@ -2052,59 +2060,58 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
 #undef RAAE_DU
       tc::split_store(Dhi, Dlo, offM + (uint32_t)(i * 16 * 128), du);
     }
-    // ---- chunks of 64 input columns ----
+    // ---- chunks of 128 input columns ----
+    RAAE_PROBE(22);
     for (int ck = 0; ck < nch; ++ck) {
-      const int b = ck & 1;
-      tc::mbar_wait(&full[b], nfull[b] & 1u);
-      ++nfull[b];
+      tc::mbar_wait(full, nfull & 1u);
+      ++nfull;
+      RAAE_PROBE(23);
       {
-        float4* X = reinterpret_cast<float4*>(Xb + b * 16384);
-        float4 x[8];
+        float4* X = reinterpret_cast<float4*>(Xhi);
+        float4* XL = reinterpret_cast<float4*>(Xlo);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = X[tid + kThreads * k];
+        for (int h = 0; h < 2; ++h) {
+          float4 x[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float4 hi, lo;
-          tc::tf32_split(x[k].x, hi.x, lo.x);
-          tc::tf32_split(x[k].y, hi.y, lo.y);
-          tc::tf32_split(x[k].z, hi.z, lo.z);
-          tc::tf32_split(x[k].w, hi.w, lo.w);
-          X[tid + kThreads * k] = hi;
-          X[2048 + tid + kThreads * k] = lo;
+          for (int k = 0; k < 8; ++k) x[k] = X[tid + kThreads * (8 * h + k)];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float4 hi, lo;
+            tc::tf32_split(x[k].x, hi.x, lo.x);
+            tc::tf32_split(x[k].y, hi.y, lo.y);
+            tc::tf32_split(x[k].z, hi.z, lo.z);
+            tc::tf32_split(x[k].w, hi.w, lo.w);
+            X[tid + kThreads * (8 * h + k)] = hi;
+            XL[tid + kThreads * (8 * h + k)] = lo;
+          }
         }
       }
       tc::fence_async_smem();
       __syncthreads();
+      RAAE_PROBE(24);
       if (leader) {
         if (tc::elect_one()) {
           tc::fence_after_sync();
-          const float* Xh = Xb + b * 16384;
-          tc::issue_gemm_tn_3xtf32(d_tmem + (uint32_t)(64 * ck), Dhi, Dlo, Xh, Xh + 8192, t > 0 ? 1u : 0u);
-          tc::mma_commit(&done[b]);
-          // refill the OTHER buffer's successor: chunk ck + 1 is already loaded (or loading); chunk ck + 2 reuses buffer b
-          // once these MMAs have completed, which is waited for at the start of the next chunk of the same parity
+          const uint32_t acc = d_tmem + (uint32_t)(64 * ck);
+          tc::issue_gemm_tn128_pass(acc, Xlo, tc::kABlockBytes, Dhi, tc::kABlockBytes, t > 0 ? 1u : 0u);
+          tc::issue_gemm_tn128_pass(acc, Xhi, tc::kABlockBytes, Dlo, tc::kABlockBytes, 1u);
+          tc::issue_gemm_tn128_pass(acc, Xhi, tc::kABlockBytes, Dhi, tc::kABlockBytes, 1u);
+          tc::mma_commit(done);
         }
         __syncwarp();
       }
-      if (ck + 2 < nch) {
-        // buffer b is needed for chunk ck + 2: wait for the MMAs just issued, then start the copy
-        tc::mbar_wait(&done[b], ndone[b] & 1u);
-        ++ndone[b];
-        if (leader) {
-          if (tc::elect_one()) load_chunk(t, ck + 2);
-          __syncwarp();
-        }
+      // the chunk buffers (and, after the last chunk, the du tile) are reused: wait for these MMAs
+      tc::mbar_wait(done, ndone & 1u);
+      ++ndone;
+      RAAE_PROBE(25);
+      if (ck + 1 < nch && leader) {
+        if (tc::elect_one()) load_chunk(t, ck + 1);
+        __syncwarp();
       }
     }
-    // all MMAs of the tile must have completed before du is re-staged and the chunk buffers are reloaded
-    for (int ck = max(0, nch - 2); ck < nch; ++ck) {
-      const int b = ck & 1;
-      tc::mbar_wait(&done[b], ndone[b] & 1u);
-      ++ndone[b];
-    }
   }
-  // ---- weight gradient from the TMEM accumulators (M = 64 layout: row n -> lane 32 (n / 16) + n % 16) ----
-  float* gradW = Xb;                  // dense [64][K]
+  // ---- weight gradient from the TMEM accumulators: lane = input column of the chunk, column = output channel ----
+  float* gradW = Xhi;                 // dense [64][K]
   float* gb = Dhi;                    // [64] db | [64] dslope
   tc::fence_after_sync();
   __syncthreads();
@@ -2116,26 +2123,18 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
   __syncthreads();
   if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[kH + tid] = s; }
   __syncthreads();
-  if (warp < 4) {
+  {
+    // warp w reads TMEM lanes 32 (w & 3) .. + 31 (input columns of the chunk) and output channels 32 (w >> 2) .. + 31
     const float* xref = c.sc + c.p->sl.xref;
-    const int n = 16 * warp + (lane & 15);
-    const float dbn = gb[n];
+    const int n0 = 32 * (warp >> 2);
     for (int ck = 0; ck < nch; ++ck) {
+      float v[32];
+      tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * ck + n0), v);
+      const int k = 128 * ck + 32 * (warp & 3) + lane;
+      if (k < K) {
+        const float xr = xref[k];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[32];
-        tc::tmem_ld32(d_tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(64 * ck + 32 * h), v);
-        if (lane < 16) {
-          const int k0 = 64 * ck + 32 * h;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (k0 + j < K) {
-              const float4 xr = *reinterpret_cast<const float4*>(xref + k0 + j);
-              *reinterpret_cast<float4*>(gradW + n * K + k0 + j) =
-                  make_float4(fmaf(dbn, xr.x, v[j]), fmaf(dbn, xr.y, v[j + 1]), fmaf(dbn, xr.z, v[j + 2]), fmaf(dbn, xr.w, v[j + 3]));
-            }
-          }
-        }
+        for (int j = 0; j < 32; ++j) gradW[(n0 + j) * K + k] = fmaf(gb[n0 + j], xr, v[j]);
       }
     }
   }
