@@ -1730,6 +1730,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   float* Plo = Phi + tc::kATileFloats;
   float* Wthi = Plo + tc::kATileFloats;                // W^T (K-major): rows = input channel k, K index = output channel n
   float* Wtlo = Wthi + tc::kBTileFloats;
+  float* Ot = Wtlo + tc::kBTileFloats;                 // [kTM][kLD] g_prev tile bounced from the TMEM layout to (ty, c4) ownership
   float* slope_in = sm->shift;
   const float* u_prev = in.src;
   const MaskSrc mk = in.mask;
@@ -1777,9 +1778,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   const float4 is_in = *reinterpret_cast<const float4*>(sm->inv[in.snet][in.slayer] + c4);
   const float4 sl_in = *reinterpret_cast<const float4*>(slope_in + c4);
   float db4[4] = {0.f, 0.f, 0.f, 0.f}, ds4[4] = {0.f, 0.f, 0.f, 0.f};
-  float sgv[32], sgxv[32];                              // this thread's row (mod 128) x 32 columns partial sums
-#pragma unroll
-  for (int j = 0; j < 32; ++j) { sgv[j] = 0.f; sgxv[j] = 0.f; }
+  float sg4[4] = {0.f, 0.f, 0.f, 0.f}, sgx4[4] = {0.f, 0.f, 0.f, 0.f};
   uint32_t phase = sm->tc_phase;
   const int erow = 32 * (warp & 3) + lane, ecol0 = 32 * (warp >> 2);     // epilogue ownership (TMEM lane, column block)
   // swizzled staging offsets of this thread's chunks: row = ty + 16 i => (row & 7) and (row & 3) do not depend on i
@@ -1841,12 +1840,14 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       dur[i] = du;
       tc::split_store(Dhi, Dlo, offK + (uint32_t)(i * 16 * 128), du);
     }
-    // ---- 2. the layer's input activations, staged MN-major ----
+    // ---- 2. the layer's input activations, staged MN-major; the keep bits are reused by the epilogue ----
+    uint32_t kbits = 0u;
 #pragma unroll
     for (int i = 0; i < kTM / 16; ++i) {
       const int r = ty + 16 * i;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       const uint32_t kb = r < nv ? mask_keep4(mk, row0 + r, c4) : 0u;
+      kbits |= kb << (4 * i);
       a.x = (kb & 1u) ? (prelu_f(up[i].x, sl_in.x) - mu_in.x) * is_in.x * mk.scale : 0.f;
       a.y = (kb & 2u) ? (prelu_f(up[i].y, sl_in.y) - mu_in.y) * is_in.y * mk.scale : 0.f;
       a.z = (kb & 4u) ? (prelu_f(up[i].z, sl_in.z) - mu_in.z) * is_in.z * mk.scale : 0.f;
@@ -1865,12 +1866,16 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     tc::mbar_wait(mbar, phase);
     phase ^= 1u;
     RAAE_PROBE(30);
-    // ---- 3. read the g_prev accumulator back FIRST (a tcgen05.ld issued behind a queued MMA batch waits for it), then
-    //         re-stage du MN-major (the K-major copy has been consumed) and start dW += du^T a ----
-    float v[32];
-    tc::fence_after_sync();
-    tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)ecol0, v);
-    tc::fence_before_sync();
+    // ---- 3. read the g_prev accumulator back (before the dW MMAs are queued) and bounce it through shared memory to the
+    //         (ty, c4) ownership of the staging passes; re-stage du MN-major (its K-major copy has been consumed) ----
+    {
+      float v[32];
+      tc::fence_after_sync();
+      tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)ecol0, v);
+      tc::fence_before_sync();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(Ot + erow * kLD + ecol0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
 #pragma unroll
     for (int i = 0; i < kTM / 16; ++i) tc::split_store(Dhi, Dlo, offM + (uint32_t)(i * 16 * 128), dur[i]);
     tc::fence_async_smem();
@@ -1881,34 +1886,26 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       tc::mma_commit(mbar);
     }
     if (t + 1 < ntiles) load_gu(t + 1);
-    // ---- 4. g_prev epilogue (overlaps the dW MMAs): dropout mask of the producing layer, BN-backward partial sums ----
-    {
-      if (erow < nv) {
-        float* grow = g_out + (size_t)(row0 + erow) * kH + ecol0;
-        const uint32_t abase = (uint32_t)((ecol0 >> 5) * tc::kABlockBytes + erow * 128);
+    // ---- 4. g_prev epilogue (overlaps the dW MMAs): dropout mask of the producing layer, BN-backward partial sums,
+    //         coalesced store; a = hi + lo is read back from this thread's own staged chunks ----
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          float gm8[8];
-#pragma unroll
-          for (int q = 0; q < 8; q += 4) {
-            const int jj = j + q;
-            const uint32_t kb = mask_keep4(mk, row0 + erow, ecol0 + jj);
-            const uint32_t off = abase + (uint32_t)((((jj >> 3) ^ (erow & 3)) << 5) + ((jj & 7) << 2));
-            const float4 ah = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Phi) + off);
-            const float4 al = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Plo) + off);
-            gm8[q] = (kb & 1u) ? v[jj] * mk.scale : 0.f;
-            gm8[q + 1] = (kb & 2u) ? v[jj + 1] * mk.scale : 0.f;
-            gm8[q + 2] = (kb & 4u) ? v[jj + 2] * mk.scale : 0.f;
-            gm8[q + 3] = (kb & 8u) ? v[jj + 3] * mk.scale : 0.f;
-            sgv[jj] += gm8[q]; sgv[jj + 1] += gm8[q + 1]; sgv[jj + 2] += gm8[q + 2]; sgv[jj + 3] += gm8[q + 3];
-            sgxv[jj] = fmaf(v[jj], ah.x + al.x, sgxv[jj]);
-            sgxv[jj + 1] = fmaf(v[jj + 1], ah.y + al.y, sgxv[jj + 1]);
-            sgxv[jj + 2] = fmaf(v[jj + 2], ah.z + al.z, sgxv[jj + 2]);
-            sgxv[jj + 3] = fmaf(v[jj + 3], ah.w + al.w, sgxv[jj + 3]);
-          }
-          *reinterpret_cast<float4*>(grow + j) = make_float4(gm8[0], gm8[1], gm8[2], gm8[3]);
-          *reinterpret_cast<float4*>(grow + j + 4) = make_float4(gm8[4], gm8[5], gm8[6], gm8[7]);
-        }
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      if (r < nv) {
+        const float4 g4 = *reinterpret_cast<const float4*>(Ot + r * kLD + c4);
+        const uint32_t off = offM + (uint32_t)(i * 16 * 128);
+        const float4 ah = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Phi) + off);
+        const float4 al = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Plo) + off);
+        const uint32_t kb = kbits >> (4 * i);
+        float4 gm;
+        gm.x = (kb & 1u) ? g4.x * mk.scale : 0.f;
+        gm.y = (kb & 2u) ? g4.y * mk.scale : 0.f;
+        gm.z = (kb & 4u) ? g4.z * mk.scale : 0.f;
+        gm.w = (kb & 8u) ? g4.w * mk.scale : 0.f;
+        sg4[0] += gm.x; sg4[1] += gm.y; sg4[2] += gm.z; sg4[3] += gm.w;
+        sgx4[0] = fmaf(g4.x, ah.x + al.x, sgx4[0]); sgx4[1] = fmaf(g4.y, ah.y + al.y, sgx4[1]);
+        sgx4[2] = fmaf(g4.z, ah.z + al.z, sgx4[2]); sgx4[3] = fmaf(g4.w, ah.w + al.w, sgx4[3]);
+        *reinterpret_cast<float4*>(g_out + (size_t)(row0 + r) * kH + c4) = gm;
       }
     }
     RAAE_PROBE(31);
@@ -1944,20 +1941,14 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   sm->red[ty][c4 + 0] = ds4[0]; sm->red[ty][c4 + 1] = ds4[1]; sm->red[ty][c4 + 2] = ds4[2]; sm->red[ty][c4 + 3] = ds4[3];
   __syncthreads();
   if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[kH + tid] = s; }
-  // column sums of the per-thread (row, 32-column) partials: warp-level transposing reduction, then the four row
-  // quarters of every column block (warps 4 cb .. 4 cb + 3) are added
-  {
-    const float a = warp_colsum32(sgv);
-    const float b2 = warp_colsum32(sgxv);
-    __syncthreads();                                   // sm->red was read by the slope-gradient reduction above
-    sm->red[warp & 3][ecol0 + lane] = a;
-    sm->red[4 + (warp & 3)][ecol0 + lane] = b2;
-  }
   __syncthreads();
-  if (tid < kH) {
-    sm->sg[tid] = sm->red[0][tid] + sm->red[1][tid] + sm->red[2][tid] + sm->red[3][tid];
-    sm->sgx[tid] = sm->red[4][tid] + sm->red[5][tid] + sm->red[6][tid] + sm->red[7][tid];
-  }
+  sm->red[ty][c4 + 0] = sg4[0]; sm->red[ty][c4 + 1] = sg4[1]; sm->red[ty][c4 + 2] = sg4[2]; sm->red[ty][c4 + 3] = sg4[3];
+  __syncthreads();
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sg[tid] = s; }
+  __syncthreads();
+  sm->red[ty][c4 + 0] = sgx4[0]; sm->red[ty][c4 + 1] = sgx4[1]; sm->red[ty][c4 + 2] = sgx4[2]; sm->red[ty][c4 + 3] = sgx4[3];
+  __syncthreads();
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sgx[tid] = s; }
   __syncthreads();
   RAAE_PROBE(27);
   adam_apply(c, sm, o, net, nl.w_off[l], kH * kH, gradW);
