@@ -37,9 +37,33 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
   const LayerIn in = hidden_out(c, kD, L - 2, inst);
   const bool want_bwd = mode == kLastRecon || mode == kLastSmooth || mode == kLastFromDv;
   const bool flex = c.p->cfg.use_flex_spec_target != 0;
+  const bool tc_fwd = (c.p->cfg.tensor_cores & 16) != 0 && mode != kLastFromDv;
+  const int nchN = (N + kH - 1) / kH;
+  float* wl = c.sc + c.p->sl.wl;
+  // tensor-core forward: operand buffers alias the Y tile (they are dead when the accumulator is copied out)
+  float* Ahi = Y;                           // [2 K blocks][128][32] swizzled
+  float* Alo = Ahi + tc::kATileFloats;
+  float* Bb = Alo + tc::kATileFloats;       // 2 x [hi 4096 | lo 4096] weight chunk
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(&sm->pipe_bar[0]);     // [2] weight chunk landed
+  uint64_t* wdone = reinterpret_cast<uint64_t*>(&sm->pipe_bar[2]);     // [2] MMAs of the chunk completed
+  uint64_t* accfull = reinterpret_cast<uint64_t*>(&sm->pipe_bar[4]);   // all MMAs of the tile completed
+  const uint32_t d_tmem = sm->tmem_base;
   __syncthreads();
   sm->bias[tid] = tid < N ? netp(c, kD)[nl.b_off[l] + tid] : 0.f;
+  if (tc_fwd) {
+    if (tid == 0)
+      for (int i = 0; i < 5; ++i) tc::mbar_init(reinterpret_cast<uint64_t*>(&sm->pipe_bar[i]), 1);
+    // K-major hi / lo image of W [N][64] in global scratch, one [hi 4096 | lo 4096] block per 64 output columns
+    for (int i = tid; i < nchN * kH * 16; i += kThreads) {
+      const int n = i >> 4, k4 = (i & 15) * 4;
+      const float4 w = n < N ? *reinterpret_cast<const float4*>(Wg + (size_t)n * kH + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float* blk = wl + (size_t)(n >> 6) * 8192;
+      tc::split_store(blk, blk + 4096, tc::sw128_chunk_off(n & 63, k4, tc::kBBlockBytes), w);
+    }
+    tc::fence_async_all();
+  }
   __syncthreads();
+  uint32_t n_acc = 0u;                      // completed phases of accfull seen
   float accW[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -62,8 +86,67 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     const long long q0 = clock64();
+    auto load_w = [&](int ck) {             // elected thread only
+      const int b = ck & 1;
+      tc::mbar_expect_tx(&wfull[b], 32768u);
+      tc::bulk_g2s(Bb + b * 8192, wl + (size_t)ck * 8192, 32768u, &wfull[b]);
+    };
+    if (tc_fwd && tc::warp_uniform_id() == 0) {
+      // the Y tile (which the operand buffers alias) is free since the barrier that ended the previous tile
+      if (tc::elect_one()) { load_w(0); if (nchN > 1) load_w(1); }
+      __syncwarp();
+    }
     build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
-    if (mode != kLastFromDv) {
+    if (tc_fwd) {
+      // v = a W^T on the tensor core: a staged K-major hi / lo from this thread's own elements of At, weight chunks
+      // streamed with bulk copies (two buffers), 24 MMAs per 64 output columns into TMEM columns [64 c, 64 c + 64)
+      const uint32_t offK = tc::sw128_chunk_off(ty, c4, tc::kABlockBytes);
+#pragma unroll
+      for (int i = 0; i < kTM / 16; ++i)
+        tc::split_store(Ahi, Alo, offK + (uint32_t)(i * 16 * 128), *reinterpret_cast<const float4*>(At + (ty + 16 * i) * kLD + c4));
+      tc::fence_async_smem();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tc::warp_uniform_id() == 0) {
+        if (tc::elect_one()) {
+          tc::fence_after_sync();
+          // buffer b has been used t * uses_b + (ck >> 1) times before chunk ck of tile t: its barrier parities follow
+          for (int ck = 0; ck < nchN; ++ck) {
+            const int b = ck & 1;
+            tc::mbar_wait(&wfull[b], (uint32_t)(((t * ((nchN + 1 - b) >> 1)) + (ck >> 1)) & 1));
+            const float* Bh = Bb + b * 8192;
+            tc::issue_gemm_3xtf32_acc(d_tmem + (uint32_t)(64 * ck), Ahi, Alo, Bh, Bh + 4096, 0u);
+            tc::mma_commit(&wdone[b]);
+            if (ck + 2 < nchN) {
+              tc::mbar_wait(&wdone[b], (uint32_t)(((t * ((nchN + 1 - b) >> 1)) + (ck >> 1)) & 1));
+              load_w(ck + 2);
+            }
+          }
+          tc::mma_commit(accfull);
+        }
+        __syncwarp();
+      }
+      tc::mbar_wait(accfull, n_acc & 1u);
+      ++n_acc;
+      tc::fence_after_sync();
+      // accumulator -> Y (+ bias): warp w owns TMEM lanes 32 (w & 3) .. + 31 and output columns 128 (w >> 2) .. + 127
+      {
+        const int row = 32 * (warp & 3) + lane;
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int col0 = 128 * (warp >> 2) + 32 * q4;
+          if (col0 < nchN * kH) {
+            float v[32];
+            tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(sm->bias + col0 + j);
+              *reinterpret_cast<float4*>(Y + row * kLDW + col0 + j) = make_float4(v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w);
+            }
+          }
+        }
+      }
+      tc::fence_before_sync();
+    } else if (mode != kLastFromDv) {
       // weight chunks double-buffered with cp.async (second buffer = the per-warp row buffers, unused during the GEMMs):
       // the copy of chunk c+1 overlaps the contraction of chunk c, one barrier per chunk
       prefetch_w_rows64(Wc, kLD, Wg, 0, N);

@@ -691,7 +691,6 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       o.w = (kb & 8u) ? (prelu_f(uu[i].w, sl.w) - mu.w) * is.w * mk.scale : 0.f;
       tc::split_store(Ahi, Alo, offK + (uint32_t)(i * 16 * 128), o);
     }
-    tc::fence_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
   };
   auto issue = [&](int t) {              // after a barrier that follows stage(t) and every TMEM read of tile t-2
     if (tc::warp_uniform_id() == 0 && tc::elect_one()) {
@@ -706,6 +705,7 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   const int erow = 32 * (warp & 3) + lane, ecol0 = 32 * (warp >> 2);
   stage(0);
+  tc::fence_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
   __syncthreads();
   issue(0);
   for (int t = 0; t < ntiles; ++t) {
@@ -720,6 +720,7 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     float v[32];
     tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (t & 1) + ecol0), v);
     tc::fence_before_sync();
+    tc::fence_async_smem();              // late: the staging stores have drained behind the mbarrier wait and the TMEM load
     __syncthreads();
     if (t + 1 < ntiles) issue(t + 1);
 #pragma unroll
@@ -736,17 +737,12 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       if (t == 0) {
         // shift of the single-pass variance: column means of PReLU(u) over the first tile (operand buffer 0 is free:
         // its MMAs have completed; buffer 1 may be in use by tile 1)
-        float* colred = A0;               // [256][33]
+        float pv[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) colred[tid * 33 + j] = erow < nv ? prelu_f(v[j], sm->slope[ecol0 + j]) : 0.f;
+        for (int j = 0; j < 32; ++j) pv[j] = erow < nv ? prelu_f(v[j], sm->slope[ecol0 + j]) : 0.f;
+        sm->red[warp & 3][ecol0 + lane] = warp_colsum32(pv);
         __syncthreads();
-        if (tid < kH) {
-          const int cb = tid >> 5, j = tid & 31;
-          float a = 0.f;
-#pragma unroll 8
-          for (int r = 0; r < 128; ++r) a += colred[(cb * 128 + r) * 33 + j];
-          sm->shift[tid] = a / (float)nv;
-        }
+        if (tid < kH) sm->shift[tid] = (sm->red[0][tid] + sm->red[1][tid] + sm->red[2][tid] + sm->red[3][tid]) / (float)nv;
         __syncthreads();
       }
       if (erow < nv) {
@@ -767,25 +763,16 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   __syncthreads();
   if (tid == 0) { sm->tc_phase = ph0; sm->tc_phase2 = ph1; }
   if (train) {
-    // column sums of the per-thread (row, 32-column) partials: threads of column block cb are warps 4 cb .. 4 cb + 3
-    float* colred = A0;                 // [256][33]
-#pragma unroll
-    for (int j = 0; j < 32; ++j) colred[tid * 33 + j] = s1[j];
-    __syncthreads();
-    float a1 = 0.f, a2 = 0.f;
-    if (tid < kH) {
-      const int cb = tid >> 5, j = tid & 31;
-#pragma unroll 8
-      for (int r = 0; r < 128; ++r) a1 += colred[(cb * 128 + r) * 33 + j];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) colred[tid * 33 + j] = s2[j];
+    // column sums of the per-thread (row, 32-column) partials: warp-level transposing reductions, then the four row
+    // quarters of every column block are added
+    const float r1 = warp_colsum32(s1);
+    const float r2 = warp_colsum32(s2);
+    sm->red[warp & 3][ecol0 + lane] = r1;
+    sm->red[4 + (warp & 3)][ecol0 + lane] = r2;
     __syncthreads();
     if (tid < kH) {
-      const int cb = tid >> 5, j = tid & 31;
-#pragma unroll 8
-      for (int r = 0; r < 128; ++r) a2 += colred[(cb * 128 + r) * 33 + j];
+      const float a1 = sm->red[0][tid] + sm->red[1][tid] + sm->red[2][tid] + sm->red[3][tid];
+      const float a2 = sm->red[4][tid] + sm->red[5][tid] + sm->red[6][tid] + sm->red[7][tid];
       bn_finalize(c, sm, net, l, tid, sm->shift[tid], a1, a2, B);
     }
   }

@@ -38,7 +38,7 @@ int validate_config(const raae_config& c) {
   if (c.n_trials <= 0) return fail(-1, "n_trials must be positive");
   if (c.max_rows < c.batch_size) return fail(-1, "max_rows must be >= batch_size");
   if (c.ctas_per_trial != 1) return fail(-1, "ctas_per_trial must be 1 in this version");
-  if (c.tensor_cores & ~15) return fail(-1, "tensor_cores: bits 0 (hidden forward), 1 (hidden backward), 2 (input block from operand images), 3 (other 256-wide forwards) are implemented");
+  if (c.tensor_cores & ~31) return fail(-1, "tensor_cores: bits 0 (hidden forward), 1 (hidden backward), 2 (input block from operand images), 3 (other 256-wide forwards), 4 (decoder output forward) are implemented");
   return 0;
 }
 
@@ -134,6 +134,7 @@ void build_layout(const raae_config& c, raae_layout& L, raae::ScratchLayout& S) 
   S.xk = s; s += tiles * S.nch64 * 8192;
   S.xm = s; s += tiles * S.nch128 * 16384;
   S.wk = s; s += S.nch64 * 8192;
+  S.wl = s; s += ((c.dim_out + 63) / 64) * 8192;
   S.xref = s; s += 256;
   S.total = (s + 255) & ~255;
   L.scratch_floats = S.total;

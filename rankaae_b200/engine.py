@@ -13,7 +13,7 @@ from . import _lib as L
 ADAMW_DEFAULT_WD = 1e-2
 # bit 0: hidden-block forward, bit 1: hidden-block backward contractions on tcgen05 (3 x TF32, fp32-grade: the parity
 # suite passes in both modes); `tensor_cores: 0` in the config (or RAAE_TENSOR_CORES=0) selects the all-FP32-FMA path
-DEFAULT_TENSOR_CORES = 7
+DEFAULT_TENSOR_CORES = 23
 
 
 def optimizer_hparams(cfg):
