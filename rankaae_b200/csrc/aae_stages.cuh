@@ -459,8 +459,8 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
   const float* eps_fake = c.a->debug ? c.a->dbg.dis_eps_fake : nullptr;
   const uint32_t key_er = stream_key(c.seed, c.step_id, kStreamDisEpsReal);
   const uint32_t key_ef = stream_key(c.seed, c.step_id, kStreamDisEpsFake);
-  const MaskSrc mk_real[2] = {make_mask(c, kS, 0, 0), make_mask(c, kS, 0, 1)};
-  const MaskSrc mk_fake[2] = {make_mask(c, kS, 1, 0), make_mask(c, kS, 1, 1)};
+  const MaskSrc mk_real0 = make_mask(c, kS, 0, 0), mk_real1 = make_mask(c, kS, 0, 1);
+  const MaskSrc mk_fake0 = make_mask(c, kS, 1, 0), mk_fake1 = make_mask(c, kS, 1, 1);
   __syncthreads();
   load_w_rows(W1s, kLD, P + nl.w_off[1], kH, 0, kH);
   for (int i = tid; i < kH * 9; i += kThreads) {
@@ -482,7 +482,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) accW1[i][j] = 0.f;
-  float accW0[2] = {0.f, 0.f};
+  float accW0[kZ] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // (ch, q) partials of dW0[ch][:]
   float dW2p = 0.f, da1p = 0.f, db1p = 0.f;          // (ch, q) partials
   float da0p[4] = {0.f, 0.f, 0.f, 0.f}, db0p[4] = {0.f, 0.f, 0.f, 0.f};   // (ty, c4) partials
   float db2p = 0.f;                                   // thread 0
@@ -492,8 +492,8 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
     const bool fake = t >= tiles_real;
     const int nrows = fake ? c.B : c.Breal;
     const int row0 = (fake ? t - tiles_real : t) * kTM, nv = min(kTM, nrows - row0);
-    const MaskSrc& mk0 = fake ? mk_fake[0] : mk_real[0];
-    const MaskSrc& mk1 = fake ? mk_fake[1] : mk_real[1];
+    const MaskSrc mk0 = fake ? mk_fake0 : mk_real0;        // register copies
+    const MaskSrc mk1 = fake ? mk_fake1 : mk_real1;
     const float label = fake ? 0.f : 1.f;
     // ---- input rows (+ input noise, model.py:659-660) ----
     for (int i = tid; i < kTM * kZ; i += kThreads) {
@@ -512,18 +512,26 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
       Zt[i] = v;
     }
     __syncthreads();
-    // ---- layer 0 ----
-    for (int i = 0; i < kTM / 4; ++i) {
-      int r = q + 4 * i;
-      float u = 0.f, h = 0.f;
-      if (r < nv) {
-        u = b0s[ch];
+    // ---- layer 0: this thread's weight row W0[ch][:] stays in registers, the input row is two broadcast loads ----
+    {
+      float w0r[kZ];
 #pragma unroll
-        for (int k = 0; k < kZ; ++k) u = fmaf(Zt[r * kZ + k], W0s[ch * 9 + k], u);
-        h = mask_keep(mk0, row0 + r, ch) ? prelu_f(u, a0s[ch]) * mk0.scale : 0.f;
+      for (int k = 0; k < kZ; ++k) w0r[k] = W0s[ch * 9 + k];
+      const float b0c = b0s[ch], a0c = a0s[ch];
+#pragma unroll 4
+      for (int i = 0; i < kTM / 4; ++i) {
+        const int r = q + 4 * i;
+        const float4 z0 = *reinterpret_cast<const float4*>(Zt + r * kZ);
+        const float4 z1 = *reinterpret_cast<const float4*>(Zt + r * kZ + 4);
+        float u = b0c;
+        u = fmaf(z0.x, w0r[0], u); u = fmaf(z0.y, w0r[1], u); u = fmaf(z0.z, w0r[2], u); u = fmaf(z0.w, w0r[3], u);
+        u = fmaf(z1.x, w0r[4], u); u = fmaf(z1.y, w0r[5], u); u = fmaf(z1.z, w0r[6], u); u = fmaf(z1.w, w0r[7], u);
+        float h = 0.f;
+        if (r < nv) h = mask_keep(mk0, row0 + r, ch) ? prelu_f(u, a0c) * mk0.scale : 0.f;
+        else u = 0.f;
+        U1[r * kLD + ch] = u;
+        H1[r * kLD + ch] = h;
       }
-      U1[r * kLD + ch] = u;
-      H1[r * kLD + ch] = h;
     }
     __syncthreads();
     // ---- layer 1 ----
@@ -616,23 +624,39 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
       }
       __syncthreads();
       // ---- layer 0: dW0 += du1^T z;  fake rows: dz = -alpha * du1 @ W0 (gradient reversal) ----
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
-        float s = accW0[e];
-        for (int r = 0; r < kTM; ++r) s = fmaf(U1[r * kLD + n], Zt[r * kZ + k], s);
-        accW0[e] = s;
+      // dW0[ch][k] over rows q, q + 4, ...: one du1 load and one broadcast input row per 8 FMAs
+#pragma unroll 4
+      for (int i = 0; i < kTM / 4; ++i) {
+        const int r = q + 4 * i;
+        const float d = U1[r * kLD + ch];
+        const float4 z0 = *reinterpret_cast<const float4*>(Zt + r * kZ);
+        const float4 z1 = *reinterpret_cast<const float4*>(Zt + r * kZ + 4);
+        accW0[0] = fmaf(d, z0.x, accW0[0]); accW0[1] = fmaf(d, z0.y, accW0[1]); accW0[2] = fmaf(d, z0.z, accW0[2]); accW0[3] = fmaf(d, z0.w, accW0[3]);
+        accW0[4] = fmaf(d, z1.x, accW0[4]); accW0[5] = fmaf(d, z1.y, accW0[5]); accW0[6] = fmaf(d, z1.z, accW0[6]); accW0[7] = fmaf(d, z1.w, accW0[7]);
       }
       if (fake) {
+        // dz[r][k] = -alpha sum_n du1[r][n] W0[n][k]: two threads per row (32 channels each), partial sums combined by shuffle
         float* dz = c.sc + c.p->sl.dz;
-        for (int i = tid; i < kTM * kZ; i += kThreads) {
-          int r = i >> 3, k = i & 7;
-          if (r < nv) {
-            float s = 0.f;
-            if (k < ns)
-              for (int n = 0; n < kH; ++n) s = fmaf(U1[r * kLD + n], W0s[n * 9 + k], s);
-            dz[(size_t)(row0 + r) * kZ + k] = -alpha * s;
+        const int r = tid >> 1, half = tid & 1;
+        float s8[kZ];
+#pragma unroll
+        for (int k = 0; k < kZ; ++k) s8[k] = 0.f;
+#pragma unroll 2
+        for (int n4 = 0; n4 < 32; n4 += 4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(U1 + r * kLD + 32 * half + n4);
+          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float* wrow = W0s + (32 * half + n4 + e) * 9;
+#pragma unroll
+            for (int k = 0; k < kZ; ++k) s8[k] = fmaf(dv[e], wrow[k], s8[k]);
           }
+        }
+#pragma unroll
+        for (int k = 0; k < kZ; ++k) s8[k] += __shfl_xor_sync(0xffffffffu, s8[k], 1);
+        if (half == 0 && r < nv) {
+          *reinterpret_cast<float4*>(dz + (size_t)(row0 + r) * kZ) = make_float4(-alpha * s8[0], -alpha * s8[1], -alpha * s8[2], -alpha * s8[3]);
+          *reinterpret_cast<float4*>(dz + (size_t)(row0 + r) * kZ + 4) = make_float4(-alpha * s8[4], -alpha * s8[5], -alpha * s8[6], -alpha * s8[7]);
         }
       }
       __syncthreads();
@@ -668,13 +692,20 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
         __syncthreads();
       }
     }
+    {
+      // reduce the four row groups of dW0 through the (free) tile area behind the gradient vectors
+      float* part = gsm + 1024;              // [4][64][8]
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
-      if (k < ns) gW0[n * ns + k] = accW0[e];
+      for (int k = 0; k < kZ; ++k) part[(q * kH + ch) * kZ + k] = accW0[k];
     }
     sm->red[q][ch] = dW2p; sm->red[4 + q][ch] = da1p; sm->red[8 + q][ch] = db1p;
     __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float* part = gsm + 1024;
+      int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
+      if (k < ns) gW0[n * ns + k] = part[(0 * kH + n) * kZ + k] + part[(1 * kH + n) * kZ + k] + part[(2 * kH + n) * kZ + k] + part[(3 * kH + n) * kZ + k];
+    }
     if (q == 0) {
       gW2[ch] = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
       ga1[ch] = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];

@@ -1433,36 +1433,46 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, c
         }
       }
     } else if (want_out && in.kind == kInWide) {
-      // dL/dx chunk by chunk; multiplied by act'(v) and written over v (g_out == the v panel, stride in.ld)
-      for (int k0 = 0; k0 < in.dim; k0 += kH) {
-        __syncthreads();
-        for (int i = tid; i < kH * (kH / 4); i += kThreads) {   // Ws[n][kk] = W[n][k0 + kk]
-          int n = i >> 4, k4 = (i & 15) * 4;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k0 + k4 < K) v = *reinterpret_cast<const float4*>(Wg + (size_t)n * K + k0 + k4);
-          *reinterpret_cast<float4*>(Ws + n * kLD + k4) = v;
+      // dL/dx chunk by chunk, multiplied by act'(v) and written over v (g_out == the v panel, stride in.ld).  The weight
+      // chunks are double-buffered with cp.async; act'(v) comes from y = act(v), which the input tile holds:
+      // softplus_2'(v) = sigmoid(2 v) = 1 - exp(-2 y), relu'(v) = [y > 0] - so v is not read back.
+      auto prefetch_wchunk = [&](float* dst, int k0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = tid + kThreads * u, n = e >> 4, k4 = (e & 15) * 4;
+          if (k0 + k4 < K) cp_async16(dst + n * kLD + k4, Wg + (size_t)n * K + k0 + k4);
+          else *reinterpret_cast<float4*>(dst + n * kLD + k4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        cp_async_commit();
+      };
+      float* Ws2 = Ws + kWTile;
+      __syncthreads();                       // every warp is done with the weight buffers of the previous tile
+      prefetch_wchunk(Ws, 0);
+      for (int k0 = 0, ci = 0; k0 < in.dim; k0 += kH, ++ci) {
+        float* Wcur = (ci & 1) ? Ws2 : Ws;
+        cp_async_wait<0>();
         __syncthreads();
+        if (k0 + kH < in.dim) prefetch_wchunk((ci & 1) ? Ws : Ws2, k0 + kH);
         float acc[8][4];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        mma_nn<kH>(Dt, kLD, Ws, kLD, acc, ty, tx);
+        mma_nn<kH>(Dt, kLD, Wcur, kLD, acc, ty, tx);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           int r = ty + 16 * i;
           if (r < nv && k0 + c4 < in.dim) {
-            float* vp = g_out + (size_t)(row0 + r) * in.ld + k0 + c4;
-            float4 v = *reinterpret_cast<const float4*>(vp);
+            const float4 y = *reinterpret_cast<const float4*>(At + r * kLDW + k0 + c4);
+            float4 v;
             if (in.act == 1) {
-              v.x = acc[i][0] * softplus2_grad_f(v.x); v.y = acc[i][1] * softplus2_grad_f(v.y);
-              v.z = acc[i][2] * softplus2_grad_f(v.z); v.w = acc[i][3] * softplus2_grad_f(v.w);
+              v.x = acc[i][0] * -expm1f(-2.f * y.x); v.y = acc[i][1] * -expm1f(-2.f * y.y);
+              v.z = acc[i][2] * -expm1f(-2.f * y.z); v.w = acc[i][3] * -expm1f(-2.f * y.w);
             } else {
-              v.x = v.x > 0.f ? acc[i][0] : 0.f; v.y = v.y > 0.f ? acc[i][1] : 0.f;
-              v.z = v.z > 0.f ? acc[i][2] : 0.f; v.w = v.w > 0.f ? acc[i][3] : 0.f;
+              v.x = y.x > 0.f ? acc[i][0] : 0.f; v.y = y.y > 0.f ? acc[i][1] : 0.f;
+              v.z = y.z > 0.f ? acc[i][2] : 0.f; v.w = y.w > 0.f ? acc[i][3] : 0.f;
             }
-            *reinterpret_cast<float4*>(vp) = v;
+            *reinterpret_cast<float4*>(g_out + (size_t)(row0 + r) * in.ld + k0 + c4) = v;
           }
         }
       }
