@@ -159,6 +159,15 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one raae_train_kernel launch, from the committed ncu capture."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_train_r01_traffic.json")))
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -260,10 +269,14 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "raae_train_kernel", "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
-                "traffic": None, "launch_ms": train_ms,
-                "note": "hidden 64x64 blocks run on tcgen05 (kind::tf32, 3xTF32 split); 256-wide layers, discriminator and "
-                        "all element-wise stages on CUDA cores; the kernel is latency/issue-bound at 8 warps/SM "
-                        "(profiles/ncu_train_r01.md), frac is against the tensor-core peak"}
+                "traffic": ncu_traffic_bytes(), "launch_ms": train_ms,
+                "note": "per launch = 5 train batches x T trials; contractions of the hidden blocks, of the encoder input "
+                        "block (forward + weight gradient, operand images streamed with bulk copies) and of the decoder "
+                        "output forward run on tcgen05 (kind::tf32, 3xTF32 round-to-nearest split, TMEM accumulators); "
+                        "the decoder output backward, the discriminator, the latent-width layers and all element-wise / "
+                        "loss stages run on CUDA cores; the kernel is latency-bound at 8 warps/SM, not at either roof "
+                        "(profiles/ncu_train_r01.md); frac is against the measured bf16 tensor peak; traffic = DRAM bytes "
+                        "of one launch from the committed ncu capture (profiles/ncu_train_r01_traffic.json)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

@@ -227,15 +227,18 @@ __device__ __forceinline__ void build_wide_tile(float* __restrict__ Xt, const fl
 // latent rows [rows][kZ] -> [kTM][kZ]; optional BN transform (encoder output)
 __device__ __forceinline__ void build_latent_tile(float* __restrict__ Zt, const float* __restrict__ src, int row0, int nv,
                                                   int nstyle, const float* mean, const float* inv) {
-  for (int o = threadIdx.x; o < kTM * kZ; o += kThreads) {
-    int r = o >> 3, k = o & 7;
-    float v = 0.f;
-    if (r < nv && k < nstyle) {
-      v = src[(size_t)(row0 + r) * kZ + k];
-      if (mean) v = (v - mean[k]) * inv[k];
-    }
-    Zt[o] = v;
+  // one float4 per thread: row tid / 2, columns 4 (tid & 1) .. (kTM * kZ / 4 == kThreads)
+  const int r = threadIdx.x >> 1, k0 = (threadIdx.x & 1) * 4;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < nv) v = *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * kZ + k0);
+  float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int k = k0 + e;
+    if (r < nv && k < nstyle) { if (mean) o[e] = (o[e] - mean[k]) * inv[k]; }
+    else o[e] = 0.f;
   }
+  *reinterpret_cast<float4*>(Zt + r * kZ + k0) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // weights [n_rows][K] (nn.Linear layout) rows [n0, n0+64) -> smem [64][ld], zero-filled
@@ -410,12 +413,22 @@ __device__ __noinline__ void fwd_hidden_edge(const Ctx& c_ref, int net, int l, c
       build_latent_tile(At, in.src, row0, nv, K, in.slayer >= 0 ? sm->mean[in.snet][in.slayer] : nullptr,
                         in.slayer >= 0 ? sm->inv[in.snet][in.slayer] : nullptr);
       __syncthreads();
-      for (int i = 0; i < kTM / 4; ++i) {
-        int r = q + 4 * i;
-        float acc = sm->bias[ch];
+      {
+        // this thread's weight row in registers, the latent row as two broadcast loads
+        float wr[kZ];
 #pragma unroll
-        for (int k = 0; k < kZ; ++k) acc = fmaf(At[r * kZ + k], Ws[ch * 9 + k], acc);
-        Ot[r * kLD + ch] = acc;
+        for (int k = 0; k < kZ; ++k) wr[k] = Ws[ch * 9 + k];
+        const float bc = sm->bias[ch];
+#pragma unroll 4
+        for (int i = 0; i < kTM / 4; ++i) {
+          const int r = q + 4 * i;
+          const float4 z0 = *reinterpret_cast<const float4*>(At + r * kZ);
+          const float4 z1 = *reinterpret_cast<const float4*>(At + r * kZ + 4);
+          float acc = bc;
+          acc = fmaf(z0.x, wr[0], acc); acc = fmaf(z0.y, wr[1], acc); acc = fmaf(z0.z, wr[2], acc); acc = fmaf(z0.w, wr[3], acc);
+          acc = fmaf(z1.x, wr[4], acc); acc = fmaf(z1.y, wr[5], acc); acc = fmaf(z1.z, wr[6], acc); acc = fmaf(z1.w, wr[7], acc);
+          Ot[r * kLD + ch] = acc;
+        }
       }
     } else {
       float acc[8][4];
@@ -1346,7 +1359,7 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, c
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) accW[i][j] = 0.f;
-  float accS[2] = {0.f, 0.f};                // latent dW: 2 outputs per thread
+  float accS[kZ] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // latent dW: (ch, row group) partials of dW[ch][:]
   const int ntiles = (c.B + kTM - 1) / kTM;
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
@@ -1399,12 +1412,16 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, c
     } else if (in.kind == kInWide) {
       mma_tn8(Dt, kLD, 8 * (tid >> 5), At, kLDW, 8 * (tid & 31), 0, kTM, accW);
     } else {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
-        float s = accS[e];
-        for (int r = 0; r < kTM; ++r) s = fmaf(Dt[r * kLD + n], At[r * kZ + k], s);
-        accS[e] = s;
+      // dW[ch][k] over rows q, q + 4, ...: one du load and one broadcast latent row per 8 FMAs
+      const int ch = tid & 63, q = tid >> 6;
+#pragma unroll 4
+      for (int i = 0; i < kTM / 4; ++i) {
+        const int r = q + 4 * i;
+        const float d = Dt[r * kLD + ch];
+        const float4 z0 = *reinterpret_cast<const float4*>(At + r * kZ);
+        const float4 z1 = *reinterpret_cast<const float4*>(At + r * kZ + 4);
+        accS[0] = fmaf(d, z0.x, accS[0]); accS[1] = fmaf(d, z0.y, accS[1]); accS[2] = fmaf(d, z0.z, accS[2]); accS[3] = fmaf(d, z0.w, accS[3]);
+        accS[4] = fmaf(d, z1.x, accS[4]); accS[5] = fmaf(d, z1.y, accS[5]); accS[6] = fmaf(d, z1.z, accS[6]); accS[7] = fmaf(d, z1.w, accS[7]);
       }
     }
     // 4. gradient w.r.t. the input
@@ -1477,14 +1494,27 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, c
         }
       }
     } else if (want_out && in.kind == kInLatent) {
-      for (int oo = tid; oo < kTM * kZ; oo += kThreads) {
-        int r = oo >> 3, k = oo & 7;
-        if (r < nv) {
-          float s = 0.f;
-          if (k < K)
-            for (int n = 0; n < kH; ++n) s = fmaf(Dt[r * kLD + n], Ws[n * 9 + k], s);
-          g_out[(size_t)(row0 + r) * kZ + k] = s;
+      // dz[r][k] = sum_n du[r][n] W[n][k]: two threads per row (32 channels each), partial sums combined by shuffle
+      const int r = tid >> 1, half = tid & 1;
+      float s8[kZ];
+#pragma unroll
+      for (int k = 0; k < kZ; ++k) s8[k] = 0.f;
+#pragma unroll 2
+      for (int n4 = 0; n4 < 32; n4 += 4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(Dt + r * kLD + 32 * half + n4);
+        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float* wrow = Ws + (32 * half + n4 + e) * 9;
+#pragma unroll
+          for (int k = 0; k < kZ; ++k) s8[k] = fmaf(dv[e], wrow[k], s8[k]);
         }
+      }
+#pragma unroll
+      for (int k = 0; k < kZ; ++k) s8[k] += __shfl_xor_sync(0xffffffffu, s8[k], 1);
+      if (half == 0 && r < nv) {
+        *reinterpret_cast<float4*>(g_out + (size_t)(row0 + r) * kZ) = make_float4(s8[0], s8[1], s8[2], s8[3]);
+        *reinterpret_cast<float4*>(g_out + (size_t)(row0 + r) * kZ + 4) = make_float4(s8[4], s8[5], s8[6], s8[7]);
       }
     }
     __syncthreads();
@@ -1532,10 +1562,18 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, c
         if (n0 + j < K) gradW[(m0 + i) * K + n0 + j] = accW[i][j];
     __syncthreads();
   } else {
+    {
+      // reduce the four row groups through shared memory (the area behind gradW / gb is free now)
+      float* part = gradW + 1024;            // [4][64][8]
+      const int ch = tid & 63, q = tid >> 6;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
-      if (k < K) gradW[n * K + k] = accS[e];
+      for (int k = 0; k < kZ; ++k) part[(q * kH + ch) * kZ + k] = accS[k];
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
+        if (k < K) gradW[n * K + k] = part[(0 * kH + n) * kZ + k] + part[(1 * kH + n) * kZ + k] + part[(2 * kH + n) * kZ + k] + part[(3 * kH + n) * kZ + k];
+      }
     }
     __syncthreads();
   }
