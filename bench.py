@@ -291,6 +291,23 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "finite": finite,
     }
+    if rank == 0 and world == 1 and not args.no_single:
+        # BASELINE.json configs[1]: the same example config with ONE trial resident (one CTA on one SM): what a single
+        # `Trainer.train()` call costs per epoch; reported beside the ensemble number, not as the headline
+        eng1 = Engine(EXAMPLE, n_trials=1, device=dev, max_rows=1056, seeds=[12345])
+        init_trial_state(eng1, 0, EXAMPLE, seed=12345)
+        eng1.bind_dataset(*dset)
+        eng1.train_epochs(0, W)
+        torch.cuda.synchronize(dev)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        eng1.train_epochs(W, K)
+        s1.record()
+        torch.cuda.synchronize(dev)
+        ms1 = s0.elapsed_time(s1) / K
+        line["single_trial"] = {"workload": "BASELINE configs[1]: example config, trials=1 (1 of 148 SMs busy)", "ms_per_epoch": ms1,
+                                "samples_per_sec": N_TRAIN / (ms1 * 1e-3), "hours_per_2000_epochs": ms1 * 2000.0 / 3.6e6}
+        eng1.close()
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
         t = cpu_epochs(cores, 3)[1:]
@@ -311,6 +328,7 @@ def main():
     ap.add_argument("--trials", type=int, default=148, help="trials resident per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-single", action="store_true", help="skip the single-trial (configs[1]) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -31,7 +31,7 @@ struct SmemFixed {
   float alpha;
   long long prof[32];                   // per-stage-type cycle counters (thread 0), see StageId; 16.. = sub-stage probes
   unsigned long long mbar;              // mbarrier the tcgen05 commits arrive on
-  unsigned long long pipe_bar[12];       // mbarriers of the bulk-copy / MMA pipelines (re-initialised by every stage that uses them)
+  unsigned long long pipe_bar[16];       // mbarriers of the bulk-copy / MMA pipelines (re-initialised by every stage that uses them)
   unsigned long long mbar2;             // second mbarrier (double-buffered accumulators of the pipelined forward)
   uint32_t tc_phase2;                   // parity of the next completion of mbar2
   uint32_t tmem_base;                   // TMEM address returned by tcgen05.alloc
@@ -958,23 +958,26 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, floa
   const float* Wg = netp(c, net) + nl.w_off[l];
   float* wk = c.sc + c.p->sl.wk;
   const float* xk = c.sc + c.p->sl.xk;
-  float* Araw = arena;                       // 2 x [8192] raw chunk (= hi operand)
+  // Loop order: groups of up to 8 row tiles; inside a group the 64-column chunks are the OUTER loop and the tiles the
+  // inner one, with the accumulators of all tiles of the group resident in TMEM (8 x 64 = all 512 columns).  The weight
+  // chunk is then fetched once per chunk instead of once per (tile, chunk) - a bulk copy costs ~850 cycles of serialised
+  // service per SM whatever its size up to 32 KB (tools/bulk_probe.cu), so halving their number matters - and the A
+  // stream is the only per-item copy.
+  float* Araw = arena;                       // 2 x [8192] raw chunk, rounded in place (= hi operand)
   float* Alo = arena + 2 * 8192;             // 2 x [8192] lo plane
-  float* Bbuf = arena + 4 * 8192;            // 2 x [hi 4096 | lo 4096]
-  const int B = c.B, train = c.train, ntiles = (B + kTM - 1) / kTM, nitems = ntiles * nch;
+  float* Bbuf = arena + 4 * 8192;            // 2 x [hi 4096 | lo 4096] weight chunk (double-buffered over the chunks)
+  const int B = c.B, train = c.train, ntiles = (B + kTM - 1) / kTM, ngroups = (ntiles + 7) / 8;
   const uint32_t d_tmem = sm->tmem_base;
-  uint64_t* full = reinterpret_cast<uint64_t*>(&sm->pipe_bar[0]);      // [2] copies landed
-  uint64_t* empty = reinterpret_cast<uint64_t*>(&sm->pipe_bar[2]);     // [2] MMAs of the buffer completed
-  uint64_t* accfull = reinterpret_cast<uint64_t*>(&sm->pipe_bar[4]);   // [2] accumulator complete
-  uint64_t* accfree = reinterpret_cast<uint64_t*>(&sm->pipe_bar[6]);   // [2] accumulator read back (4 warps arrive)
-  uint64_t* conv = reinterpret_cast<uint64_t*>(&sm->pipe_bar[8]);      // [2] lo plane of the buffer written
+  uint64_t* full = reinterpret_cast<uint64_t*>(&sm->pipe_bar[0]);      // [2] A chunk landed
+  uint64_t* empty = reinterpret_cast<uint64_t*>(&sm->pipe_bar[2]);     // [2] MMAs of the A buffer completed
+  uint64_t* conv = reinterpret_cast<uint64_t*>(&sm->pipe_bar[4]);      // [2] hi / lo planes of the A buffer written
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(&sm->pipe_bar[6]);     // [2] weight chunk landed
+  uint64_t* accfull = reinterpret_cast<uint64_t*>(&sm->pipe_bar[8]);   // accumulators of the group complete
+  uint64_t* accfree = reinterpret_cast<uint64_t*>(&sm->pipe_bar[9]);   // accumulators of the group read back (4 warps arrive)
   __syncthreads();
   if (tid == 0) {
-    for (int i = 0; i < 6; ++i) tc::mbar_init(reinterpret_cast<uint64_t*>(&sm->pipe_bar[i]), 1);
-    tc::mbar_init(&accfree[0], 4);
-    tc::mbar_init(&accfree[1], 4);
-    tc::mbar_init(&conv[0], 1);
-    tc::mbar_init(&conv[1], 1);
+    for (int i = 0; i < 9; ++i) tc::mbar_init(reinterpret_cast<uint64_t*>(&sm->pipe_bar[i]), 1);
+    tc::mbar_init(accfree, 8);
   }
   // K-major hi / lo image of W_l [64][K] in global scratch, one [hi 4096 | lo 4096] block per 64 input columns
   for (int i = tid; i < kH * nch * 16; i += kThreads) {
@@ -985,6 +988,7 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, floa
   }
   {
     // effective bias: b + W xref (the images are centred on xref); 4 threads per output channel, float64 partial sums
+    // (a float32 dot product here costs the deep-stack parity case its margin: the constant feeds PReLU before BatchNorm)
     const float* xref = c.sc + c.p->sl.xref;
     const int n = tid >> 2, part = tid & 3;
     double acc = 0.0;
@@ -1006,126 +1010,154 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, floa
   }
   tc::fence_async_all();
   __syncthreads();
+  // Roles per group of tiles: warp 0 = producer / issuer (elected lane), warps 1..7 = converters (224 threads); afterwards
+  // all 8 warps read the group's accumulators back.  Items are counted in execution order: for g, for ck, for tl < T_g.
   const int warp_u = tc::warp_uniform_id();
-  if (warp_u == 0) {
-    if (tc::elect_one()) {
-      auto load_item = [&](int it) {
-        const int b = it & 1, ck = it % nch;
-        tc::mbar_expect_tx(&full[b], 32768u + 32768u);
+  const int erow = 32 * (warp & 3) + lane, eh = warp >> 2;                 // epilogue ownership: TMEM lane, column half
+  float shv[32], s1v[32], s2v[32];                                          // this thread's row x 32 columns: shift, partial sums
 #pragma unroll
-        for (int part = 0; part < 4; ++part) {                                          // item order == image order
-          tc::bulk_g2s(Araw + b * 8192 + part * 2048, xk + (size_t)it * 8192 + part * 2048, 8192u, &full[b]);
-          tc::bulk_g2s(Bbuf + b * 8192 + part * 2048, wk + (size_t)ck * 8192 + part * 2048, 8192u, &full[b]);
+  for (int j = 0; j < 32; ++j) { shv[j] = 0.f; s1v[j] = 0.f; s2v[j] = 0.f; }
+  float sh = 0.f;                                                           // lane j: shift of column 32 eh + j
+  int nrows_w = 0;                                                          // rows this warp has accumulated
+  // driver state (meaningful in the elected lane of warp 0 only; elect.sync picks the same lane every time)
+  int it = 0, wit = 0, wloaded = 0;
+  int lg = 0, lck = 0, ltl = 0, lit = 0;                                    // next A item to load
+  int cit = 0;                                                              // converters: next item
+  for (int g = 0; g < ngroups; ++g) {
+    const int Tg = min(8, ntiles - 8 * g);
+    if (warp_u == 0) {
+      if (tc::elect_one()) {
+        auto load_next = [&]() {
+          if (lg >= ngroups) return;
+          const int b = lit & 1, tile = 8 * lg + ltl;
+          tc::mbar_expect_tx(&full[b], 32768u);
+          tc::bulk_g2s(Araw + b * 8192, xk + ((size_t)tile * nch + lck) * 8192, 32768u, &full[b]);
+          ++lit;
+          const int Tl = min(8, ntiles - 8 * lg);
+          if (++ltl == Tl) { ltl = 0; if (++lck == nch) { lck = 0; ++lg; } }
+        };
+        auto load_w = [&](int ck, int n) {                    // n-th weight chunk load overall -> buffer n & 1
+          tc::mbar_expect_tx(&wfull[n & 1], 32768u);
+          tc::bulk_g2s(Bbuf + (n & 1) * 8192, wk + (size_t)ck * 8192, 32768u, &wfull[n & 1]);
+        };
+        if (g == 0) {
+          load_next();
+          load_next();
+          load_w(0, wloaded++);
+        } else {
+          tc::mbar_wait(accfree, (uint32_t)((g - 1) & 1));                       // the previous group has been read back
         }
-      };
-      load_item(0);
-      if (nitems > 1) load_item(1);
-      for (int it = 0; it < nitems; ++it) {
-        const int b = it & 1, tile = it / nch, ck = it - tile * nch;
-        tc::mbar_wait(&conv[b], (uint32_t)((it >> 1) & 1));                             // raw landed and lo derived
-        if (ck == 0 && tile >= 2) tc::mbar_wait(&accfree[tile & 1], (uint32_t)(((tile >> 1) - 1) & 1));
-        tc::fence_after_sync();
-        const float* Bh = Bbuf + b * 8192;
-        tc::issue_gemm_3xtf32_acc(d_tmem + (uint32_t)(64 * (tile & 1)), Araw + b * 8192, Alo + b * 8192, Bh, Bh + 4096,
-                                  ck > 0 ? 1u : 0u);
-        tc::mma_commit(&empty[b]);
-        if (ck == nch - 1) tc::mma_commit(&accfull[tile & 1]);
-        if (it + 2 < nitems) {
-          tc::mbar_wait(&empty[b], (uint32_t)((it >> 1) & 1));
-          load_item(it + 2);
+        for (int ck = 0; ck < nch; ++ck, ++wit) {
+          // prefetch the next weight chunk into the other buffer, whose previous user (chunk wit - 1) is complete when
+          // the MMAs of its last item (item it - 1) are
+          const bool more_w = (ck + 1 < nch) || (g + 1 < ngroups);
+          if (more_w) {
+            if (it >= 1) tc::mbar_wait(&empty[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
+            load_w(ck + 1 < nch ? ck + 1 : 0, wloaded++);
+          }
+          tc::mbar_wait(&wfull[wit & 1], (uint32_t)((wit >> 1) & 1));
+          const float* Bh = Bbuf + (wit & 1) * 8192;
+          for (int tl = 0; tl < Tg; ++tl, ++it) {
+            const int b = it & 1;
+            tc::mbar_wait(&conv[b], (uint32_t)((it >> 1) & 1));                    // raw landed and split
+            tc::fence_after_sync();
+            tc::issue_gemm_3xtf32_acc(d_tmem + (uint32_t)(64 * tl), Araw + b * 8192, Alo + b * 8192, Bh, Bh + 4096,
+                                      ck > 0 ? 1u : 0u);
+            tc::mma_commit(&empty[b]);
+            if (lit < it + 3) {                                                     // keep two items in flight
+              tc::mbar_wait(&empty[b], (uint32_t)((it >> 1) & 1));
+              load_next();
+            }
+          }
         }
+        tc::mma_commit(accfull);
+      }
+      __syncwarp();
+    } else {
+      // converters (224 threads): round-to-nearest hi / lo split, element for element in the swizzled layout
+      const int ctid = tid - 32;
+      for (int k0 = 0; k0 < Tg * nch; ++k0, ++cit) {
+        const int b = cit & 1;
+        tc::mbar_wait(&full[b], (uint32_t)((cit >> 1) & 1));
+        float4* src = reinterpret_cast<float4*>(Araw + b * 8192);   // rounded in place: becomes the hi plane
+        float4* dst = reinterpret_cast<float4*>(Alo + b * 8192);
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          float4 x[5];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) { const int q = ctid + 224 * (5 * hb + k); x[k] = q < 2048 ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int q = ctid + 224 * (5 * hb + k);
+            float4 hi, lo;
+            tc::tf32_split(x[k].x, hi.x, lo.x);
+            tc::tf32_split(x[k].y, hi.y, lo.y);
+            tc::tf32_split(x[k].z, hi.z, lo.z);
+            tc::tf32_split(x[k].w, hi.w, lo.w);
+            if (q < 2048) { src[q] = hi; dst[q] = lo; }
+          }
+        }
+        tc::fence_async_smem();
+        asm volatile("bar.sync 2, 224;" ::: "memory");
+        if (ctid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&conv[b])) : "memory");
       }
     }
-    __syncwarp();
-  } else if (warp_u < 4) {
-    // converters (96 threads): round-to-nearest hi / lo split, element for element in the swizzled layout
-    const int ctid = tid - 32;
-    for (int it = 0; it < nitems; ++it) {
-      const int b = it & 1;
-      tc::mbar_wait(&full[b], (uint32_t)((it >> 1) & 1));
-      float4* src = reinterpret_cast<float4*>(Araw + b * 8192);     // rounded in place: becomes the hi plane
-      float4* dst = reinterpret_cast<float4*>(Alo + b * 8192);
-      for (int q0 = ctid; q0 < 2048; q0 += 96 * 4) {
-        float4 x[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const int q = q0 + 96 * k; x[k] = q < 2048 ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f); }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int q = q0 + 96 * k;
-          float4 hi, lo;
-          tc::tf32_split(x[k].x, hi.x, lo.x);
-          tc::tf32_split(x[k].y, hi.y, lo.y);
-          tc::tf32_split(x[k].z, hi.z, lo.z);
-          tc::tf32_split(x[k].w, hi.w, lo.w);
-          if (q < 2048) { src[q] = hi; dst[q] = lo; }
-        }
-      }
-      tc::fence_async_smem();
-      asm volatile("bar.sync 2, 96;" ::: "memory");
-      if (ctid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&conv[b])) : "memory");
-    }
-  } else if (warp_u >= 4) {
-    // epilogue: this thread owns TMEM lane (row) 32 (warp - 4) + lane, both 32-column halves
-    const int erow = 32 * (warp - 4) + lane;
-    float sh[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};     // lane j: columns j and 32 + j
-    int nrows_w = 0;                                                        // rows this warp has accumulated
-    for (int t = 0; t < ntiles; ++t) {
+    // ---- read-back of the group's accumulators by all 8 warps: TMEM lane (row) erow, columns 32 eh .. + 31 of every tile ----
+    tc::mbar_wait(accfull, (uint32_t)(g & 1));
+    tc::fence_after_sync();
+    for (int tl = 0; tl < Tg; ++tl) {
+      const int t = 8 * g + tl;
       const int row0 = t * kTM, nv = min(kTM, B - row0);
-      tc::mbar_wait(&accfull[t & 1], (uint32_t)((t >> 1) & 1));
-      tc::fence_after_sync();
-      const int nvw = max(0, min(32, nv - 32 * (warp - 4)));                // valid rows of this warp in the tile
+      const int nvw = max(0, min(32, nv - 32 * (warp & 3)));                // valid rows of this warp in the tile
+      float v[32];
+      tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * tl + 32 * eh), v);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[32];
-        tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp - 4)) << 16) + (uint32_t)(64 * (t & 1) + 32 * h), v);
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bb = *reinterpret_cast<const float4*>(sm->bias + 32 * eh + j);
+        v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+      }
+      if (erow < nv) {
+        float* urow = u_out + (size_t)(row0 + erow) * kH + 32 * eh;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(sm->bias + 32 * h + j);
-          v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(urow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      if (train && nvw > 0) {
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pv[j] = erow < nv ? prelu_f(v[j], sm->slope[32 * eh + j]) : 0.f;
+        if (nrows_w == 0) {
+          // warp-local shift: mean of the warp's first rows, broadcast into every thread's registers
+          float qv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) qv[j] = pv[j];
+          sh = warp_colsum32(qv) / (float)nvw;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) shv[j] = __shfl_sync(0xffffffffu, sh, j);
         }
         if (erow < nv) {
-          float* urow = u_out + (size_t)(row0 + erow) * kH + 32 * h;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(urow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        if (train && nvw > 0) {
-          float pv[32], qv[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) pv[j] = erow < nv ? prelu_f(v[j], sm->slope[32 * h + j]) : 0.f;
-          if (nrows_w == 0) {
-            // warp-local shift: mean of the warp's first rows
-#pragma unroll
-            for (int j = 0; j < 32; ++j) qv[j] = pv[j];
-            sh[h] = warp_colsum32(qv) / (float)nvw;
-          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float shj = __shfl_sync(0xffffffffu, sh[h], j);
-            const float d = erow < nv ? pv[j] - shj : 0.f;
-            pv[j] = d;
-            qv[j] = d * d;
+            const float d = pv[j] - shv[j];
+            s1v[j] += d;
+            s2v[j] = fmaf(d, d, s2v[j]);
           }
-          s1[h] += warp_colsum32(pv);
-          s2[h] += warp_colsum32(qv);
         }
       }
       if (train) nrows_w += nvw;
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&accfree[t & 1])) : "memory");
     }
-    if (train) {
-      // per-warp (count, mean, M2) of every column -> sm->red rows 0..11
-      const float nw = (float)nrows_w;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float mean_w = nrows_w > 0 ? sh[h] + s1[h] / nw : 0.f;
-        const float m2_w = nrows_w > 0 ? fmaxf(s2[h] - s1[h] * s1[h] / nw, 0.f) : 0.f;
-        sm->red[warp - 4][32 * h + lane] = mean_w;
-        sm->red[4 + warp - 4][32 * h + lane] = m2_w;
-      }
-      if (lane == 0) sm->redw[warp - 4] = nw;
-    }
+    tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(accfree)) : "memory");
+  }
+  if (train) {
+    // per-warp (count, mean, M2) of its columns -> sm->red rows 0..7; the column reductions run once per stage
+    const float s1 = warp_colsum32(s1v), s2 = warp_colsum32(s2v);
+    const float nw = (float)nrows_w;
+    const float mean_w = nrows_w > 0 ? sh + s1 / nw : 0.f;
+    const float m2_w = nrows_w > 0 ? fmaxf(s2 - s1 * s1 / nw, 0.f) : 0.f;
+    sm->red[warp & 3][32 * eh + lane] = mean_w;
+    sm->red[4 + (warp & 3)][32 * eh + lane] = m2_w;
+    if (lane == 0 && eh == 0) sm->redw[warp & 3] = nw;
   }
   __syncthreads();
   if (train && tid < kH) {
@@ -2043,10 +2075,8 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
 #pragma unroll
     for (int part = 0; part < 8; ++part) tc::bulk_g2s(Xhi + part * 2048, src + part * 2048, 8192u, full);
   };
-  RAAE_PROBE_INIT();
   for (int t = 0; t < ntiles; ++t) {
     const int row0 = t * kTM, nv = min(kTM, B - row0);
-    RAAE_PROBE(26);
     if (leader) {
       if (tc::elect_one()) load_chunk(t, 0);               // overlaps the du pass
       __syncwarp();
@@ -2087,11 +2117,9 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
       tc::split_store(Dhi, Dlo, offM + (uint32_t)(i * 16 * 128), du);
     }
     // ---- chunks of 128 input columns ----
-    RAAE_PROBE(22);
     for (int ck = 0; ck < nch; ++ck) {
       tc::mbar_wait(full, nfull & 1u);
       ++nfull;
-      RAAE_PROBE(23);
       {
         float4* X = reinterpret_cast<float4*>(Xhi);
         float4* XL = reinterpret_cast<float4*>(Xlo);
@@ -2114,7 +2142,6 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
       }
       tc::fence_async_smem();
       __syncthreads();
-      RAAE_PROBE(24);
       if (leader) {
         if (tc::elect_one()) {
           tc::fence_after_sync();
@@ -2129,7 +2156,6 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
       // the chunk buffers (and, after the last chunk, the du tile) are reused: wait for these MMAs
       tc::mbar_wait(done, ndone & 1u);
       ++ndone;
-      RAAE_PROBE(25);
       if (ck + 1 < nch && leader) {
         if (tc::elect_one()) load_chunk(t, ck + 1);
         __syncwarp();
