@@ -485,7 +485,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
   float accW0[kZ] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // (ch, q) partials of dW0[ch][:]
   float dW2p = 0.f, da1p = 0.f, db1p = 0.f;          // (ch, q) partials
   float da0p[4] = {0.f, 0.f, 0.f, 0.f}, db0p[4] = {0.f, 0.f, 0.f, 0.f};   // (ty, c4) partials
-  float db2p = 0.f;                                   // thread 0
+  float db2p = 0.f;                                   // lane 0 of every warp
   double lossp = 0.0;
   const int tiles_real = (c.Breal + kTM - 1) / kTM, tiles_fake = (c.B + kTM - 1) / kTM;
   for (int t = 0; t < tiles_real + tiles_fake; ++t) {
@@ -495,6 +495,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
     const MaskSrc mk0 = fake ? mk_fake0 : mk_real0;        // register copies
     const MaskSrc mk1 = fake ? mk_fake1 : mk_real1;
     const float label = fake ? 0.f : 1.f;
+    const double inv_rows = 1.0 / (double)nrows;
     // ---- input rows (+ input noise, model.py:659-660) ----
     for (int i = tid; i < kTM * kZ; i += kThreads) {
       int r = i >> 3, k = i & 7;
@@ -565,10 +566,11 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
         if (r < nv) {
           float x = s + b2;
           float li = fmaxf(x, 0.f) - x * label + log1pf(expf(-fabsf(x)));
-          lossp += (double)li / (double)nrows;
+          lossp += (double)li * inv_rows;              // inv_rows: one float64 division per tile, not per row
           dl = (sigmoid_f(x) - label) / (float)nrows;
         }
         sm->dlogit[r] = dl;
+        db2p += dl;                                    // lane 0 of every warp: partial sum of dL/dlogit (reduced at the end)
       }
     }
     __syncthreads();
@@ -589,7 +591,6 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
         }
         U2[r * kLD + ch] = du;
       }
-      if (tid == 0) { float s = db2p; for (int r = 0; r < kTM; ++r) s += sm->dlogit[r]; db2p = s; }
       __syncthreads();
       // ---- layer 1: dW1 += du2^T h1, dh1 = du2 @ W1 ----
       {
@@ -711,7 +712,10 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
       ga1[ch] = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
       gb1[ch] = sm->red[8][ch] + sm->red[9][ch] + sm->red[10][ch] + sm->red[11][ch];
     }
-    if (tid == 0) gb2[0] = db2p;
+    {
+      const float tot = block_sum(lane == 0 ? db2p : 0.f, sm->redw);
+      if (tid == 0) gb2[0] = tot;
+    }
     __syncthreads();
     sm->red[ty][c4 + 0] = da0p[0]; sm->red[ty][c4 + 1] = da0p[1]; sm->red[ty][c4 + 2] = da0p[2]; sm->red[ty][c4 + 3] = da0p[3];
     __syncthreads();

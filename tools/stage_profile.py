@@ -44,10 +44,10 @@ for i, n in enumerate(["dec_last: act tile + fwd GEMM", "dec_last: recon loss pa
                        "dec_last: dW (mma_tn8)", "dec_last: g GEMM + epilogue"]):
     v = p[:, 16 + i].mean()
     print(f"    probe {n:30s} {v/1e3:10.1f} kcyc  per tile {v/(8 if 'loss pass' in n else 16):8.0f} cyc")
-for i, n in [(25, "fwd_wide_img whole stage (5 calls; per item = /160)"), (26, "bwd_wide_img whole stage (3 calls)"), (22, "fwdwide: prologue (W image, bias) per call = x32"), (23, "fwdwide: main loop per call = x32"), (24, "fwdwide: read-back per call = x32"),
+for i, n in [(23, "dis: input rows + noise"), (24, "dis: layer 0"), (25, "dis: layer 1 GEMM + H2"), (26, "dis: logits + BCE"), (16, "dis: du2 pass"), (17, "dis: dW1 + dh1 GEMMs + epilogue"), (22, "dis: dW0 + dz + loop end"),
              (28, "bwd64tc: wait prev dW + du pass"), (29, "bwd64tc: act staging"),
              (30, "bwd64tc: g_prev MMA"), (31, "bwd64tc: g epilogue + trailing sync"), (27, "bwd64tc: tail reductions + adam (per call x8)")]:
     v = p[:, i].mean()
-    calls_tiles = (5 * 32 if 22 <= i < 27 else 21 * 8)
+    calls_tiles = (16 if (22 <= i < 27 or i in (16, 17)) else 21 * 8)
     print(f"    probe {n:50s} {v/1e3:10.1f} kcyc  per item/tile {v/calls_tiles:8.0f} cyc")
 print(f"  {'(unaccounted)':22s} {(tot - p[:, :15].sum(1).mean())/1e3:10.1f} kcyc")
