@@ -126,10 +126,12 @@ __device__ __forceinline__ uint32_t sw128_chunk_off(int row, int k, int block_by
 // one-sided error of ~2^-21 |x| per operand that adds up coherently over K (measured: 2e-6 absolute on the K = 256
 // input layer, 50 x the FP32-FMA error, enough to fail gradient parity on its low-variance channels), whereas both
 // rounded halves are exact TF32 numbers, so nothing is truncated and the residual has a random sign.
+// round to nearest (ties away from zero) to 10 mantissa bits, i.e. cvt.rna.tf32.f32, done with two full-rate integer
+// instructions: the conversion instruction issues at a fraction of the ALU rate and the staging passes need two per
+// element (ncu: math-pipe throttle on that line).  Adding half a TF32 ulp to the sign-magnitude bit pattern and clearing
+// the 13 low bits is exact for finite inputs (a carry into the exponent is the correct round-up to the next binade).
 __device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
   hi = tf32_rna(x);
