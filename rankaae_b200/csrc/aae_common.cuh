@@ -42,7 +42,10 @@ struct ScratchLayout {
   int xk;                       // [tiles][nch64][8192] fp32 (batch - xref), K-major SWIZZLE_128B blocks (forward of the input layer)
   int xm;                       // [tiles][nch128][16384] fp32 (batch - xref), MN-major SW128_32B blocks (weight gradient of the input layer)
   int wk;                       // [nch64][hi 4096 | lo 4096] K-major image of the input layer's weights (rebuilt by each forward)
+  int yk;                       // like xk, for y = act(v) of the MI phase (written by the decoder output stage, mode kLastStoreV)
+  int ym;                       // like xm, for y (reserved for the MI-phase weight gradient)
   int wl;                       // [nch64 of dim_out][hi 4096 | lo 4096] K-major image of the decoder output weights (rebuilt per call)
+  int yref;                     // [kMaxDim] reference row of the y image (column means of the first rows of act(v))
   int xref;                     // [kMaxDim] reference row the images are centred on (mean of the first rows of the batch)
   int nch64, nch128;
   int total;

@@ -184,7 +184,8 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask, bool run_p0 =
     const LayerIn zs = latent_in(c.sc + p.sl.zs, ns, -1);
     decoder_forward_hidden(c, zs, 2);
     dec_last(c, kLastStoreV, 2, kMI);
-    const LayerIn y = wide_in(c.sc + p.sl.v, p.sl.vld, p.cfg.dim_out, act);
+    LayerIn y = wide_in(c.sc + p.sl.v, p.sl.vld, p.cfg.dim_out, act);
+    y.img = (p.cfg.dim_in == p.cfg.dim_out) ? 2 : 0;     // dec_last(kLastStoreV) wrote the operand image of act(v)
     encoder_forward(c, y, 4);
     mi_mse_stage(c, 1);
     if (tid == 0) adam_prepare(c, sm, kMI);
@@ -467,7 +468,11 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
   // mutual information on z_sample (trainer.py:240-246)
   decoder_forward_hidden(c, latent_in(zs, ns, -1), 0);
   dec_last(c, kLastStoreV, 0, kMI);
-  encoder_forward(c, wide_in(c.sc + p.sl.v, p.sl.vld, p.cfg.dim_out, act), 0);
+  {
+    LayerIn y = wide_in(c.sc + p.sl.v, p.sl.vld, p.cfg.dim_out, act);
+    y.img = (p.cfg.dim_in == p.cfg.dim_out) ? 2 : 0;
+    encoder_forward(c, y, 0);
+  }
   mi_mse_stage(c, 0);
   if (tid == 0) {
     float* misc = c.st + p.lay.misc_off;

@@ -174,9 +174,47 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
     __syncthreads();
     const long long q1 = clock64();
     if (mode == kLastStoreV) {
+      // v -> panel (the MI backward needs act'(v) and overwrites it with dL/dv); y = act(v) - xref -> K-major operand image
+      // of the re-encoding forward (same layout and reference row as the batch image, ScratchLayout::yk)
       const int cc = (tid & 63) * 4;
-      for (int r = tid >> 6; r < nv; r += 4)
-        if (cc < N) *reinterpret_cast<float4*>(vpanel + (size_t)(row0 + r) * vld + cc) = *reinterpret_cast<const float4*>(Y + r * kLDW + cc);
+      const bool img = (c.p->cfg.tensor_cores & 4) != 0 && N == c.p->cfg.dim_in;
+      const int nch64 = c.p->sl.nch64;
+      float* yk = c.sc + c.p->sl.yk;
+      float* yref = c.sc + c.p->sl.yref;
+      if (img && t == 0) {
+        // reference row of the image: column means of y over the first (up to 32) rows - y of random latents need not be
+        // close to the batch reference, and the tensor core's truncating accumulation wants small centred operands
+        const int nref = min(32, nv);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cc < N)
+          for (int r = tid >> 6; r < nref; r += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(Y + r * kLDW + cc);
+            if (act == 1) { acc.x += softplus2_f(v4.x); acc.y += softplus2_f(v4.y); acc.z += softplus2_f(v4.z); acc.w += softplus2_f(v4.w); }
+            else { acc.x += fmaxf(v4.x, 0.f); acc.y += fmaxf(v4.y, 0.f); acc.z += fmaxf(v4.z, 0.f); acc.w += fmaxf(v4.w, 0.f); }
+          }
+        float* red = &sm->red[0][0];                 // [4][256]
+        *reinterpret_cast<float4*>(red + (tid >> 6) * 256 + cc) = acc;
+        __syncthreads();
+        yref[tid] = (red[tid] + red[256 + tid] + red[512 + tid] + red[768 + tid]) / (float)nref;
+        __threadfence_block();
+        __syncthreads();
+      }
+      const float4 xr = (img && cc < N) ? *reinterpret_cast<const float4*>(yref + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = tid >> 6; r < kTM; r += 4) {
+        float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nv && cc < N) {
+          const float4 v4 = *reinterpret_cast<const float4*>(Y + r * kLDW + cc);
+          *reinterpret_cast<float4*>(vpanel + (size_t)(row0 + r) * vld + cc) = v4;
+          if (act == 1) { y4.x = softplus2_f(v4.x); y4.y = softplus2_f(v4.y); y4.z = softplus2_f(v4.z); y4.w = softplus2_f(v4.w); }
+          else { y4.x = fmaxf(v4.x, 0.f); y4.y = fmaxf(v4.y, 0.f); y4.z = fmaxf(v4.z, 0.f); y4.w = fmaxf(v4.w, 0.f); }
+          y4.x -= xr.x; y4.y -= xr.y; y4.z -= xr.z; y4.w -= xr.w;
+        }
+        if (img && cc < nch64 * 64) {
+          float* bk = yk + (size_t)(t * nch64 + (cc >> 6)) * 8192;
+          *reinterpret_cast<float4*>(reinterpret_cast<char*>(bk) + tc::sw128_chunk_off(r, cc & 63, tc::kABlockBytes)) = y4;
+        }
+      }
+      if (img) tc::fence_async_all();        // read by bulk copies in the next stage
       __syncthreads();
       continue;
     }

@@ -348,7 +348,8 @@ struct LayerIn {
   int kind;
   const float* src;    // hidden: u_prev [rows][64]; wide: [rows][ld]; latent: [rows][kZ]
   int ld, dim, act;    // wide only
-  int img;             // wide only: 1 = the rows are the noised batch, whose operand images exist (ScratchLayout::xk / xm)
+  int img;             // wide only: 1 = the rows are the noised batch, whose operand images exist (ScratchLayout::xk / xm);
+                       // 2 = the rows are y = act(v) of the MI phase (ScratchLayout::yk, forward only)
   int snet, slayer;    // hidden: BN statistics sm->mean/inv[snet][slayer] of the producing layer;
                        // latent: BN of the encoder output, or slayer < 0 for raw rows
   const float* slope;  // hidden: PReLU slopes (global) of the producing layer
@@ -948,7 +949,8 @@ __device__ __noinline__ void fwd_wide_tc(const Ctx& c_ref, int net, int l, const
 // warps 4..7 read the finished 128 x 64 accumulators back (two TMEM accumulators, so the MMAs of tile t+1 overlap the
 // epilogue of tile t), add the bias, store u and keep the BatchNorm sums per warp with warp-local shifts that are
 // merged exactly at the end.  HBM traffic: the batch once (the hi/lo split never leaves the SM).
-__device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, float* __restrict__ u_out) {
+__device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, const float* __restrict__ xk, const float* __restrict__ xref,
+                                          float* __restrict__ u_out) {
   const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStFwdWide]);
@@ -957,7 +959,6 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, floa
   const int K = nl.in_dim[l], nch = c.p->sl.nch64;
   const float* Wg = netp(c, net) + nl.w_off[l];
   float* wk = c.sc + c.p->sl.wk;
-  const float* xk = c.sc + c.p->sl.xk;
   // Loop order: groups of up to 8 row tiles; inside a group the 64-column chunks are the OUTER loop and the tiles the
   // inner one, with the accumulators of all tiles of the group resident in TMEM (8 x 64 = all 512 columns).  The weight
   // chunk is then fetched once per chunk instead of once per (tile, chunk) - a bulk copy costs ~850 cycles of serialised
@@ -989,7 +990,6 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, floa
   {
     // effective bias: b + W xref (the images are centred on xref); 4 threads per output channel, float64 partial sums
     // (a float32 dot product here costs the deep-stack parity case its margin: the constant feeds PReLU before BatchNorm)
-    const float* xref = c.sc + c.p->sl.xref;
     const int n = tid >> 2, part = tid & 3;
     double acc = 0.0;
     for (int k = part * 4; k < K; k += 16) {
@@ -1282,7 +1282,7 @@ __device__ __forceinline__ void fwd_hidden(const Ctx& c, int net, int l, const L
     if (c.p->cfg.tensor_cores & 1) fwd_hidden64_tc(c, net, l, in, u_out);
     else fwd_hidden64(c, net, l, in, u_out);
   } else if (in.kind == kInWide && (c.p->cfg.tensor_cores & 4) && in.img) {
-    fwd_wide_img(c, net, l, u_out);
+    fwd_wide_img(c, net, l, c.sc + (in.img == 2 ? c.p->sl.yk : c.p->sl.xk), c.sc + (in.img == 2 ? c.p->sl.yref : c.p->sl.xref), u_out);
   } else if (in.kind == kInWide && (c.p->cfg.tensor_cores & 8)) {
     fwd_wide_tc(c, net, l, in, u_out);
   } else {
@@ -2334,7 +2334,7 @@ __device__ __forceinline__ void bwd_hidden(const Ctx& c, int net, int l, const L
   if (in.kind == kInHidden && g_out != nullptr) {
     if (c.p->cfg.tensor_cores & 2) bwd_hidden64_tc(c, net, l, in, u_l, g_in, g_out, o);
     else bwd_hidden64(c, net, l, in, u_l, g_in, g_out, o);
-  } else if (in.kind == kInWide && in.img && g_out == nullptr && (c.p->cfg.tensor_cores & 4)) {
+  } else if (in.kind == kInWide && in.img == 1 && g_out == nullptr && (c.p->cfg.tensor_cores & 4)) {
     bwd_wide_img(c, net, l, u_l, g_in, o);
   } else {
     bwd_hidden_edge(c, net, l, in, u_l, g_in, g_out, o);

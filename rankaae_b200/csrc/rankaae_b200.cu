@@ -133,9 +133,12 @@ void build_layout(const raae_config& c, raae_layout& L, raae::ScratchLayout& S) 
   s = (s + 255) & ~255;                                  // 1 KB alignment of the operand images
   S.xk = s; s += tiles * S.nch64 * 8192;
   S.xm = s; s += tiles * S.nch128 * 16384;
+  S.yk = s; s += tiles * S.nch64 * 8192;
+  S.ym = s; s += tiles * S.nch128 * 16384;
   S.wk = s; s += S.nch64 * 8192;
   S.wl = s; s += ((c.dim_out + 63) / 64) * 8192;
   S.xref = s; s += 256;
+  S.yref = s; s += 256;
   S.total = (s + 255) & ~255;
   L.scratch_floats = S.total;
 }
