@@ -178,8 +178,9 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
       // of the re-encoding forward (same layout and reference row as the batch image, ScratchLayout::yk)
       const int cc = (tid & 63) * 4;
       const bool img = (c.p->cfg.tensor_cores & 4) != 0 && N == c.p->cfg.dim_in;
-      const int nch64 = c.p->sl.nch64;
+      const int nch64 = c.p->sl.nch64, nch128 = c.p->sl.nch128;
       float* yk = c.sc + c.p->sl.yk;
+      float* ym = c.sc + c.p->sl.ym;
       float* yref = c.sc + c.p->sl.yref;
       if (img && t == 0) {
         // reference row of the image: column means of y over the first (up to 32) rows - y of random latents need not be
@@ -212,6 +213,10 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
         if (img && cc < nch64 * 64) {
           float* bk = yk + (size_t)(t * nch64 + (cc >> 6)) * 8192;
           *reinterpret_cast<float4*>(reinterpret_cast<char*>(bk) + tc::sw128_chunk_off(r, cc & 63, tc::kABlockBytes)) = y4;
+          if (c.train && cc < nch128 * 128) {        // MN-major image for the weight gradient of the re-encoding forward
+            float* bm = ym + (size_t)(t * nch128 + (cc >> 7)) * 16384;
+            *reinterpret_cast<float4*>(reinterpret_cast<char*>(bm) + tc::sw128_32b_chunk_off(r, cc & 127, tc::kABlockBytes)) = y4;
+          }
         }
       }
       if (img) tc::fence_async_all();        // read by bulk copies in the next stage

@@ -2030,15 +2030,19 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
 // (ScratchLayout::xm) in 128-column chunks (bulk copy 64 KB, rounded hi / lo split in shared memory) as the A operand
 // (M = 128 input columns), and dW^T[chunk] += x^T du accumulates in TMEM over the whole batch (M = 128: full-rate MMAs,
 // half as many as with M = 64).  dW = dWc + db (x) xref undoes the centring.
+// With dx_out != null (MI phase: the input is y = act(v), imaged by the decoder output stage) the input gradient
+// dL/dy act'(v) = (du W) act'(v) is also produced, tile by tile after the weight-gradient MMAs (FP32 FMA on the du tile
+// rebuilt from its hi + lo planes, weight chunks double-buffered with cp.async in the then idle chunk buffers), and
+// written over v.
 __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, const float* __restrict__ u_l,
-                                          const float* __restrict__ g_in, int o) {
+                                          const float* __restrict__ g_in, int o, const float* __restrict__ xm,
+                                          const float* __restrict__ xref, float* dx_out, int dx_ld, int act) {
   const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStBwdWide]);
   const raae_net_layout& nl = NL(c, net);
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, warp = tid >> 5, lane = tid & 31;
   const int K = nl.in_dim[l], nch = c.p->sl.nch128;
-  const float* xm = c.sc + c.p->sl.xm;
   float* Dhi = arena;                        // du tile, MN-major [2 blocks][128 rows][32]
   float* Dlo = Dhi + 8192;
   float* Xhi = Dlo + 8192;                   // batch chunk, MN-major [4 blocks][128 rows][32]: raw, rounded in place
@@ -2161,6 +2165,66 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
         __syncwarp();
       }
     }
+    if (dx_out != nullptr) {
+      // ---- input gradient of the tile (all MMAs of the tile have completed: the chunk buffers are idle) ----
+      const float* Wg = netp(c, net) + nl.w_off[l];
+      float* Dt = Xhi;                         // [kTM][kLD] du = hi + lo, row-major
+      float* Ws0 = Xlo;                        // two [64][kLD] weight chunks
+      float* Ws1 = Xlo + kWTile;
+      auto prefetch_wchunk = [&](float* dst, int k0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = tid + kThreads * u, n = e >> 4, k4 = (e & 15) * 4;
+          if (k0 + k4 < K) cp_async16(dst + n * kLD + k4, Wg + (size_t)n * K + k0 + k4);
+          else *reinterpret_cast<float4*>(dst + n * kLD + k4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        cp_async_commit();
+      };
+      prefetch_wchunk(Ws0, 0);
+#pragma unroll
+      for (int i = 0; i < kTM / 16; ++i) {      // this thread's own staged chunks
+        const uint32_t off = offM + (uint32_t)(i * 16 * 128);
+        const float4 h = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Dhi) + off);
+        const float4 lo = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(Dlo) + off);
+        *reinterpret_cast<float4*>(Dt + (ty + 16 * i) * kLD + c4) = make_float4(h.x + lo.x, h.y + lo.y, h.z + lo.z, h.w + lo.w);
+      }
+      for (int k0 = 0, ci = 0; k0 < K; k0 += kH, ++ci) {
+        float* Wcur = (ci & 1) ? Ws1 : Ws0;
+        // act'(v) of this chunk: loads in flight during the contraction
+        float4 vv[kTM / 16];
+#pragma unroll
+        for (int i = 0; i < kTM / 16; ++i) {
+          const int r = ty + 16 * i;
+          vv[i] = (r < nv && k0 + c4 < K) ? *reinterpret_cast<const float4*>(dx_out + (size_t)(row0 + r) * dx_ld + k0 + c4)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        if (k0 + kH < K) prefetch_wchunk((ci & 1) ? Ws0 : Ws1, k0 + kH);
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        mma_nn<kH>(Dt, kLD, Wcur, kLD, acc, ty, tx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = ty + 16 * i;
+          if (r < nv && k0 + c4 < K) {
+            float4 v = vv[i];
+            if (act == 1) {
+              v.x = acc[i][0] * softplus2_grad_f(v.x); v.y = acc[i][1] * softplus2_grad_f(v.y);
+              v.z = acc[i][2] * softplus2_grad_f(v.z); v.w = acc[i][3] * softplus2_grad_f(v.w);
+            } else {
+              v.x = v.x > 0.f ? acc[i][0] : 0.f; v.y = v.y > 0.f ? acc[i][1] : 0.f;
+              v.z = v.z > 0.f ? acc[i][2] : 0.f; v.w = v.w > 0.f ? acc[i][3] : 0.f;
+            }
+            *reinterpret_cast<float4*>(dx_out + (size_t)(row0 + r) * dx_ld + k0 + c4) = v;
+          }
+        }
+      }
+      __syncthreads();                         // the chunk buffers are reloaded by the next tile
+    }
   }
   // ---- weight gradient from the TMEM accumulators: lane = input column of the chunk, column = output channel ----
   float* gradW = Xhi;                 // dense [64][K]
@@ -2177,7 +2241,6 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
   __syncthreads();
   {
     // warp w reads TMEM lanes 32 (w & 3) .. + 31 (input columns of the chunk) and output channels 32 (w >> 2) .. + 31
-    const float* xref = c.sc + c.p->sl.xref;
     const int n0 = 32 * (warp >> 2);
     for (int ck = 0; ck < nch; ++ck) {
       float v[32];
@@ -2335,7 +2398,9 @@ __device__ __forceinline__ void bwd_hidden(const Ctx& c, int net, int l, const L
     if (c.p->cfg.tensor_cores & 2) bwd_hidden64_tc(c, net, l, in, u_l, g_in, g_out, o);
     else bwd_hidden64(c, net, l, in, u_l, g_in, g_out, o);
   } else if (in.kind == kInWide && in.img == 1 && g_out == nullptr && (c.p->cfg.tensor_cores & 4)) {
-    bwd_wide_img(c, net, l, u_l, g_in, o);
+    bwd_wide_img(c, net, l, u_l, g_in, o, c.sc + c.p->sl.xm, c.sc + c.p->sl.xref, nullptr, 0, 0);
+  } else if (in.kind == kInWide && in.img == 2 && g_out != nullptr && (c.p->cfg.tensor_cores & 4)) {
+    bwd_wide_img(c, net, l, u_l, g_in, o, c.sc + c.p->sl.ym, c.sc + c.p->sl.yref, g_out, in.ld, in.act);
   } else {
     bwd_hidden_edge(c, net, l, in, u_l, g_in, g_out, o);
   }
