@@ -236,6 +236,12 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const KParams& p, const RunArgs
   c.train = 1;
   c.x = c.sc + p.sl.xn;
   c.xld = p.sl.xld;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const double pd = c.hp[g ? RAAE_HP_DIS_DROPOUT : RAAE_HP_DROPOUT];
+    c.drop_scale[g] = pd > 0.0 ? 1.f / (float)(1.0 - pd) : 1.f;
+    c.drop_thresh[g] = pd > 0.0 ? (uint32_t)(pd * 65536.0 + 0.5) : 0u;
+  }
 }
 
 constexpr size_t kSmemBytes = kArenaOffset + (size_t)kArenaFloats * sizeof(float);

@@ -68,6 +68,8 @@ struct Ctx {
   int apply;          // apply optimizer updates
   int epoch;
   int trial;
+  float drop_scale[2];     // [0] encoder / decoder, [1] discriminator: 1 / (1 - p), read once per kernel from the hp row
+  uint32_t drop_thresh[2]; // round(p * 65536); 0 = no dropout
 };
 
 // Shared memory is always reached through the `extern __shared__` symbol (never through a pointer stored
@@ -91,9 +93,9 @@ __device__ inline MaskSrc make_mask(const Ctx& c, int net, int inst, int layer) 
   MaskSrc m;
   m.ptr = nullptr; m.key = 0u; m.thresh = 0u; m.scale = 1.f;
   if (!c.train) return m;
-  double pd = c.hp[net == kS ? RAAE_HP_DIS_DROPOUT : RAAE_HP_DROPOUT];
-  if (pd <= 0.0) return m;
-  m.scale = 1.f / (float)(1.0 - pd);
+  const int g = net == kS ? 1 : 0;
+  if (c.drop_thresh[g] == 0u) return m;
+  m.scale = c.drop_scale[g];
   if (c.a->debug) {
     const uint8_t* ptr = net == kE ? c.a->dbg.mask_enc[inst][layer]
                        : net == kD ? c.a->dbg.mask_dec[inst][layer] : c.a->dbg.mask_dis[inst][layer];
@@ -101,7 +103,7 @@ __device__ inline MaskSrc make_mask(const Ctx& c, int net, int inst, int layer) 
   }
   uint32_t kind = (net == kE ? kStreamEncMask : net == kD ? kStreamDecMask : kStreamDisMask) + inst * 8 + layer;
   m.key = stream_key(c.seed, c.step_id, kind);
-  m.thresh = (uint32_t)(pd * 65536.0 + 0.5);
+  m.thresh = c.drop_thresh[g];
   return m;
 }
 
