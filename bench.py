@@ -284,7 +284,7 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"example fix_config ensemble, synthetic 7000x256 (4900 train/1050 val), batch 1024, "
                                f"{T} trials per GPU, 1 step = 1 epoch of every trial incl. validation + metrics",
-                   "trials_per_gpu": T, "l2": "per-step working set 5 MB x trials > 126 MB L2"},
+                   "trials_per_gpu": T, "l2": "per-step working set 10 MB x trials > 126 MB L2"},
         "steps_per_sec": world * T * 5 / (ms_per_step * 1e-3),
         "trials_per_hour_2000_epochs": world * T * 3600.0 / (ms_per_step * 1e-3 * 2000.0),
         "e2e": {"value": world * T * N_TRAIN / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

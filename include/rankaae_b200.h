@@ -74,8 +74,9 @@ typedef struct raae_config {
   int32_t ctas_per_trial;      /* thread-block cluster size per trial; 1 in this version */
   int32_t tensor_cores;        /* contractions on tcgen05 (kind::tf32, 3 x TF32 round-to-nearest split, TMEM accumulators): bit 0
                                   hidden-block forward, bit 1 hidden-block backward, bit 2 input block of the encoder on the batch
-                                  (forward + weight gradient from operand images in scratch, streamed with bulk copies), bit 3 the
-                                  other wide forwards, bit 4 decoder output forward; 0 = everything as FP32 FMA */
+                                  (forward + weight gradient from operand images in scratch, streamed with bulk copies; also the
+                                  re-encoding pass of the MI phase), bit 4 decoder output forward; bit 3 is unused; 0 = everything as
+                                  FP32 FMA */
   int32_t reserved[2];
 } raae_config;
 

@@ -795,155 +795,6 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   __syncthreads();
 }
 
-// forward of the 256-wide first encoder block (input = noised spectra, or the decoder output in the MI phase) on the
-// tensor core: K = dim is consumed in 64-column chunks, each chunk staged hi / lo (K-major SWIZZLE_128B) together with
-// the matching weight chunk, 24 MMAs per chunk accumulating in TMEM; the global loads of chunk c+1 are issued before
-// waiting for the MMAs of chunk c.
-__device__ __noinline__ void fwd_wide_tc(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
-  const LayerIn in = in_ref;
-  RAAE_SMEM();
-  StageTimer timer_(&sm->prof[kStFwdWide]);
-  const raae_net_layout& nl = NL(c, net);
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, warp = tid >> 5, lane = tid & 31;
-  const int K = nl.in_dim[l];
-  const float* Wg = netp(c, net) + nl.w_off[l];
-  float* Ahi = arena;
-  float* Alo = Ahi + tc::kATileFloats;
-  float* Whi = Alo + tc::kATileFloats;
-  float* Wlo = Whi + tc::kBTileFloats;
-  float* Ot = Wlo + tc::kBTileFloats;              // [kTM][kLD]
-  const int ntiles = (c.B + kTM - 1) / kTM, nchunks = (K + kH - 1) / kH;
-  const uint32_t d_tmem = sm->tmem_base;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(&sm->mbar);
-  __syncthreads();
-  if (tid < kH) {
-    sm->bias[tid] = netp(c, net)[nl.b_off[l] + tid];
-    sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
-    if (!c.train) {
-      sm->mean[net][l][tid] = c.st[nl.rm_off[l] + tid];
-      sm->inv[net][l][tid] = 1.f / sqrtf(c.st[nl.rv_off[l] + tid] + kBnEps);
-    }
-  }
-  __syncthreads();
-  float4 s1v = make_float4(0.f, 0.f, 0.f, 0.f), s2v = make_float4(0.f, 0.f, 0.f, 0.f);
-  uint32_t phase = sm->tc_phase;
-  for (int t = 0; t < ntiles; ++t) {
-    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
-    float4 xa[kTM / 16], wa[4];
-    auto load_chunk = [&](int k0) {
-#pragma unroll
-      for (int i = 0; i < kTM / 16; ++i) {
-        const int r = ty + 16 * i;
-        xa[i] = (r < nv && k0 + c4 < in.dim) ? *reinterpret_cast<const float4*>(in.src + (size_t)(row0 + r) * in.ld + k0 + c4)
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {            // W[n][k0 .. k0+63], n = ty + 16 i
-        const int n = ty + 16 * i;
-        wa[i] = (k0 + c4 < K) ? *reinterpret_cast<const float4*>(Wg + (size_t)n * K + k0 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    load_chunk(0);
-    for (int ck = 0; ck < nchunks; ++ck) {
-      // stage the chunk held in registers (the previous chunk's MMAs have been waited for)
-#pragma unroll
-      for (int i = 0; i < kTM / 16; ++i) {
-        const int r = ty + 16 * i;
-        float4 o = xa[i];
-        if (r < nv && ck * kH + c4 < in.dim) {
-          if (in.act == 1) { o.x = softplus2_f(o.x); o.y = softplus2_f(o.y); o.z = softplus2_f(o.z); o.w = softplus2_f(o.w); }
-          else if (in.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        }
-        tc::split_store(Ahi, Alo, tc::sw128_chunk_off(r, c4, tc::kABlockBytes), o);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) tc::split_store(Whi, Wlo, tc::sw128_chunk_off(ty + 16 * i, c4, tc::kBBlockBytes), wa[i]);
-      tc::fence_async_smem();
-      __syncthreads();
-      if (tc::warp_uniform_id() == 0 && tc::elect_one()) {
-        tc::fence_after_sync();
-        tc::issue_gemm_3xtf32_acc(d_tmem, Ahi, Alo, Whi, Wlo, ck > 0 ? 1u : 0u);
-        tc::mma_commit(mbar);
-      }
-      if (ck + 1 < nchunks) load_chunk((ck + 1) * kH);     // global loads in flight while the tensor core works
-      tc::mbar_wait(mbar, phase);
-      phase ^= 1u;
-    }
-    tc::fence_after_sync();
-    // accumulator -> Ot (+ bias): warp w owns TMEM lanes 32 (w % 4) .. +31 and columns 32 (w / 4) .. +31
-    {
-      float v[32];
-      const int row = 32 * (warp & 3) + lane, col0 = 32 * (warp >> 2);
-      tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o = make_float4(v[j] + sm->bias[col0 + j], v[j + 1] + sm->bias[col0 + j + 1], v[j + 2] + sm->bias[col0 + j + 2],
-                               v[j + 3] + sm->bias[col0 + j + 3]);
-        *reinterpret_cast<float4*>(Ot + row * kLD + col0 + j) = o;
-      }
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    const float4 a_sl = *reinterpret_cast<const float4*>(sm->slope + c4);
-    float4 uo[kTM / 16];
-#pragma unroll
-    for (int i = 0; i < kTM / 16; ++i) uo[i] = *reinterpret_cast<const float4*>(Ot + (ty + 16 * i) * kLD + c4);
-    if (c.train && t == 0) {
-      float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < kTM / 16; ++i)
-        if (ty + 16 * i < nv) {
-          sp.x += prelu_f(uo[i].x, a_sl.x); sp.y += prelu_f(uo[i].y, a_sl.y);
-          sp.z += prelu_f(uo[i].z, a_sl.z); sp.w += prelu_f(uo[i].w, a_sl.w);
-        }
-      *reinterpret_cast<float4*>(&sm->red[ty][c4]) = sp;
-      __syncthreads();
-      if (tid < kH) {
-        float sacc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) sacc += sm->red[i][tid];
-        sm->shift[tid] = sacc / (float)nv;
-      }
-      __syncthreads();
-    }
-    const float4 sh = c.train ? *reinterpret_cast<const float4*>(sm->shift + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < kTM / 16; ++i) {
-      const int r = ty + 16 * i;
-      if (r < nv) {
-        *reinterpret_cast<float4*>(u_out + (size_t)(row0 + r) * kH + c4) = uo[i];
-        float d;
-        d = prelu_f(uo[i].x, a_sl.x) - sh.x; s1v.x += d; s2v.x = fmaf(d, d, s2v.x);
-        d = prelu_f(uo[i].y, a_sl.y) - sh.y; s1v.y += d; s2v.y = fmaf(d, d, s2v.y);
-        d = prelu_f(uo[i].z, a_sl.z) - sh.z; s1v.z += d; s2v.z = fmaf(d, d, s2v.z);
-        d = prelu_f(uo[i].w, a_sl.w) - sh.w; s1v.w += d; s2v.w = fmaf(d, d, s2v.w);
-      }
-    }
-    // next tile: its first barrier (after staging) orders these Ot reads before the next Ot writes
-  }
-  __syncthreads();
-  if (tid == 0) sm->tc_phase = phase;
-  if (c.train) {
-    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s1v;
-    __syncthreads();
-    float a1 = 0.f, a2 = 0.f;
-    if (tid < kH) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) a1 += sm->red[i][tid];
-    }
-    __syncthreads();
-    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s2v;
-    __syncthreads();
-    if (tid < kH) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) a2 += sm->red[i][tid];
-      bn_finalize(c, sm, net, l, tid, sm->shift[tid], a1, a2, c.B);
-    }
-  }
-  __syncthreads();
-}
-
 // Forward of the input block of the encoder on the noised batch, fed from the raw K-major operand image
 // (ScratchLayout::xk) that build_batch wrote.  Warp 0 drives a two-deep pipeline of bulk asynchronous copies (raw A chunk
 // 32 KB + weight chunk hi/lo 32 KB per 64 input columns) and the 24 MMAs of every chunk; warps 1..3 split every raw
@@ -1285,8 +1136,6 @@ __device__ __forceinline__ void fwd_hidden(const Ctx& c, int net, int l, const L
     else fwd_hidden64(c, net, l, in, u_out);
   } else if (in.kind == kInWide && (c.p->cfg.tensor_cores & 4) && in.img) {
     fwd_wide_img(c, net, l, c.sc + (in.img == 2 ? c.p->sl.yk : c.p->sl.xk), c.sc + (in.img == 2 ? c.p->sl.yref : c.p->sl.xref), u_out);
-  } else if (in.kind == kInWide && (c.p->cfg.tensor_cores & 8)) {
-    fwd_wide_tc(c, net, l, in, u_out);
   } else {
     fwd_hidden_edge(c, net, l, in, u_out);
   }

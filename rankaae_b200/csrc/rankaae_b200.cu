@@ -38,7 +38,8 @@ int validate_config(const raae_config& c) {
   if (c.n_trials <= 0) return fail(-1, "n_trials must be positive");
   if (c.max_rows < c.batch_size) return fail(-1, "max_rows must be >= batch_size");
   if (c.ctas_per_trial != 1) return fail(-1, "ctas_per_trial must be 1 in this version");
-  if (c.tensor_cores & ~31) return fail(-1, "tensor_cores: bits 0 (hidden forward), 1 (hidden backward), 2 (input block from operand images), 3 (other 256-wide forwards), 4 (decoder output forward) are implemented");
+  if (c.tensor_cores & ~0x17)
+    return fail(-1, "tensor_cores: bits 0 (hidden forward), 1 (hidden backward), 2 (input block from operand images), 4 (decoder output forward) are implemented");
   return 0;
 }
 
