@@ -203,6 +203,28 @@ int raae_train_phase(raae_handle* h, int epoch, int step, int phase_mask, const 
 int raae_apply_adam(raae_handle* h, int phase, const float* grads, void* stream);
 int raae_validate_epoch(raae_handle* h, int epoch, float* out_losses, float* out_metrics, void* stream);
 
+/* Peer-memory gradient exchange for the data-parallel mode ("one-shot ... fused into the phase epilogue"):
+ * replaces `all_reduce(grads) ; grads /= world ; raae_apply_adam` by ONE launch that signals the peers, waits for their
+ * gradient vectors, sums them in rank order straight out of the peers' HBM over NVLink (P2P loads, no NCCL call, no
+ * staging copy), divides by `world` and applies AdamW — every rank forms bit-identical updates.
+ *   raae_peer_alloc    allocates this rank's exchange block (flag words + one gradient vector per phase) with cudaMalloc
+ *                      (the only device memory the library owns) and returns its 64-byte CUDA IPC handle;
+ *   raae_peer_connect  maps the blocks of all ranks (handles: [world][64] bytes gathered by the caller in rank order,
+ *                      e.g. with torch.distributed.all_gather_object); the caller runs a barrier afterwards;
+ *   raae_peer_grad_ptr the local gradient vector of `phase` — pass it to raae_train_phase as grads[phase];
+ *   raae_apply_adam_peer  the fused exchange + mean + AdamW launch.  Every rank must call it for the same phases in the
+ *                      same order (the flag protocol counts calls).  A rank that waits > 10 s for a peer traps (the
+ *                      stream reports a launch failure) instead of hanging.
+ *   raae_peer_free     unmaps / frees (also done by raae_destroy); the caller runs a barrier before it.
+ * world <= RAAE_MAX_PEERS ranks on one NVLink / NVSwitch domain, one process per GPU. */
+#define RAAE_MAX_PEERS 8
+#define RAAE_IPC_HANDLE_BYTES 64
+int raae_peer_alloc(raae_handle* h, int world, int rank, unsigned char* ipc_handle_out);
+int raae_peer_connect(raae_handle* h, const unsigned char* all_handles);
+int raae_peer_grad_ptr(raae_handle* h, int phase, float** out);
+int raae_apply_adam_peer(raae_handle* h, int phase, void* stream);
+int raae_peer_free(raae_handle* h);
+
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 int64_t raae_launch_count(const raae_handle* h);
 

@@ -67,7 +67,10 @@ class ValIO(C.Structure):
 EXPORTS = ("raae_last_error", "raae_version", "raae_query_layout", "raae_create", "raae_destroy", "raae_bind_state",
            "raae_bind_dataset", "raae_bind_shapiro_weights", "raae_reset_optimizers", "raae_step_debug",
            "raae_validate", "raae_train_epochs", "raae_launch_count", "raae_set_profile_buffer",
-           "raae_train_phase", "raae_apply_adam", "raae_validate_epoch")
+           "raae_train_phase", "raae_apply_adam", "raae_validate_epoch",
+           "raae_peer_alloc", "raae_peer_connect", "raae_peer_grad_ptr", "raae_apply_adam_peer", "raae_peer_free")
+MAX_PEERS = 8
+IPC_HANDLE_BYTES = 64
 
 _lib = None
 
@@ -103,6 +106,11 @@ def load():
     lib.raae_train_phase.argtypes = [_p, C.c_int, C.c_int, C.c_int, _p, C.POINTER(_p), _p]
     lib.raae_apply_adam.argtypes = [_p, C.c_int, _p, _p]
     lib.raae_validate_epoch.argtypes = [_p, C.c_int, _p, _p, _p]
+    lib.raae_peer_alloc.argtypes = [_p, C.c_int, C.c_int, C.c_char_p]
+    lib.raae_peer_connect.argtypes = [_p, C.c_char_p]
+    lib.raae_peer_grad_ptr.argtypes = [_p, C.c_int, C.POINTER(_p)]
+    lib.raae_apply_adam_peer.argtypes = [_p, C.c_int, _p]
+    lib.raae_peer_free.argtypes = [_p]
     _lib = lib
     return lib
 

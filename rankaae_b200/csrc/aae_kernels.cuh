@@ -516,32 +516,107 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
 }
 
 // AdamW of optimizer `o` from a gradient vector in global memory (data-parallel mode); grid = (blocks, n_trials)
+struct AdamScalars { float decay, w1, b2, w2, ss, bc2s; };
+__device__ __forceinline__ AdamScalars adam_scalars(const float* st, const double* hp, const raae_opt_layout& ol, int o) {
+  const double lr = (double)st[ol.scalar_off + 0], t = (double)st[ol.scalar_off + 1] + 1.0;
+  const double b1 = hp[RAAE_HP_BETA1 + o], b2d = hp[RAAE_HP_BETA2 + o], wd = hp[RAAE_HP_WD + o];
+  AdamScalars a;
+  a.decay = (float)(1.0 - lr * wd); a.w1 = (float)(1.0 - b1); a.b2 = (float)b2d; a.w2 = (float)(1.0 - b2d);
+  a.ss = (float)(lr / (1.0 - pow(b1, t))); a.bc2s = (float)sqrt(1.0 - pow(b2d, t));
+  return a;
+}
+__device__ __forceinline__ void adam_element(const KParams& p, float* st, const raae_opt_layout& ol, const AdamScalars& a, int i, float gi) {
+  int net = -1, rel = 0;
+  for (int k = 0; k < RAAE_NUM_NETS; ++k)
+    if (ol.net_off[k] >= 0 && i >= ol.net_off[k] && i < ol.net_off[k] + p.lay.net[k].n_params) { net = k; rel = i - ol.net_off[k]; }
+  float* P = st + p.lay.net[net].param_off + rel;
+  float* M = st + ol.m_off + i;
+  float* V = st + ol.v_off + i;
+  float pp = *P * a.decay;
+  float m = *M;
+  m = m + (gi - m) * a.w1;
+  float v = *V * a.b2 + (a.w2 * gi) * gi;
+  float denom = sqrtf(v) / a.bc2s + kAdamEps;
+  *P = pp - a.ss * (m / denom);
+  *M = m;
+  *V = v;
+}
 __global__ void raae_adam_kernel(const __grid_constant__ KParams p, int o, const float* __restrict__ grads) {
   const int trial = blockIdx.y;
   float* st = p.state + (size_t)trial * p.lay.state_floats;
-  const double* hp = p.hp + (size_t)trial * RAAE_HP_COUNT;
   const raae_opt_layout& ol = p.lay.opt[o];
-  const double lr = (double)st[ol.scalar_off + 0], t = (double)st[ol.scalar_off + 1] + 1.0;
-  const double b1 = hp[RAAE_HP_BETA1 + o], b2d = hp[RAAE_HP_BETA2 + o], wd = hp[RAAE_HP_WD + o];
-  const float decay = (float)(1.0 - lr * wd), w1 = (float)(1.0 - b1), b2 = (float)b2d, w2 = (float)(1.0 - b2d),
-              ss = (float)(lr / (1.0 - pow(b1, t))), bc2s = (float)sqrt(1.0 - pow(b2d, t));
+  const AdamScalars a = adam_scalars(st, p.hp + (size_t)trial * RAAE_HP_COUNT, ol, o);
   const float* g = grads + (size_t)trial * ol.n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ol.n; i += gridDim.x * blockDim.x) adam_element(p, st, ol, a, i, g[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Data-parallel mode, peer-memory exchange: gradient all-reduce (mean) over NVLink P2P loads fused with AdamW.
+// Replaces all_reduce + divide + raae_adam_kernel + raae_adam_tick_kernel (trainer.py:125-204 under DDP semantics).
+// Protocol, per call `seq` (the same on every rank): block (0,0) release-stores `seq` into word [rank] of every rank's
+// flag array (this rank's vector was written by the preceding raae_train_phase launch on the same stream); every block
+// acquire-polls its OWN flag array until all `world` words reached `seq`, then each element is the sum of the ranks'
+// vectors in rank order (bit-identical on every rank) divided by world.  A vector of phase o is rewritten one step later,
+// after >= 3 further exchanges which every peer enters only once its previous launch (the reader) has finished.
+// ------------------------------------------------------------------------------------------
+struct PeerArgs {
+  const float* grads[RAAE_MAX_PEERS];    // this phase's gradient vector on every rank (peer-mapped), [n_trials][opt[o].n]
+  unsigned* flags[RAAE_MAX_PEERS];       // every rank's flag words [RAAE_MAX_PEERS]
+  unsigned* done;                        // local: blocks finished (for the optimizer step counter)
+  int world, rank;
+  unsigned seq;
+};
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void raae_adam_peer_kernel(const __grid_constant__ KParams p, int o, const __grid_constant__ PeerArgs pa) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < pa.world) {
+    __threadfence_system();
+    st_release_sys(pa.flags[threadIdx.x] + pa.rank, pa.seq);
+  }
+  if (threadIdx.x < pa.world) {
+    const unsigned* f = pa.flags[pa.rank] + threadIdx.x;
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_acquire_sys(f) - pa.seq) < 0) {
+      __nanosleep(64);
+      if (global_ns() - t0 > 10000000000ull) __trap();      // a peer never arrived: fail the launch instead of hanging
+    }
+  }
+  __syncthreads();
+  const int trial = blockIdx.y;
+  float* st = p.state + (size_t)trial * p.lay.state_floats;
+  const raae_opt_layout& ol = p.lay.opt[o];
+  const AdamScalars a = adam_scalars(st, p.hp + (size_t)trial * RAAE_HP_COUNT, ol, o);
+  const float wf = (float)pa.world;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ol.n; i += gridDim.x * blockDim.x) {
-    int net = -1, rel = 0;
-    for (int k = 0; k < RAAE_NUM_NETS; ++k)
-      if (ol.net_off[k] >= 0 && i >= ol.net_off[k] && i < ol.net_off[k] + p.lay.net[k].n_params) { net = k; rel = i - ol.net_off[k]; }
-    float* P = st + p.lay.net[net].param_off + rel;
-    float* M = st + ol.m_off + i;
-    float* V = st + ol.v_off + i;
-    const float gi = g[i];
-    float pp = *P * decay;
-    float m = *M;
-    m = m + (gi - m) * w1;
-    float v = *V * b2 + (w2 * gi) * gi;
-    float denom = sqrtf(v) / bc2s + kAdamEps;
-    *P = pp - ss * (m / denom);
-    *M = m;
-    *V = v;
+    float g = 0.f;
+    for (int r = 0; r < pa.world; ++r) g += ld_relaxed_sys(pa.grads[r] + (size_t)trial * ol.n + i);
+    adam_element(p, st, ol, a, i, pa.world > 1 ? g / wf : g);
+  }
+  // optimizer step counter: by the last block to finish (every block has read the scalars by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned total = gridDim.x * gridDim.y;
+    if (atomicAdd(pa.done, 1u) == total - 1) {
+      *pa.done = 0;
+      for (int t = 0; t < (int)gridDim.y; ++t) p.state[(size_t)t * p.lay.state_floats + ol.scalar_off + 1] += 1.f;
+    }
   }
 }
 // step counter of optimizer o, after raae_adam_kernel

@@ -153,7 +153,30 @@ struct raae_handle {
   bool bound_state, bound_data;
   int shapiro_n;
   long long* prof;
+  // peer-memory exchange of the data-parallel mode (raae_peer_*)
+  struct Peer {
+    int world, rank;
+    bool connected;
+    unsigned seq;
+    size_t bytes, grad_off[RAAE_NUM_PHASES];
+    unsigned char* local;                       // cudaMalloc: [256 B flags + done counter][gradient vector per phase]
+    unsigned char* mapped[RAAE_MAX_PEERS];      // every rank's block in this process' address space
+  } peer;
 };
+
+namespace {
+constexpr size_t kPeerHeaderBytes = 256;        // words [0, 8): flags, word 16: finished-block counter
+int peer_release(raae_handle* h) {
+  if (!h->peer.local) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < h->peer.world; ++r)
+    if (r != h->peer.rank && h->peer.mapped[r]) cudaIpcCloseMemHandle(h->peer.mapped[r]);
+  cudaFree(h->peer.local);
+  std::memset(&h->peer, 0, sizeof(h->peer));
+  return 0;
+}
+}  // namespace
 
 extern "C" {
 
@@ -188,6 +211,7 @@ int raae_create(const raae_config* cfg, int device, raae_handle** out) {
   h->bound_state = h->bound_data = false;
   h->shapiro_n = 0;
   h->prof = nullptr;
+  std::memset(&h->peer, 0, sizeof(h->peer));
   RAAE_CUDA(cudaFuncSetAttribute(raae::raae_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raae::kSmemBytes));
   RAAE_CUDA(cudaFuncSetAttribute(raae::raae_val_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raae::kSmemBytes));
   *out = h;
@@ -195,6 +219,7 @@ int raae_create(const raae_config* cfg, int device, raae_handle** out) {
 }
 
 int raae_destroy(raae_handle* h) {
+  if (h) peer_release(h);
   delete h;
   return 0;
 }
@@ -371,6 +396,94 @@ int raae_validate_epoch(raae_handle* h, int epoch, float* out_losses, float* out
   RAAE_CUDA(cudaGetLastError());
   h->launches++;
   return 0;
+}
+
+int raae_peer_alloc(raae_handle* h, int world, int rank, unsigned char* ipc_handle_out) {
+  if (!h || !ipc_handle_out) return fail(-1, "null argument");
+  if (world < 1 || world > RAAE_MAX_PEERS || rank < 0 || rank >= world) return fail(-1, "world must be in [1, 8] and rank in [0, world)");
+  if (h->peer.local) return fail(-1, "exchange block already allocated");
+  static_assert(sizeof(cudaIpcMemHandle_t) == RAAE_IPC_HANDLE_BYTES, "IPC handle size");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  size_t off = kPeerHeaderBytes;
+  for (int o = 0; o < RAAE_NUM_PHASES; ++o) {
+    h->peer.grad_off[o] = off;
+    off += (((size_t)h->kp.cfg.n_trials * h->kp.lay.opt[o].n * sizeof(float)) + 255) & ~(size_t)255;
+  }
+  void* ptr = nullptr;
+  RAAE_CUDA(cudaMalloc(&ptr, off));
+  RAAE_CUDA(cudaMemset(ptr, 0, off));
+  RAAE_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t ipc;
+  cudaError_t e = cudaIpcGetMemHandle(&ipc, ptr);
+  if (e != cudaSuccess) { cudaFree(ptr); return fail(-2, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+  std::memcpy(ipc_handle_out, &ipc, RAAE_IPC_HANDLE_BYTES);
+  h->peer.world = world;
+  h->peer.rank = rank;
+  h->peer.bytes = off;
+  h->peer.local = (unsigned char*)ptr;
+  h->peer.mapped[rank] = h->peer.local;
+  h->peer.seq = 0;
+  h->peer.connected = false;
+  return 0;
+}
+
+int raae_peer_connect(raae_handle* h, const unsigned char* all_handles) {
+  if (!h || !all_handles) return fail(-1, "null argument");
+  if (!h->peer.local) return fail(-1, "raae_peer_alloc has not been called");
+  if (h->peer.connected) return fail(-1, "already connected");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  for (int r = 0; r < h->peer.world; ++r) {
+    if (r == h->peer.rank) continue;
+    cudaIpcMemHandle_t ipc;
+    std::memcpy(&ipc, all_handles + (size_t)r * RAAE_IPC_HANDLE_BYTES, RAAE_IPC_HANDLE_BYTES);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+      return fail(-2, "cudaIpcOpenMemHandle (rank " + std::to_string(r) + "): " + cudaGetErrorString(e) +
+                          " - the peer exchange needs one process per GPU on a P2P-capable (NVLink) node");
+    h->peer.mapped[r] = (unsigned char*)ptr;
+  }
+  h->peer.connected = true;
+  return 0;
+}
+
+int raae_peer_grad_ptr(raae_handle* h, int phase, float** out) {
+  if (!h || !out) return fail(-1, "null argument");
+  if (phase < 0 || phase >= RAAE_NUM_PHASES) return fail(-1, "phase out of range");
+  if (!h->peer.local) return fail(-1, "raae_peer_alloc has not been called");
+  *out = (float*)(h->peer.local + h->peer.grad_off[phase]);
+  return 0;
+}
+
+int raae_apply_adam_peer(raae_handle* h, int phase, void* stream) {
+  if (!h) return fail(-1, "null handle");
+  if (phase < 0 || phase >= RAAE_NUM_PHASES) return fail(-1, "phase out of range");
+  if (!h->bound_state) return fail(-1, "state not bound");
+  if (!h->peer.connected) return fail(-1, "peer exchange not connected (raae_peer_alloc / raae_peer_connect)");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  raae::PeerArgs pa;
+  std::memset(&pa, 0, sizeof(pa));
+  for (int r = 0; r < h->peer.world; ++r) {
+    pa.grads[r] = (const float*)(h->peer.mapped[r] + h->peer.grad_off[phase]);
+    pa.flags[r] = (unsigned*)h->peer.mapped[r];
+  }
+  pa.done = (unsigned*)h->peer.local + 16;
+  pa.world = h->peer.world;
+  pa.rank = h->peer.rank;
+  pa.seq = ++h->peer.seq;
+  const int nt = h->kp.cfg.n_trials;
+  int bx = (h->kp.lay.opt[phase].n + 255) / 256;
+  if (bx > 592) bx = 592;                       // 4 blocks per SM: every block resident, the flag wait cannot starve a peer
+  dim3 grid(bx, nt);
+  raae::raae_adam_peer_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->kp, phase, pa);
+  RAAE_CUDA(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int raae_peer_free(raae_handle* h) {
+  if (!h) return fail(-1, "null handle");
+  return peer_release(h);
 }
 
 int64_t raae_launch_count(const raae_handle* h) { return h ? h->launches : 0; }

@@ -1,13 +1,21 @@
-"""Single-trial data-parallel training (BASELINE.json configs[3]: one trial, per-rank batch, NCCL gradient all-reduce).
+"""Single-trial data-parallel training (BASELINE.json configs[3]: one trial, per-rank batch, gradient all-reduce).
 
 Every rank holds the same weights and AdamW state and its own shard of the training rows.  Each loss phase of each batch
 is one split-phase kernel launch that exports the phase's gradient vector instead of applying it
-(`raae_train_phase`), one `torch.distributed.all_reduce` (mean) of that vector — 5 all-reduces of 118–238 KB per step,
-latency-bound — and one fused AdamW launch (`raae_apply_adam`).  BatchNorm batch statistics and Kendall
-pairs stay rank-local (DistributedDataParallel semantics, not large-batch semantics); the BatchNorm running buffers
-are averaged across ranks before every validation block so that all ranks score the same model.
+(`raae_train_phase`), followed by the exchange of that vector (118-238 KB, 5 per step, latency-bound):
+
+* `exchange="peer"` (default for world > 1): ONE launch, `raae_apply_adam_peer` — the ranks signal each other through
+  flag words in peer-mapped memory, every rank sums the gradient vectors in rank order straight out of the peers' HBM
+  (P2P loads over NVLink, CUDA IPC mappings, no NCCL call), divides by world and applies AdamW in the same kernel;
+* `exchange="nccl"`: `torch.distributed.all_reduce` + divide + `raae_apply_adam` (+ its step-counter kernel) — four
+  launches, kept as the yardstick (bit-identical to the peer path for world 2, where the sum has one order).
+
+BatchNorm batch statistics and Kendall pairs stay rank-local (DistributedDataParallel semantics, not large-batch
+semantics); the BatchNorm running buffers are averaged across ranks before every validation block so that all ranks
+score the same model.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -25,8 +33,15 @@ def shard_rows(n_rows, world, rank):
 
 
 class DataParallelTrainer:
-    def __init__(self, cfg, spec_train, aux_train, spec_val, aux_val, device, rank=0, world=1, seed=0):
+    def __init__(self, cfg, spec_train, aux_train, spec_val, aux_val, device, rank=0, world=1, seed=0, exchange=None):
         self.rank, self.world = rank, world
+        if exchange is None:
+            exchange = os.environ.get("RAAE_DP_EXCHANGE", "peer" if world > 1 else "nccl")
+        if exchange not in ("peer", "nccl"):
+            raise ValueError(f"exchange must be 'peer' or 'nccl', got {exchange!r}")
+        if world > L.MAX_PEERS and exchange == "peer":
+            raise ValueError(f"the peer exchange supports up to {L.MAX_PEERS} ranks (one NVLink domain)")
+        self.exchange = exchange
         self.cfg = dict(cfg)
         self.cfg.setdefault("epoch_stop_smooth", 500)
         lo, hi = shard_rows(len(spec_train), world, rank)
@@ -36,10 +51,45 @@ class DataParallelTrainer:
         self.engine.load_modules(0, *self.modules)
         self.engine.bind_dataset(spec_train[lo:hi], aux_train[lo:hi], spec_val, aux_val)
         lay = self.engine.lay
-        self.grads = [torch.zeros(1, lay.opt[o].n, dtype=torch.float32, device=self.engine.device) for o in range(L.NUM_PHASES)]
         self._gptr = (L._p * L.NUM_PHASES)()
+        if exchange == "peer":
+            self._connect_peers()
+        else:
+            self.grads = [torch.zeros(1, lay.opt[o].n, dtype=torch.float32, device=self.engine.device) for o in range(L.NUM_PHASES)]
+            self._grad_ptrs = [g.data_ptr() for g in self.grads]
         bs = int(cfg["batch_size"])
         self.n_steps = (self.engine.n_train + bs - 1) // bs
+
+    def _connect_peers(self):
+        """Allocates this rank's exchange block, gathers the CUDA IPC handles of all ranks and maps their blocks."""
+        eng = self.engine
+        mine = C.create_string_buffer(L.IPC_HANDLE_BYTES)
+        L.check(eng.lib.raae_peer_alloc(eng.handle, self.world, self.rank, mine))
+        handles = bytes(mine.raw)
+        if self.world > 1:                              # [world][64] bytes in rank order, gathered on this rank's own device
+            t = torch.frombuffer(bytearray(handles), dtype=torch.uint8).to(eng.device)
+            out = torch.empty(self.world * L.IPC_HANDLE_BYTES, dtype=torch.uint8, device=eng.device)
+            torch.distributed.all_gather_into_tensor(out, t)
+            handles = out.cpu().numpy().tobytes()
+        L.check(eng.lib.raae_peer_connect(eng.handle, handles))
+        self._grad_ptrs = []
+        for o in range(L.NUM_PHASES):
+            ptr = L._p()
+            L.check(eng.lib.raae_peer_grad_ptr(eng.handle, o, C.byref(ptr)))
+            self._grad_ptrs.append(ptr.value)
+        if self.world > 1:                              # every block is mapped before the first flag is written
+            torch.distributed.all_reduce(torch.zeros(1, device=eng.device))
+            torch.cuda.synchronize(eng.device)
+
+    def close(self):
+        """Barrier + unmap (no rank may free its block while a peer can still read it), then the engine."""
+        if self.exchange == "peer" and self.engine.handle:
+            torch.cuda.synchronize(self.engine.device)
+            if self.world > 1:
+                torch.distributed.all_reduce(torch.zeros(1, device=self.engine.device))
+                torch.cuda.synchronize(self.engine.device)
+            L.check(self.engine.lib.raae_peer_free(self.engine.handle))
+        self.engine.close()
 
     def _allreduce(self, t):
         if self.world > 1:
@@ -67,10 +117,13 @@ class DataParallelTrainer:
                 if o == 4 and epoch >= stop_smooth:
                     continue
                 for k in range(L.NUM_PHASES):
-                    self._gptr[k] = self.grads[k].data_ptr() if k == o else None
+                    self._gptr[k] = self._grad_ptrs[k] if k == o else None
                 L.check(eng.lib.raae_train_phase(eng.handle, int(epoch), s, 1 << o, perm.data_ptr(), self._gptr, eng.stream))
-                self._allreduce(self.grads[o])
-                L.check(eng.lib.raae_apply_adam(eng.handle, o, self.grads[o].data_ptr(), eng.stream))
+                if self.exchange == "peer":
+                    L.check(eng.lib.raae_apply_adam_peer(eng.handle, o, eng.stream))
+                else:
+                    self._allreduce(self.grads[o])
+                    L.check(eng.lib.raae_apply_adam(eng.handle, o, self._grad_ptrs[o], eng.stream))
         self._sync_bn_buffers()
         losses = torch.zeros(1, 12, dtype=torch.float32, device=eng.device)
         metrics = torch.zeros(1, 6, dtype=torch.float32, device=eng.device)

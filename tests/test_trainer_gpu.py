@@ -124,6 +124,30 @@ def test_data_parallel_world1_equals_fused_epoch():
     dp.engine.close()
 
 
+def test_data_parallel_peer_exchange_world1_bitwise():
+    """The fused exchange + AdamW launch (raae_apply_adam_peer; flags, rank-ordered sum, in-kernel step counter) with one
+    rank must give bit-identical weights to raae_apply_adam fed the same gradient vector."""
+    import torch
+    from rankaae_b200.dp import DataParallelTrainer
+    cfg = dict(EXAMPLE, batch_size=128, max_epoch=30)
+    spec, aux = O.synthetic_dataset(700, O.Config.from_dict(cfg), seed=8, dtype=np.float32)
+    tr, va = (spec[:450], aux[:450]), (spec[450:560], aux[450:560])
+    a = DataParallelTrainer(cfg, tr[0], tr[1], va[0], va[1], "cuda:0", rank=0, world=1, seed=4, exchange="nccl")
+    b = DataParallelTrainer(cfg, tr[0], tr[1], va[0], va[1], "cuda:0", rank=0, world=1, seed=4, exchange="peer")
+    perm = a.engine.make_perm(2)
+    for e in range(2):
+        la, ma = a.train_epoch(e, perm[e])
+        lb, mb = b.train_epoch(e, perm[e])
+        torch.cuda.synchronize()
+        assert torch.equal(ma, mb) and torch.equal(la, lb), (ma, mb)
+    assert torch.equal(a.engine.state[0], b.engine.state[0])          # parameters, moments, step counters, BN buffers
+    n0 = b.engine.launch_count
+    b.train_epoch(2, perm[0])
+    assert b.engine.launch_count - n0 == 4 * 5 * 2 + 1               # per phase: 1 phase launch + 1 fused exchange/AdamW
+    a.close()
+    b.close()
+
+
 DP_WORKER = r"""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
@@ -135,20 +159,29 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{{local}}"))
 cfg = dict(EXAMPLE, batch_size=128, max_epoch=12, n_aux=6)            # config #4 uses 6 descriptors
 spec, aux = O.synthetic_dataset(1200, O.Config.from_dict(cfg), seed=8, dtype=np.float32)
-dp = DataParallelTrainer(cfg, spec[:840], aux[:840], spec[840:1020], aux[840:1020], f"cuda:{{local}}", rank, world, seed=2)
-hist = []
-m = dp.train(callback=lambda e, mm: hist.append(mm))
-v = dp.state_vector()
-ref = v.clone(); dist.broadcast(ref, 0)
-assert float((v - ref).abs().max()) == 0.0, "ranks diverged"          # identical updates on every rank
-assert all(np.isfinite(x) for x in m) and hist[-1][1] < 0.6 * hist[0][1], (hist[0], hist[-1])
+final = {{}}
+for exchange in ("peer", "nccl"):
+    dp = DataParallelTrainer(cfg, spec[:840], aux[:840], spec[840:1020], aux[840:1020], f"cuda:{{local}}", rank, world, seed=2,
+                             exchange=exchange)
+    torch.manual_seed(11)                                              # same shuffles in both modes
+    hist = []
+    m = dp.train(callback=lambda e, mm: hist.append(mm))
+    v = dp.state_vector()
+    ref = v.clone(); dist.broadcast(ref, 0)
+    assert float((v - ref).abs().max()) == 0.0, f"ranks diverged ({{exchange}})"   # identical updates on every rank
+    assert all(np.isfinite(x) for x in m) and hist[-1][1] < 0.6 * hist[0][1], (exchange, hist[0], hist[-1])
+    final[exchange] = dp.engine.state[0].clone()
+    dp.close()
+# with 2 ranks the sum has one order: the peer-memory exchange must reproduce the NCCL path bit for bit
+assert torch.equal(final["peer"], final["nccl"]), float((final["peer"] - final["nccl"]).abs().max())
 open(os.path.join({out!r}, f"ok{{rank}}"), "w").write(repr(m))
 dist.destroy_process_group()
 """
 
 
 def test_data_parallel_two_gpus(tmp_path):
-    """2 ranks, NCCL all-reduce per phase: weights stay bit-identical across ranks and the trial learns."""
+    """2 ranks, gradient exchange per phase through peer memory (fused with AdamW) and through NCCL: weights stay
+    bit-identical across ranks, the trial learns, and both exchanges give the same bits."""
     import subprocess
     import sys
     import torch
