@@ -61,30 +61,40 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.window = None                      # (t0, t1) wall-clock bounds of the timed `value` region
 
     def run(self):
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                                      str(self.index)], capture_output=True, text=True, timeout=30).stdout.strip()
                 if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                    self.rows.append([c.strip() for c in out.split(",")] + [time.time()])
             except Exception:
                 pass
             time.sleep(0.2)
 
     def summary(self):
+        """Median SM clock and throttle reasons.  The sampler runs from the warm-up to the end of the last timed leg (the GPU
+        executes the same kernels throughout); samples that fall inside the timed `value` region are used when there are
+        any (a query takes longer than a short region when 8 ranks share the box), else all samples under load."""
         self.stop_flag = True
+        self.join(timeout=35)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        rows, window = self.rows, "warm-up + timed legs (same kernels)"
+        if self.window is not None:
+            inside = [r for r in self.rows if self.window[0] <= r[-1] <= self.window[1] + 0.25]
+            if inside:
+                rows, window = inside, "timed region"
+        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][2]) if self.rows else None,
-                "samples": len(self.rows), "reasons": sorted(reasons)}
+                "samples": len(rows), "window": window, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------
@@ -180,6 +190,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
@@ -207,24 +219,25 @@ def run_ours(args):
 
     K, W = args.steps, args.warmup
     epoch = 0
+    sampler = ClockSampler(local)
+    sampler.start()
     eng.train_epochs(epoch, W)
     epoch += W
     barrier()
 
     # ---- value: inputs resident, K epochs back to back, device-timed ----
     perm = eng.make_perm(K)
-    sampler = ClockSampler(local)
-    sampler.start()
     l0 = eng.launch_count
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
     e0.record()
     losses, metrics = eng.train_epochs(epoch, K, perm)
     e1.record()
     barrier()
+    sampler.window = (w0, time.time())
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count - l0
-    clocks = sampler.summary()
     epoch += K
     finite = bool(torch.isfinite(losses).all().item() and torch.isfinite(metrics).all().item())
     ms_per_step = ms_total / K
@@ -258,6 +271,7 @@ def run_ours(args):
     r1.record()
     barrier()
     train_ms = r0.elapsed_time(r1) / K
+    clocks = sampler.summary()
     eng.bind_dataset(*dset)
     peaks = {}
     try:

@@ -865,7 +865,14 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
       Ss[i] = s; Ds[i] = d;
     }
     __syncthreads();
-    for (int i = tid; i < B; i += kThreads) {
+    for (int ib = 0; ib < B; ib += kThreads) {
+      // without the gradient only the totals are needed and p_ij = p_ji: each unordered pair is visited once (j > i) and
+      // the totals are doubled at the end; alternate passes run the rows in reverse so that every thread gets long and
+      // short rows (row i has B - 1 - i partners)
+      const int i = (want_grad || !((ib / kThreads) & 1)) ? ib + tid : ib + kThreads - 1 - tid;
+      if (i >= B) continue;
+      const int jb = want_grad ? 0 : max(0, i + 1 - j0);         // first staged row of this chunk that row i pairs with
+      if (jb >= nj) continue;
       float si[kZ], di[kZ], A[kZ], T[kZ], fp[kZ], fn[kZ];
 #pragma unroll
       for (int k = 0; k < kZ; ++k) {
@@ -874,14 +881,14 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
         A[k] = 0.f; T[k] = 0.f; fp[k] = 0.f; fn[k] = 0.f;
       }
       switch (K) {
-        case 1: kendall_row<1>(Ss, Ds, nj, si, di, A, T, fp, fn, cs, co); break;
-        case 2: kendall_row<2>(Ss, Ds, nj, si, di, A, T, fp, fn, cs, co); break;
-        case 3: kendall_row<3>(Ss, Ds, nj, si, di, A, T, fp, fn, cs, co); break;
-        case 4: kendall_row<4>(Ss, Ds, nj, si, di, A, T, fp, fn, cs, co); break;
-        case 5: kendall_row<5>(Ss, Ds, nj, si, di, A, T, fp, fn, cs, co); break;
-        case 6: kendall_row<6>(Ss, Ds, nj, si, di, A, T, fp, fn, cs, co); break;
-        case 7: kendall_row<7>(Ss, Ds, nj, si, di, A, T, fp, fn, cs, co); break;
-        default: kendall_row<8>(Ss, Ds, nj, si, di, A, T, fp, fn, cs, co); break;
+        case 1: kendall_row<1>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 2: kendall_row<2>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 3: kendall_row<3>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 4: kendall_row<4>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 5: kendall_row<5>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 6: kendall_row<6>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 7: kendall_row<7>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
+        default: kendall_row<8>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
       }
 #pragma unroll
       for (int k = 0; k < kZ; ++k) { sp[k] += (double)fp[k]; sn[k] -= (double)fn[k]; }
@@ -900,10 +907,11 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
   double loss = 0.0;
   for (int k = 0; k < kZ; ++k) {
     if (k >= K) break;
-    double tsp = block_sum_d(sp[k], sm->redd);
-    double tsn = block_sum_d(sn[k], sm->redd);
-    double tcs = block_sum_d((double)cs[k], sm->redd);
-    double tco = block_sum_d((double)co[k], sm->redd);
+    const double sym = want_grad ? 1.0 : 2.0;             // ordered pairs = 2 x unordered pairs
+    double tsp = sym * block_sum_d(sp[k], sm->redd);
+    double tsn = sym * block_sum_d(sn[k], sm->redd);
+    double tcs = sym * block_sum_d((double)cs[k], sm->redd);
+    double tco = sym * block_sum_d((double)co[k], sm->redd);
     double w = 1.0;
     if (c.p->cfg.kendall_activation) {
       double n_same = tcs > 1.0 ? tcs : 1.0, n_opp = tco > 1.0 ? tco : 1.0;
