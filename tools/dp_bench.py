@@ -92,7 +92,16 @@ def main():
         for _ in range(20):
             exchange_update(dp, 2)
         us = min(timed(lambda: [exchange_update(dp, 2) for _ in range(reps)], dev, world) for r in range(3)) * 1e3 / reps
-        res[exchange] = {"ms_per_epoch": ms, "ms_per_step": ms / dp.n_steps, "steps_per_sec": dp.n_steps / ms * 1e3,
+        v = dp.state_vector()
+        same = True
+        if world > 1:                                                   # every rank must hold the same weights, bit for bit
+            ref = v.clone()
+            dist.broadcast(ref, 0)
+            flag = torch.tensor([float(torch.equal(v, ref))], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            same = bool(flag.item() == 1.0)
+        finite = bool(torch.isfinite(v).all().item())
+        res[exchange] = {"ranks_bit_identical": same, "finite": finite, "ms_per_epoch": ms, "ms_per_step": ms / dp.n_steps, "steps_per_sec": dp.n_steps / ms * 1e3,
                          "samples_per_sec": dp.n_steps * bs * world / ms * 1e3, "exchange_update_us": us,
                          "launches_per_phase": 2 if exchange == "peer" else (5 if world > 1 else 3)}
         dp.close()
