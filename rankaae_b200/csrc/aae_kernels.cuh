@@ -564,6 +564,7 @@ struct PeerArgs {
   unsigned* flags[RAAE_MAX_PEERS];       // every rank's flag words [RAAE_MAX_PEERS]
   unsigned* done;                        // local: blocks finished (for the optimizer step counter)
   int world, rank;
+  int replicas;                          // trials resident per rank (identical weights, one shard each)
   unsigned seq;
 };
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
@@ -585,7 +586,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 __global__ void raae_adam_peer_kernel(const __grid_constant__ KParams p, int o, const __grid_constant__ PeerArgs pa) {
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < pa.world) {
+  if (blockIdx.x == 0 && threadIdx.x < pa.world) {
     __threadfence_system();
     st_release_sys(pa.flags[threadIdx.x] + pa.rank, pa.seq);
   }
@@ -598,24 +599,37 @@ __global__ void raae_adam_peer_kernel(const __grid_constant__ KParams p, int o, 
     }
   }
   __syncthreads();
-  const int trial = blockIdx.y;
-  float* st = p.state + (size_t)trial * p.lay.state_floats;
+  // `replicas` = the trials resident on every rank: they hold the SAME weights and act as further data-parallel ranks
+  // (one CTA each in raae_train_phase), so the mean runs over world x replicas vectors, summed in (rank, replica) order,
+  // and the one update is applied to every local replica's state
+  const int V = pa.replicas;
   const raae_opt_layout& ol = p.lay.opt[o];
-  const AdamScalars a = adam_scalars(st, p.hp + (size_t)trial * RAAE_HP_COUNT, ol, o);
-  const float wf = (float)pa.world;
+  const float wf = (float)(pa.world * V);
+  // the replicas share the hyper-parameter row (dp.py) and, as long as their schedulers agree, lr and step count:
+  // the float64 AdamW scalars are formed once and only re-formed for a replica whose lr / step differ
+  const AdamScalars a0 = adam_scalars(p.state, p.hp, ol, o);
+  const float lr0 = p.state[ol.scalar_off + 0], t0 = p.state[ol.scalar_off + 1];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ol.n; i += gridDim.x * blockDim.x) {
     float g = 0.f;
-    for (int r = 0; r < pa.world; ++r) g += ld_relaxed_sys(pa.grads[r] + (size_t)trial * ol.n + i);
-    adam_element(p, st, ol, a, i, pa.world > 1 ? g / wf : g);
+    for (int r = 0; r < pa.world; ++r) {
+      const float* src = pa.grads[r] + i;
+#pragma unroll 4
+      for (int v = 0; v < V; ++v) g += ld_relaxed_sys(src + (size_t)v * ol.n);
+    }
+    if (pa.world * V > 1) g = g / wf;
+    for (int v = 0; v < V; ++v) {
+      float* st = p.state + (size_t)v * p.lay.state_floats;
+      const bool same = st[ol.scalar_off + 0] == lr0 && st[ol.scalar_off + 1] == t0;
+      adam_element(p, st, ol, same ? a0 : adam_scalars(st, p.hp + (size_t)v * RAAE_HP_COUNT, ol, o), i, g);
+    }
   }
-  // optimizer step counter: by the last block to finish (every block has read the scalars by then)
+  // optimizer step counters: by the last block to finish (every block has read the scalars by then)
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned total = gridDim.x * gridDim.y;
-    if (atomicAdd(pa.done, 1u) == total - 1) {
+    if (atomicAdd(pa.done, 1u) == gridDim.x - 1) {
       *pa.done = 0;
-      for (int t = 0; t < (int)gridDim.y; ++t) p.state[(size_t)t * p.lay.state_floats + ol.scalar_off + 1] += 1.f;
+      for (int v = 0; v < V; ++v) p.state[(size_t)v * p.lay.state_floats + ol.scalar_off + 1] += 1.f;
     }
   }
 }

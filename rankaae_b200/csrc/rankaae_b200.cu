@@ -470,12 +470,11 @@ int raae_apply_adam_peer(raae_handle* h, int phase, void* stream) {
   pa.done = (unsigned*)h->peer.local + 16;
   pa.world = h->peer.world;
   pa.rank = h->peer.rank;
+  pa.replicas = h->kp.cfg.n_trials;
   pa.seq = ++h->peer.seq;
-  const int nt = h->kp.cfg.n_trials;
   int bx = (h->kp.lay.opt[phase].n + 255) / 256;
   if (bx > 592) bx = 592;                       // 4 blocks per SM: every block resident, the flag wait cannot starve a peer
-  dim3 grid(bx, nt);
-  raae::raae_adam_peer_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->kp, phase, pa);
+  raae::raae_adam_peer_kernel<<<bx, 256, 0, (cudaStream_t)stream>>>(h->kp, phase, pa);
   RAAE_CUDA(cudaGetLastError());
   h->launches++;
   return 0;

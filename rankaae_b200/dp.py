@@ -33,10 +33,17 @@ def shard_rows(n_rows, world, rank):
 
 
 class DataParallelTrainer:
-    def __init__(self, cfg, spec_train, aux_train, spec_val, aux_val, device, rank=0, world=1, seed=0, exchange=None):
-        self.rank, self.world = rank, world
+    """`replicas` > 1 puts that many data-parallel replicas of the trial on EVERY GPU (one CTA / SM each, identical
+    weights, own shard, own noise streams): the job then has world x replicas shards with DistributedDataParallel
+    semantics - global batch = batch_size x world x replicas - and the exchange kernel averages over all of them.
+    replicas = 1 is BASELINE.json configs[3] as written (one 512-row batch per GPU, one SM busy per GPU)."""
+
+    def __init__(self, cfg, spec_train, aux_train, spec_val, aux_val, device, rank=0, world=1, seed=0, exchange=None,
+                 replicas=1, shard_seeds=None):
+        self.rank, self.world, self.replicas = rank, world, int(replicas)
+        V = self.replicas
         if exchange is None:
-            exchange = os.environ.get("RAAE_DP_EXCHANGE", "peer" if world > 1 else "nccl")
+            exchange = os.environ.get("RAAE_DP_EXCHANGE", "peer" if world * V > 1 else "nccl")
         if exchange not in ("peer", "nccl"):
             raise ValueError(f"exchange must be 'peer' or 'nccl', got {exchange!r}")
         if world > L.MAX_PEERS and exchange == "peer":
@@ -44,21 +51,29 @@ class DataParallelTrainer:
         self.exchange = exchange
         self.cfg = dict(cfg)
         self.cfg.setdefault("epoch_stop_smooth", 500)
-        lo, hi = shard_rows(len(spec_train), world, rank)
-        self.engine = Engine(self.cfg, n_trials=1, device=device, max_rows=max(int(cfg["batch_size"]), len(spec_val)),
-                             seeds=[seed * 1000 + rank])            # rank-local noise / dropout streams
-        self.modules = build_modules(self.cfg, seed=seed)             # identical initial weights on every rank
-        self.engine.load_modules(0, *self.modules)
-        self.engine.bind_dataset(spec_train[lo:hi], aux_train[lo:hi], spec_val, aux_val)
+        self.per = len(spec_train) // (world * V)                     # rows of one shard; shard q = rank * V + replica
+        lo, hi = rank * V * self.per, (rank + 1) * V * self.per
+        self.engine = Engine(self.cfg, n_trials=V, device=device, max_rows=max(int(cfg["batch_size"]), len(spec_val)),
+                             seeds=shard_seeds if shard_seeds is not None else
+                             [seed * 1000 + rank * V + v for v in range(V)])         # shard-local noise / dropout streams
+        self.modules = build_modules(self.cfg, seed=seed)             # identical initial weights on every rank / replica
+        for v in range(V):
+            self.engine.load_modules(v, *self.modules)
+        self.engine.bind_dataset(spec_train[lo:hi], aux_train[lo:hi], spec_val, aux_val, rows_per_trial=self.per)
         lay = self.engine.lay
         self._gptr = (L._p * L.NUM_PHASES)()
         if exchange == "peer":
             self._connect_peers()
         else:
-            self.grads = [torch.zeros(1, lay.opt[o].n, dtype=torch.float32, device=self.engine.device) for o in range(L.NUM_PHASES)]
+            self.grads = [torch.zeros(V, lay.opt[o].n, dtype=torch.float32, device=self.engine.device) for o in range(L.NUM_PHASES)]
             self._grad_ptrs = [g.data_ptr() for g in self.grads]
         bs = int(cfg["batch_size"])
-        self.n_steps = (self.engine.n_train + bs - 1) // bs
+        self.n_steps = (self.per + bs - 1) // bs
+        self._shard_off = (torch.arange(V, device=self.engine.device, dtype=torch.int32) * self.per).view(V, 1)
+
+    def make_perm(self):
+        """One shuffle per replica, as indices into the rank's rows: replica v owns rows [v * per, (v + 1) * per)."""
+        return (self.engine.make_perm(1)[0] + self._shard_off).contiguous()
 
     def _connect_peers(self):
         """Allocates this rank's exchange block, gathers the CUDA IPC handles of all ranks and maps their blocks."""
@@ -96,21 +111,47 @@ class DataParallelTrainer:
             torch.distributed.all_reduce(t)
             t /= self.world
 
+    def _mean_over_shards(self, block):
+        """block: [replicas][k] view of the state -> every replica (on every rank) gets the mean over all shards."""
+        m = block.mean(0, keepdim=True) if self.replicas > 1 else block.clone()
+        self._allreduce(m)
+        block.copy_(m.expand_as(block))
+
     def _sync_bn_buffers(self):
-        if self.world == 1:
+        """Before the validation block: BatchNorm running buffers and the running sum / count of the mutual-information
+        loss (the one rank-local input of the combined metric, trainer.py:294-297) are averaged over all shards, so every
+        replica scores the same model with the same metric and the ReduceLROnPlateau states cannot drift apart."""
+        if self.world * self.replicas == 1:
             return
-        lay, st = self.engine.lay, self.engine.state[0]
+        lay, st = self.engine.lay, self.engine.state
         for ni in (0, 1):
             n = lay.net[ni]
             nbn = n.n_linear if ni == 0 else n.n_linear - 1
             lo, hi = n.rm_off[0], n.rv_off[nbn - 1] + n.out_dim[nbn - 1]
-            self._allreduce(st[lo:hi])
+            self._mean_over_shards(st[:, lo:hi])
+        self._mean_over_shards(st[:, lay.misc_off + 5:lay.misc_off + 7])
+
+    def _exchange_update(self, o):
+        eng = self.engine
+        if self.exchange == "peer":
+            L.check(eng.lib.raae_apply_adam_peer(eng.handle, o, eng.stream))
+        else:
+            g = self.grads[o]
+            if self.replicas > 1:
+                m = g.sum(0, keepdim=True)
+                self._allreduce(m)
+                g.copy_((m / self.replicas).expand_as(g))
+            else:
+                self._allreduce(g)
+            L.check(eng.lib.raae_apply_adam(eng.handle, o, self._grad_ptrs[o], eng.stream))
 
     def train_epoch(self, epoch, perm=None):
-        """One epoch: every batch runs its five phases as launch -> all-reduce -> AdamW.  Returns (losses[12], metrics[6])."""
+        """One epoch: every batch runs its five phases as launch -> gradient exchange + AdamW.  `perm`: int32
+        [replicas][rows per shard] indices into the rank's rows (make_perm).  Returns (losses[12], metrics[6])."""
         eng = self.engine
         if perm is None:
-            perm = eng.make_perm(1)[0]
+            perm = self.make_perm()
+        perm = perm.view(self.replicas, self.per)
         stop_smooth = float(self.cfg["epoch_stop_smooth"])
         for s in range(self.n_steps):
             for o in range(L.NUM_PHASES):
@@ -119,14 +160,10 @@ class DataParallelTrainer:
                 for k in range(L.NUM_PHASES):
                     self._gptr[k] = self._grad_ptrs[k] if k == o else None
                 L.check(eng.lib.raae_train_phase(eng.handle, int(epoch), s, 1 << o, perm.data_ptr(), self._gptr, eng.stream))
-                if self.exchange == "peer":
-                    L.check(eng.lib.raae_apply_adam_peer(eng.handle, o, eng.stream))
-                else:
-                    self._allreduce(self.grads[o])
-                    L.check(eng.lib.raae_apply_adam(eng.handle, o, self._grad_ptrs[o], eng.stream))
+                self._exchange_update(o)
         self._sync_bn_buffers()
-        losses = torch.zeros(1, 12, dtype=torch.float32, device=eng.device)
-        metrics = torch.zeros(1, 6, dtype=torch.float32, device=eng.device)
+        losses = torch.zeros(self.replicas, 12, dtype=torch.float32, device=eng.device)
+        metrics = torch.zeros(self.replicas, 6, dtype=torch.float32, device=eng.device)
         L.check(eng.lib.raae_validate_epoch(eng.handle, int(epoch), losses.data_ptr(), metrics.data_ptr(), eng.stream))
         return losses[0], metrics[0]
 

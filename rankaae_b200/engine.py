@@ -154,13 +154,16 @@ class Engine:
     def set_hp(self, trial, hp_np):
         self.hp[trial].copy_(torch.from_numpy(np.asarray(hp_np, dtype=np.float64)))
 
-    def bind_dataset(self, spec_train, aux_train, spec_val, aux_val):
-        """float32 row-major device tensors (copied to the device if needed)."""
+    def bind_dataset(self, spec_train, aux_train, spec_val, aux_val, rows_per_trial=None):
+        """float32 row-major device tensors (copied to the device if needed).  `rows_per_trial` (data-parallel replicas,
+        dp.py): every trial works on its own `rows_per_trial` rows - the permutations handed to the kernels have that
+        length and index the whole bound array."""
         def dev(x):
             return torch.as_tensor(x, dtype=torch.float32).to(self.device).contiguous()
         st, at, sv, av = dev(spec_train), dev(aux_train), dev(spec_val), dev(aux_val)
         self._data = (st, at, sv, av)
-        self.n_train, self.n_val = st.shape[0], sv.shape[0]
+        self.n_train, self.n_val = st.shape[0] if rows_per_trial is None else int(rows_per_trial), sv.shape[0]
+        assert self.n_train <= st.shape[0]
         L.check(self.lib.raae_bind_dataset(self.handle, st.data_ptr(), at.data_ptr(), self.n_train,
                                            sv.data_ptr(), av.data_ptr(), self.n_val))
         if self.n_val >= 3:

@@ -54,21 +54,17 @@ def train_only(dp, epoch, perm):
             for k in range(L.NUM_PHASES):
                 dp._gptr[k] = dp._grad_ptrs[k] if k == o else None
             L.check(eng.lib.raae_train_phase(eng.handle, epoch, s, 1 << o, perm.data_ptr(), dp._gptr, eng.stream))
-            exchange_update(dp, o)
+            dp._exchange_update(o)
 
 
 def exchange_update(dp, o):
-    eng = dp.engine
-    if dp.exchange == "peer":
-        L.check(eng.lib.raae_apply_adam_peer(eng.handle, o, eng.stream))
-    else:
-        dp._allreduce(dp.grads[o])
-        L.check(eng.lib.raae_apply_adam(eng.handle, o, dp._grad_ptrs[o], eng.stream))
+    dp._exchange_update(o)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--replicas", type=int, default=1, help="data-parallel replicas of the trial per GPU (one SM each)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -77,14 +73,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     bs = CFG["batch_size"]
-    n_train = bs * args.steps * world
+    V = args.replicas
+    n_train = bs * args.steps * world * V
     spec, aux = O.synthetic_dataset(n_train + 1050, O.Config.from_dict(CFG), seed=3, dtype=np.float32)
     res = {"workload": f"config #4 shape: 256-point spectra, 6 descriptors, per-rank batch {bs}, {args.steps} batches per rank, "
-                       f"{world} rank(s), 5 phases per batch", "n_gpus": world}
+                       f"{world} rank(s) x {V} replica(s) per GPU (global batch {bs * world * V}), 5 phases per batch", "n_gpus": world,
+           "replicas_per_gpu": V}
     for exchange in ("peer", "nccl"):
         dp = DataParallelTrainer(CFG, spec[:n_train], aux[:n_train], spec[n_train:], aux[n_train:], dev, rank, world, seed=1,
-                                 exchange=exchange)
-        perm = dp.engine.make_perm(1)[0]
+                                 exchange=exchange, replicas=V)
+        perm = dp.make_perm()
         for e in range(2):                                              # warm-up epochs
             train_only(dp, e, perm)
         ms = min(timed(lambda: train_only(dp, 2 + r, perm), dev, world) for r in range(3))
@@ -102,8 +100,8 @@ def main():
             same = bool(flag.item() == 1.0)
         finite = bool(torch.isfinite(v).all().item())
         res[exchange] = {"ranks_bit_identical": same, "finite": finite, "ms_per_epoch": ms, "ms_per_step": ms / dp.n_steps, "steps_per_sec": dp.n_steps / ms * 1e3,
-                         "samples_per_sec": dp.n_steps * bs * world / ms * 1e3, "exchange_update_us": us,
-                         "launches_per_phase": 2 if exchange == "peer" else (5 if world > 1 else 3)}
+                         "samples_per_sec": dp.n_steps * bs * world * V / ms * 1e3, "exchange_update_us": us,
+                         "launches_per_phase": 2 if exchange == "peer" else 3 + (2 if world > 1 else 0) + (3 if V > 1 else 0)}
         dp.close()
     if rank == 0:
         line = json.dumps(res)
