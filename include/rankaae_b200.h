@@ -216,6 +216,9 @@ int raae_validate_epoch(raae_handle* h, int epoch, float* out_losses, float* out
  *                      same order (the flag protocol counts calls).  A rank that waits > 10 s for a peer traps (the
  *                      stream reports a launch failure) instead of hanging.
  *   raae_peer_free     unmaps / frees (also done by raae_destroy); the caller runs a barrier before it.
+ * With n_trials > 1 the resident trials are data-parallel REPLICAS of one trial (identical weights, one shard each): the
+ * launch first sums the replicas' vectors locally, the peers read that one vector per rank, the mean runs over
+ * world x n_trials shards and the one update is applied to every replica's state (rankaae_b200/dp.py, `replicas`).
  * world <= RAAE_MAX_PEERS ranks on one NVLink / NVSwitch domain, one process per GPU. */
 #define RAAE_MAX_PEERS 8
 #define RAAE_IPC_HANDLE_BYTES 64

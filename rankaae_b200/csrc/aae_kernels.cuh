@@ -560,9 +560,12 @@ __global__ void raae_adam_kernel(const __grid_constant__ KParams p, int o, const
 // after >= 3 further exchanges which every peer enters only once its previous launch (the reader) has finished.
 // ------------------------------------------------------------------------------------------
 struct PeerArgs {
-  const float* grads[RAAE_MAX_PEERS];    // this phase's gradient vector on every rank (peer-mapped), [n_trials][opt[o].n]
+  const float* sums[RAAE_MAX_PEERS];     // every rank's gradient vector of this phase, summed over its replicas (peer-mapped), [opt[o].n]
   unsigned* flags[RAAE_MAX_PEERS];       // every rank's flag words [RAAE_MAX_PEERS]
+  const float* lgrads;                   // local: the replicas' vectors [replicas][opt[o].n] as raae_train_phase wrote them
+  float* lsum;                           // local: their sum (== lgrads when replicas == 1)
   unsigned* done;                        // local: blocks finished (for the optimizer step counter)
+  unsigned* arrive;                      // local: blocks whose slice of lsum is complete
   int world, rank;
   int replicas;                          // trials resident per rank (identical weights, one shard each)
   unsigned seq;
@@ -586,9 +589,34 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 __global__ void raae_adam_peer_kernel(const __grid_constant__ KParams p, int o, const __grid_constant__ PeerArgs pa) {
-  if (blockIdx.x == 0 && threadIdx.x < pa.world) {
+  const int V = pa.replicas;
+  const raae_opt_layout& ol = p.lay.opt[o];
+  if (V > 1) {
+    // local pre-reduction: the peers read ONE vector per rank, not `replicas` (replica order; every block sums its slice,
+    // block 0 publishes once all slices are complete - all blocks of this small grid are resident)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ol.n; i += gridDim.x * blockDim.x) {
+      float g = 0.f;
+#pragma unroll 4
+      for (int v = 0; v < V; ++v) g += pa.lgrads[(size_t)v * ol.n + i];
+      pa.lsum[i] = g;
+    }
     __threadfence_system();
-    st_release_sys(pa.flags[threadIdx.x] + pa.rank, pa.seq);
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(pa.arrive, 1u);
+  }
+  if (blockIdx.x == 0) {
+    if (V > 1) {
+      if (threadIdx.x == 0) {
+        while (atomicAdd(pa.arrive, 0u) < gridDim.x) __nanosleep(32);
+        *pa.arrive = 0u;
+        __threadfence_system();
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < pa.world) {
+      __threadfence_system();
+      st_release_sys(pa.flags[threadIdx.x] + pa.rank, pa.seq);
+    }
   }
   if (threadIdx.x < pa.world) {
     const unsigned* f = pa.flags[pa.rank] + threadIdx.x;
@@ -600,10 +628,8 @@ __global__ void raae_adam_peer_kernel(const __grid_constant__ KParams p, int o, 
   }
   __syncthreads();
   // `replicas` = the trials resident on every rank: they hold the SAME weights and act as further data-parallel ranks
-  // (one CTA each in raae_train_phase), so the mean runs over world x replicas vectors, summed in (rank, replica) order,
-  // and the one update is applied to every local replica's state
-  const int V = pa.replicas;
-  const raae_opt_layout& ol = p.lay.opt[o];
+  // (one CTA each in raae_train_phase), so the mean runs over world x replicas vectors - the ranks' pre-reduced sums added in
+  // rank order - and the one update is applied to every local replica's state
   const float wf = (float)(pa.world * V);
   // the replicas share the hyper-parameter row (dp.py) and, as long as their schedulers agree, lr and step count:
   // the float64 AdamW scalars are formed once and only re-formed for a replica whose lr / step differ
@@ -611,16 +637,38 @@ __global__ void raae_adam_peer_kernel(const __grid_constant__ KParams p, int o, 
   const float lr0 = p.state[ol.scalar_off + 0], t0 = p.state[ol.scalar_off + 1];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ol.n; i += gridDim.x * blockDim.x) {
     float g = 0.f;
-    for (int r = 0; r < pa.world; ++r) {
-      const float* src = pa.grads[r] + i;
 #pragma unroll 4
-      for (int v = 0; v < V; ++v) g += ld_relaxed_sys(src + (size_t)v * ol.n);
-    }
+    for (int r = 0; r < pa.world; ++r) g += ld_relaxed_sys(pa.sums[r] + i);
     if (pa.world * V > 1) g = g / wf;
-    for (int v = 0; v < V; ++v) {
-      float* st = p.state + (size_t)v * p.lay.state_floats;
-      const bool same = st[ol.scalar_off + 0] == lr0 && st[ol.scalar_off + 1] == t0;
-      adam_element(p, st, ol, same ? a0 : adam_scalars(st, p.hp + (size_t)v * RAAE_HP_COUNT, ol, o), i, g);
+    // the replicas' parameter / moment triples are independent: loads of four replicas are issued before the first store
+    // (the compiler cannot hoist them across the stores itself), so the update costs one memory latency per four replicas
+    int net = -1, rel = 0;
+    for (int k = 0; k < RAAE_NUM_NETS; ++k)
+      if (ol.net_off[k] >= 0 && i >= ol.net_off[k] && i < ol.net_off[k] + p.lay.net[k].n_params) { net = k; rel = i - ol.net_off[k]; }
+    const size_t po = (size_t)p.lay.net[net].param_off + rel, mo = (size_t)ol.m_off + i, vo = (size_t)ol.v_off + i;
+    for (int v0 = 0; v0 < V; v0 += 4) {
+      float P4[4], M4[4], V4[4];
+      bool same[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (v0 + u < V) {
+          const float* st = p.state + (size_t)(v0 + u) * p.lay.state_floats;
+          P4[u] = st[po]; M4[u] = st[mo]; V4[u] = st[vo];
+          same[u] = st[ol.scalar_off + 0] == lr0 && st[ol.scalar_off + 1] == t0;
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (v0 + u < V) {
+          float* st = p.state + (size_t)(v0 + u) * p.lay.state_floats;
+          const AdamScalars a = same[u] ? a0 : adam_scalars(st, p.hp + (size_t)(v0 + u) * RAAE_HP_COUNT, ol, o);
+          const float pp = P4[u] * a.decay;
+          const float m = M4[u] + (g - M4[u]) * a.w1;
+          const float vv = V4[u] * a.b2 + (a.w2 * g) * g;
+          const float denom = sqrtf(vv) / a.bc2s + kAdamEps;
+          st[po] = pp - a.ss * (m / denom);
+          st[mo] = m;
+          st[vo] = vv;
+        }
     }
   }
   // optimizer step counters: by the last block to finish (every block has read the scalars by then)

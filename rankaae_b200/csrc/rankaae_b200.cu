@@ -158,14 +158,14 @@ struct raae_handle {
     int world, rank;
     bool connected;
     unsigned seq;
-    size_t bytes, grad_off[RAAE_NUM_PHASES];
+    size_t bytes, grad_off[RAAE_NUM_PHASES], sum_off[RAAE_NUM_PHASES];   // sum_off == grad_off when n_trials == 1
     unsigned char* local;                       // cudaMalloc: [256 B flags + done counter][gradient vector per phase]
     unsigned char* mapped[RAAE_MAX_PEERS];      // every rank's block in this process' address space
   } peer;
 };
 
 namespace {
-constexpr size_t kPeerHeaderBytes = 256;        // words [0, 8): flags, word 16: finished-block counter
+constexpr size_t kPeerHeaderBytes = 256;        // words [0, 8): flags, word 16: finished-block counter, word 17: pre-reduction arrivals
 int peer_release(raae_handle* h) {
   if (!h->peer.local) return 0;
   cudaSetDevice(h->device);
@@ -406,8 +406,12 @@ int raae_peer_alloc(raae_handle* h, int world, int rank, unsigned char* ipc_hand
   RAAE_CUDA(cudaSetDevice(h->device));
   size_t off = kPeerHeaderBytes;
   for (int o = 0; o < RAAE_NUM_PHASES; ++o) {
-    h->peer.grad_off[o] = off;
+    h->peer.grad_off[o] = h->peer.sum_off[o] = off;
     off += (((size_t)h->kp.cfg.n_trials * h->kp.lay.opt[o].n * sizeof(float)) + 255) & ~(size_t)255;
+    if (h->kp.cfg.n_trials > 1) {                // the replicas' pre-reduced sum, the vector the peers read
+      h->peer.sum_off[o] = off;
+      off += (((size_t)h->kp.lay.opt[o].n * sizeof(float)) + 255) & ~(size_t)255;
+    }
   }
   void* ptr = nullptr;
   RAAE_CUDA(cudaMalloc(&ptr, off));
@@ -464,10 +468,13 @@ int raae_apply_adam_peer(raae_handle* h, int phase, void* stream) {
   raae::PeerArgs pa;
   std::memset(&pa, 0, sizeof(pa));
   for (int r = 0; r < h->peer.world; ++r) {
-    pa.grads[r] = (const float*)(h->peer.mapped[r] + h->peer.grad_off[phase]);
+    pa.sums[r] = (const float*)(h->peer.mapped[r] + h->peer.sum_off[phase]);
     pa.flags[r] = (unsigned*)h->peer.mapped[r];
   }
+  pa.lgrads = (const float*)(h->peer.local + h->peer.grad_off[phase]);
+  pa.lsum = (float*)(h->peer.local + h->peer.sum_off[phase]);
   pa.done = (unsigned*)h->peer.local + 16;
+  pa.arrive = (unsigned*)h->peer.local + 17;
   pa.world = h->peer.world;
   pa.rank = h->peer.rank;
   pa.replicas = h->kp.cfg.n_trials;
