@@ -32,6 +32,13 @@ def shard_rows(n_rows, world, rank):
     return rank * per, (rank + 1) * per
 
 
+def shard_layout(n_rows, world, rank, replicas=1):
+    """Rows of a rank under `world x replicas` equally sized shards (shard q = rank * replicas + replica; remainder rows
+    dropped): returns (rows per shard, first row of the rank, one past its last row)."""
+    per = n_rows // (world * replicas)
+    return per, rank * replicas * per, (rank + 1) * replicas * per
+
+
 class DataParallelTrainer:
     """`replicas` > 1 puts that many data-parallel replicas of the trial on EVERY GPU (one CTA / SM each, identical
     weights, own shard, own noise streams): the job then has world x replicas shards with DistributedDataParallel
@@ -51,8 +58,7 @@ class DataParallelTrainer:
         self.exchange = exchange
         self.cfg = dict(cfg)
         self.cfg.setdefault("epoch_stop_smooth", 500)
-        self.per = len(spec_train) // (world * V)                     # rows of one shard; shard q = rank * V + replica
-        lo, hi = rank * V * self.per, (rank + 1) * V * self.per
+        self.per, lo, hi = shard_layout(len(spec_train), world, rank, V)     # rows of one shard; shard q = rank * V + replica
         self.engine = Engine(self.cfg, n_trials=V, device=device, max_rows=max(int(cfg["batch_size"]), len(spec_val)),
                              seeds=shard_seeds if shard_seeds is not None else
                              [seed * 1000 + rank * V + v for v in range(V)])         # shard-local noise / dropout streams

@@ -213,3 +213,36 @@ def test_metric_gather_world2_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_data_parallel_shard_layout_partitions_rows():
+    """world x replicas equally sized, disjoint, contiguous shards; 2 ranks x 1 replica and 1 rank x 2 replicas cover the
+    same rows in the same shard order (what makes the two configurations bit-identical on the GPU)."""
+    from rankaae_b200.dp import shard_layout
+    for n_rows, world, V in ((840, 2, 1), (840, 1, 2), (1_000_000, 8, 16), (1001, 3, 2)):
+        per = n_rows // (world * V)
+        seen = []
+        for r in range(world):
+            p, lo, hi = shard_layout(n_rows, world, r, V)
+            assert p == per and hi - lo == V * per
+            seen += [(lo + v * per, lo + (v + 1) * per) for v in range(V)]
+        assert seen == [(q * per, (q + 1) * per) for q in range(world * V)]
+    assert shard_layout(840, 2, 1, 1) == (420, 420, 840) and shard_layout(840, 1, 0, 2) == (420, 0, 840)
+
+
+def test_sweep_points_are_deterministic_and_in_range():
+    """tools/sweep_1024.py: the hyper-parameters of global trial t depend on t only (not on the partition over ranks)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("sweep_1024", os.path.join(root, "tools", "sweep_1024.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    a, b = mod.sweep_point(17), mod.sweep_point(17)
+    assert a == b and a != mod.sweep_point(18)
+    for t in range(0, 1024, 37):
+        p = mod.sweep_point(t)
+        assert 3e-4 <= p["lr_base"] <= 3e-3 and 1e-3 <= p["weight_decay"] <= 1e-1 and 0.0 <= p["dropout_rate"] <= 0.1
+        assert p["n_layers"] == mod.BASE["n_layers"] and p["batch_size"] == 1024          # structural keys are fixed per launch
+    from rankaae_b200.ensemble import shard_trials
+    assert sorted(sum((shard_trials(1024, 8, r) for r in range(8)), [])) == list(range(1024))
+    assert all(len(shard_trials(1024, 8, r)) == 128 for r in range(8))
