@@ -158,6 +158,7 @@ struct raae_handle {
     int world, rank;
     bool connected;
     unsigned seq;
+    int max_blocks;                             // co-resident blocks of the exchange kernel on this device (0 = not queried yet)
     size_t bytes, grad_off[RAAE_NUM_PHASES], sum_off[RAAE_NUM_PHASES];   // sum_off == grad_off when n_trials == 1
     unsigned char* local;                       // cudaMalloc: [256 B flags + done counter][gradient vector per phase]
     unsigned char* mapped[RAAE_MAX_PEERS];      // every rank's block in this process' address space
@@ -479,8 +480,16 @@ int raae_apply_adam_peer(raae_handle* h, int phase, void* stream) {
   pa.rank = h->peer.rank;
   pa.replicas = h->kp.cfg.n_trials;
   pa.seq = ++h->peer.seq;
+  // every block of the grid must be resident: block 0 waits for the other blocks' slices of the local pre-reduction and all
+  // blocks wait for the peers' flags, so a block that cannot be scheduled would stall the whole exchange
+  if (h->peer.max_blocks == 0) {
+    int per_sm = 0, sms = 0;
+    RAAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raae::raae_adam_peer_kernel, 256, 0));
+    RAAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    h->peer.max_blocks = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+  }
   int bx = (h->kp.lay.opt[phase].n + 255) / 256;
-  if (bx > 592) bx = 592;                       // 4 blocks per SM: every block resident, the flag wait cannot starve a peer
+  if (bx > h->peer.max_blocks) bx = h->peer.max_blocks;
   raae::raae_adam_peer_kernel<<<bx, 256, 0, (cudaStream_t)stream>>>(h->kp, phase, pa);
   RAAE_CUDA(cudaGetLastError());
   h->launches++;
