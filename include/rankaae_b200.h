@@ -71,7 +71,9 @@ typedef struct raae_config {
   int32_t use_flex_spec_target;/* bool */
   int32_t decoder_softplus;    /* 1 = Softplus(beta=2), 0 = ReLU */
   int32_t max_rows;            /* scratch rows per trial: >= max(batch_size, n_val) */
-  int32_t ctas_per_trial;      /* thread-block cluster size per trial; 1 in this version */
+  int32_t ctas_per_trial;      /* thread-block cluster per trial: 1, 2, 4 or 8 CTAs share one trial (128-row tiles of a batch are
+                                  dealt round-robin; BatchNorm statistics, weight gradients, loss and Kendall totals are reduced
+                                  through distributed shared memory).  1 = one CTA per trial (ensembles of >= 148 trials) */
   int32_t tensor_cores;        /* contractions on tcgen05 (kind::tf32, 3 x TF32 round-to-nearest split, TMEM accumulators): bit 0
                                   hidden-block forward, bit 1 hidden-block backward, bit 2 input block of the encoder on the batch
                                   (forward + weight gradient from operand images in scratch, streamed with bulk copies; also the
@@ -221,6 +223,7 @@ int raae_validate_epoch(raae_handle* h, int epoch, float* out_losses, float* out
  * world x n_trials shards and the one update is applied to every replica's state (rankaae_b200/dp.py, `replicas`).
  * world <= RAAE_MAX_PEERS ranks on one NVLink / NVSwitch domain, one process per GPU. */
 #define RAAE_MAX_PEERS 8
+#define RAAE_MAX_CTAS 8         /* largest thread-block cluster per trial (portable cluster size) */
 #define RAAE_IPC_HANDLE_BYTES 64
 int raae_peer_alloc(raae_handle* h, int world, int rank, unsigned char* ipc_handle_out);
 int raae_peer_connect(raae_handle* h, const unsigned char* all_handles);

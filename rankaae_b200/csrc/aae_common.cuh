@@ -291,6 +291,39 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return s;
 }
 
+// ------------------------------------------------------------------------------------------
+// thread-block cluster per trial (raae_config::ctas_per_trial > 1): cluster rank / barrier / distributed shared memory
+// ------------------------------------------------------------------------------------------
+namespace cl {
+__device__ __forceinline__ uint32_t ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// every thread of every CTA of the cluster; release / acquire at cluster scope: global and shared-memory writes made before
+// the barrier by any CTA are visible to every CTA after it (ptxas invalidates L1 on the acquire side)
+__device__ __forceinline__ void sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of this CTA's shared-memory location `p` in the shared memory of cluster rank `rank`
+__device__ __forceinline__ uint32_t map(const void* p, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float ld_f32(uint32_t a) { float v; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ double ld_f64(uint32_t a) { double v; asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+// rows are owned tile-wise: 128-row tile t belongs to cluster rank t % csize in EVERY stage, so per-row panels never cross CTAs
+__device__ __forceinline__ int own_tiles(int B, int crank, int csize) {
+  const int nt = (B + kTM - 1) / kTM;
+  return nt > crank ? (nt - crank + csize - 1) / csize : 0;
+}
+__device__ __forceinline__ int own_rows(int B, int crank, int csize) {
+  int n = 0;
+  for (int t = crank; t * kTM < B; t += csize) n += min(kTM, B - t * kTM);
+  return n;
+}
+// row of own-row slot s (slots of a CTA: own_tiles x 128; the row may be >= B in the last tile)
+__device__ __forceinline__ int slot_row(int s, int crank, int csize) { return ((s >> 7) * csize + crank) * kTM + (s & (kTM - 1)); }
+}  // namespace cl
+
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

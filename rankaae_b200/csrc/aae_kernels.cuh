@@ -36,7 +36,9 @@ __device__ __noinline__ void build_batch(const Ctx& c_ref, const int32_t* __rest
   // accumulates with truncation, ~1 ulp of the running sum per MMA; spectra are a large common profile plus small
   // variations, and BatchNorm then divides by the small spread, so the images hold (row - reference) and the consumers
   // add reference . W^T (forward) / db (x) reference (weight gradient) back in FP32: exact algebra, 20 x smaller sums.
-  float* xref = c.sc + p.sl.xref;
+  // cluster per trial: every CTA builds the rows of ITS tiles; the reference row is the same in all of them (own copy each)
+  const int crank = c.crank, csize = c.csize;
+  float* xref = c.sc + p.sl.xref + crank * kMaxDim;
   if (images) {
     const int nref = min(32, c.B), c4 = (tid & 63) * 4, g = tid >> 6;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -64,9 +66,11 @@ __device__ __noinline__ void build_batch(const Ctx& c_ref, const int32_t* __rest
     __syncthreads();
   }
   const int q_per_row = images ? nch64 * 16 : (dim >> 2);                 // float4 quads per row (padded to whole 64-col chunks)
-  const int rows_all = images ? ((c.B + kTM - 1) / kTM) * kTM : c.B;      // whole tiles: rows >= B are zero-filled
+  const int rows_all = csize > 1 ? cl::own_tiles(c.B, crank, csize) * kTM
+                     : images ? ((c.B + kTM - 1) / kTM) * kTM : c.B;      // whole tiles: rows >= B are zero-filled
   for (int i = tid; i < rows_all * q_per_row; i += kThreads) {
-    const int r = i / q_per_row, c4 = (i - r * q_per_row) * 4;
+    const int sl = i / q_per_row, c4 = (i - sl * q_per_row) * 4;
+    const int r = csize == 1 ? sl : cl::slot_row(sl, crank, csize);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < c.B && c4 < dim) {
       const size_t srow = dbg ? (size_t)r : (size_t)idx[r];
@@ -96,15 +100,19 @@ __device__ __noinline__ void build_batch(const Ctx& c_ref, const int32_t* __rest
       }
     }
   }
-  for (int i = tid; i < c.B * kZ; i += kThreads) {
-    int r = i >> 3, k = i & 7;
+  const int nslots = csize == 1 ? c.B : cl::own_tiles(c.B, crank, csize) * kTM;
+  for (int e = tid; e < nslots * kZ; e += kThreads) {
+    const int k = e & 7, r = csize == 1 ? (e >> 3) : cl::slot_row(e >> 3, crank, csize);
+    if (r >= c.B) continue;
     const float* arow = dbg ? c.a->dbg.aux + (size_t)r * K : p.aux_train + (size_t)idx[r] * K;
-    aux[i] = k < K ? arow[k] : 0.f;
+    aux[r * kZ + k] = k < K ? arow[k] : 0.f;
   }
   const float* zsp = dbg ? c.a->dbg.z_sample : nullptr;
   const uint32_t kz = stream_key(c.seed, c.step_id, kStreamZSample);
-  for (int i = tid; i < c.B * kZ; i += kThreads) {
-    int r = i >> 3, k = i & 7;
+  for (int e = tid; e < nslots * kZ; e += kThreads) {
+    const int k = e & 7, r = csize == 1 ? (e >> 3) : cl::slot_row(e >> 3, crank, csize);
+    if (r >= c.B) continue;
+    const int i = r * kZ + k;
     zs[i] = k < ns ? (zsp ? zsp[(size_t)r * ns + k] : normal_at(kz, (uint32_t)i)) : 0.f;
   }
   if (images) tc::fence_async_all();     // the images are read by bulk copies (async proxy) in later stages
@@ -137,7 +145,7 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask, bool run_p0 =
   // buffers advance, so its hidden blocks run (the output Linear has no side effect and is skipped).
   if (run_p0) {
     encoder_forward(c, x, 0);
-    if (c.a->debug && c.a->dbg.styles) {
+    if (c.a->debug && c.a->dbg.styles && c.crank == 0) {
       for (int i = tid; i < c.B * ns; i += kThreads) {
         int r = i / ns, k = i - r * ns;
         c.a->dbg.styles[i] = (zE[(size_t)r * kZ + k] - meanZ[k]) * invZ[k];
@@ -208,7 +216,7 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask, bool run_p0 =
     if (tid == 0) adam_finish(c, kSmooth);
     __syncthreads();
   }
-  if (tid == 0) {
+  if (tid == 0 && c.crank == 0) {
     float* misc = c.st + p.lay.misc_off;
     for (int i = 0; i < RAAE_NUM_PHASES; ++i)
       if (phase_mask & (1 << i)) misc[i] = (float)sm->loss_acc[i];
@@ -219,7 +227,7 @@ __device__ __forceinline__ void train_step(Ctx& c, int phase_mask, bool run_p0 =
     if (c.a->debug && c.a->dbg.losses)
       for (int i = 0; i < RAAE_NUM_PHASES; ++i) c.a->dbg.losses[i] = (float)sm->loss_acc[i];
   }
-  __syncthreads();
+  stage_sync(c);
 }
 
 __device__ __forceinline__ void init_ctx(Ctx& c, const KParams& p, const RunArgs& a, int trial) {
@@ -236,6 +244,8 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const KParams& p, const RunArgs
   c.train = 1;
   c.x = c.sc + p.sl.xn;
   c.xld = p.sl.xld;
+  c.crank = (int)cl::ctarank();
+  c.csize = (int)cl::nctarank();
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     const double pd = c.hp[g ? RAAE_HP_DIS_DROPOUT : RAAE_HP_DROPOUT];
@@ -248,6 +258,10 @@ constexpr size_t kSmemBytes = kArenaOffset + (size_t)kArenaFloats * sizeof(float
 
 // TMEM accumulator + mbarrier for the tcgen05 path (one CTA per SM, so the allocation never contends)
 __device__ __forceinline__ void tc_setup(const KParams& p, SmemFixed* sm) {
+  // cluster per trial: no CTA may touch a peer's shared memory before that peer runs, nor exit while a peer may still read its own
+  if (threadIdx.x == 0) sm->xpar = 0u;
+  if (cl::nctarank() > 1) cl::sync();
+  else __syncthreads();
   if (!p.cfg.tensor_cores) return;
   if (threadIdx.x < 32) tc::tmem_alloc(&sm->tmem_base, tc::kTmemCols);
   if (threadIdx.x == 0) {
@@ -261,6 +275,7 @@ __device__ __forceinline__ void tc_setup(const KParams& p, SmemFixed* sm) {
   tc::fence_after_sync();
 }
 __device__ __forceinline__ void tc_teardown(const KParams& p, SmemFixed* sm) {
+  if (cl::nctarank() > 1) cl::sync();
   if (!p.cfg.tensor_cores) return;
   tc::fence_before_sync();
   __syncthreads();
@@ -270,7 +285,7 @@ __device__ __forceinline__ void tc_teardown(const KParams& p, SmemFixed* sm) {
 __global__ void __launch_bounds__(kThreads, 1)
 raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunArgs a) {
   RAAE_SMEM();
-  const int trial = a.trial0 + blockIdx.x;
+  const int trial = a.trial0 + (int)(blockIdx.x / cl::nctarank());     // one thread-block cluster (ctas_per_trial CTAs) per trial
   Ctx c;
   init_ctx(c, p, a, trial);
   if (threadIdx.x < 32) sm->prof[threadIdx.x] = 0;
@@ -292,7 +307,7 @@ raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ Run
     // one batch, selected phases, gradients exported instead of applied (data-parallel mode: the host all-reduces
     // them and raae_adam_kernel applies the update).  The batch and the P0 forward belong to the launch that runs P1.
     const bool first = (a.phase_mask & (1 << kAdv)) != 0;
-    if (first && a.step0 == 0 && threadIdx.x == 0) { c.st[p.lay.misc_off + 5] = 0.f; c.st[p.lay.misc_off + 6] = 0.f; }
+    if (first && a.step0 == 0 && threadIdx.x == 0 && c.crank == 0) { c.st[p.lay.misc_off + 5] = 0.f; c.st[p.lay.misc_off + 6] = 0.f; }
     c.B = min(bs, p.n_train - a.step0 * bs);
     c.step_id = (uint32_t)(a.epoch * a.n_steps + a.step0);
     c.apply = 0;
@@ -301,14 +316,14 @@ raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ Run
     tc_teardown(p, sm);
     return;
   }
-  if (threadIdx.x == 0) { c.st[p.lay.misc_off + 5] = 0.f; c.st[p.lay.misc_off + 6] = 0.f; }
+  if (threadIdx.x == 0 && c.crank == 0) { c.st[p.lay.misc_off + 5] = 0.f; c.st[p.lay.misc_off + 6] = 0.f; }
   for (int s = 0; s < a.n_steps; ++s) {
     c.B = min(bs, p.n_train - s * bs);
     c.step_id = (uint32_t)(a.epoch * a.n_steps + s);
     build_batch(c, perm + s * bs);
     train_step(c, 0x1f);
   }
-  if (a.prof && threadIdx.x == 0) {      // [n_trials][32]: per-stage-type SM cycles, slot 15 = whole kernel, 16.. = probes
+  if (a.prof && threadIdx.x == 0 && c.crank == 0) {      // [n_trials][32]: per-stage-type SM cycles, slot 15 = whole kernel, 16.. = probes
     for (int i = 0; i < 15; ++i) a.prof[(size_t)trial * 32 + i] += sm->prof[i];
     a.prof[(size_t)trial * 32 + 15] += clock64() - t_start;
     for (int i = 16; i < 32; ++i) a.prof[(size_t)trial * 32 + i] += sm->prof[i];
@@ -356,7 +371,10 @@ __device__ __noinline__ void latent_metrics(const Ctx& c_ref) {
   float* key = arena;
   int* idx = reinterpret_cast<int*>(arena + npad);
   float wmin = 1e30f;
+  // cluster per trial: style k is sorted by rank k % csize, rank-correlation pair q by rank q % csize; min / max merged at the end
+  const int crank = c.crank, csize = c.csize;
   for (int k = 0; k < ns; ++k) {
+    if (k % csize != crank) continue;
     __syncthreads();
     const float mu = sm->mean[kE][lE][k], is = sm->inv[kE][lE][k];
     for (int i = tid; i < npad; i += kThreads) {
@@ -383,7 +401,7 @@ __device__ __noinline__ void latent_metrics(const Ctx& c_ref) {
       ranks[(size_t)k * rstride + idx[i]] = 0.5f * (float)(lo + hi) + 1.f;
     }
   }
-  __syncthreads();
+  stage_sync(c);                         // the other CTAs' rank columns
   // Pearson correlation of the rank columns
   const double rm = 0.5 * ((double)n + 1.0);
   float cmax = 0.f;
@@ -393,8 +411,10 @@ __device__ __noinline__ void latent_metrics(const Ctx& c_ref) {
     for (int i = tid; i < n; i += kThreads) { double d = (double)ranks[(size_t)a * rstride + i] - rm; s += d * d; }
     var[a] = block_sum_d(s, sm->redd);
   }
+  int pair = 0;
   for (int a = 0; a < ns; ++a)
     for (int b = a + 1; b < ns; ++b) {
+      if ((pair++) % csize != crank) continue;
       double s = 0.0;
       for (int i = tid; i < n; i += kThreads)
         s += ((double)ranks[(size_t)a * rstride + i] - rm) * ((double)ranks[(size_t)b * rstride + i] - rm);
@@ -404,6 +424,22 @@ __device__ __noinline__ void latent_metrics(const Ctx& c_ref) {
     }
   if (tid == 0) { sm->zs[2][0] = wmin; sm->zs[2][1] = cmax; }
   __syncthreads();
+  if (csize > 1) {
+    const uint32_t par = sm->xpar;
+    float* x = &sm->xchg[par][0][0];
+    if (tid < 2) x[tid] = sm->zs[2][tid];
+    cl::sync();
+    if (tid == 0) {
+      float w = 1e30f, cm = 0.f;
+      for (int r = 0; r < csize; ++r) {
+        w = fminf(w, cl::ld_f32(cl::map(x, (uint32_t)r)));
+        cm = fmaxf(cm, cl::ld_f32(cl::map(x + 1, (uint32_t)r)));
+      }
+      sm->zs[2][0] = w; sm->zs[2][1] = cm;
+      sm->xpar = par ^ 1u;
+    }
+    __syncthreads();
+  }
 }
 
 // torch ReduceLROnPlateau(mode="min", threshold_mode="rel", threshold=0.01, cooldown=0, min_lr=0, eps=1e-8)
@@ -427,7 +463,7 @@ __device__ inline void plateau_step(const Ctx& c, double metric) {
 __global__ void __launch_bounds__(kThreads, 1)
 raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunArgs a) {
   RAAE_SMEM();
-  const int trial = a.trial0 + blockIdx.x;
+  const int trial = a.trial0 + (int)(blockIdx.x / cl::nctarank());
   Ctx c;
   init_ctx(c, p, a, trial);
   const int tid = threadIdx.x, ns = p.cfg.nstyle, K = p.cfg.n_aux;
@@ -448,10 +484,15 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
   float* aux = c.sc + p.sl.aux;
   float* zs = c.sc + p.sl.zs;
   const uint32_t kz = stream_key(c.seed, c.step_id, kStreamValZSample);
-  for (int i = tid; i < c.B * kZ; i += kThreads) {
-    int r = i >> 3, k = i & 7;
-    aux[i] = k < K ? p.aux_val[(size_t)r * K + k] : 0.f;
-    zs[i] = k < ns ? (io.z_sample ? io.z_sample[(size_t)r * ns + k] : normal_at(kz, (uint32_t)i)) : 0.f;
+  {
+    const int nslots = c.csize == 1 ? c.B : cl::own_tiles(c.B, c.crank, c.csize) * kTM;      // cluster per trial: own rows
+    for (int e = tid; e < nslots * kZ; e += kThreads) {
+      const int k = e & 7, r = c.csize == 1 ? (e >> 3) : cl::slot_row(e >> 3, c.crank, c.csize);
+      if (r >= c.B) continue;
+      const int i = r * kZ + k;
+      aux[i] = k < K ? p.aux_val[(size_t)r * K + k] : 0.f;
+      zs[i] = k < ns ? (io.z_sample ? io.z_sample[(size_t)r * ns + k] : normal_at(kz, (uint32_t)i)) : 0.f;
+    }
   }
   __syncthreads();
   const float* zE = c.sc + p.sl.zE;
@@ -460,7 +501,8 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
   const int act = p.cfg.decoder_softplus ? 1 : 2;
   // z = E(x_val); spec_out = D(z)   (trainer.py:213-214)
   encoder_forward(c, wide_in(p.spec_val, p.cfg.dim_in, p.cfg.dim_in, 0), 0);
-  if (io.z)
+  stage_sync(c);                         // eval-mode stages have no barrier of their own: every CTA's latent rows are in place
+  if (io.z && c.crank == 0)
     for (int i = tid; i < c.B * ns; i += kThreads) {
       int r = i / ns, k = i - r * ns;
       io.z[i] = (zE[(size_t)r * kZ + k] - meanZ[k]) * invZ[k];
@@ -480,7 +522,7 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
     encoder_forward(c, y, 0);
   }
   mi_mse_stage(c, 0);
-  if (tid == 0) {
+  if (tid == 0 && c.crank == 0) {
     float* misc = c.st + p.lay.misc_off;
     float avg_mi = io.avg_mutual_info > -1e30f ? io.avg_mutual_info : (misc[6] > 0.f ? misc[5] / misc[6] : 0.f);
     double m[5] = {(double)wmin, sm->loss_acc[kRecon], (double)avg_mi, (double)coupling, sm->loss_acc[kCorr]};

@@ -83,7 +83,9 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
     for (int j = 0; j < 8; ++j) { acc += kGauss17[j]; tapP[j] = acc; }
   }
   const int ntiles = (c.B + kTM - 1) / kTM;
-  for (int t = 0; t < ntiles; ++t) {
+  float* const sg_dst = c.csize > 1 ? sm->sgp : sm->sg;         // cluster per trial: partial sums, gathered after the barrier
+  float* const sgx_dst = c.csize > 1 ? sm->sgxp : sm->sgx;
+  for (int t = c.crank, it = 0; t < ntiles; t += c.csize, ++it) {      // this CTA's tiles; `it` counts them
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     const long long q0 = clock64();
     auto load_w = [&](int ck) {             // elected thread only
@@ -113,12 +115,12 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
           // buffer b has been used t * uses_b + (ck >> 1) times before chunk ck of tile t: its barrier parities follow
           for (int ck = 0; ck < nchN; ++ck) {
             const int b = ck & 1;
-            tc::mbar_wait(&wfull[b], (uint32_t)(((t * ((nchN + 1 - b) >> 1)) + (ck >> 1)) & 1));
+            tc::mbar_wait(&wfull[b], (uint32_t)(((it * ((nchN + 1 - b) >> 1)) + (ck >> 1)) & 1));
             const float* Bh = Bb + b * 8192;
             tc::issue_gemm_3xtf32_acc(d_tmem + (uint32_t)(64 * ck), Ahi, Alo, Bh, Bh + 4096, 0u);
             tc::mma_commit(&wdone[b]);
             if (ck + 2 < nchN) {
-              tc::mbar_wait(&wdone[b], (uint32_t)(((t * ((nchN + 1 - b) >> 1)) + (ck >> 1)) & 1));
+              tc::mbar_wait(&wdone[b], (uint32_t)(((it * ((nchN + 1 - b) >> 1)) + (ck >> 1)) & 1));
               load_w(ck + 2);
             }
           }
@@ -181,8 +183,8 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
       const int nch64 = c.p->sl.nch64, nch128 = c.p->sl.nch128;
       float* yk = c.sc + c.p->sl.yk;
       float* ym = c.sc + c.p->sl.ym;
-      float* yref = c.sc + c.p->sl.yref;
-      if (img && t == 0) {
+      float* yref = c.sc + c.p->sl.yref + c.crank * kMaxDim;      // per CTA: the consumers of its tiles add its reference back
+      if (img && it == 0) {
         // reference row of the image: column means of y over the first (up to 32) rows - y of random latents need not be
         // close to the batch reference, and the tensor core's truncating accumulation wants small centred operands
         const int nref = min(32, nv);
@@ -437,19 +439,21 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
   if (mode == kLastRecon || mode == kLastEval) {
     double s = block_sum_d(loss_a, sm->redd);
     if (tid == 0) sm->loss_acc[kRecon] = s;
+    cluster_allreduce_d(c, sm, &sm->loss_acc[kRecon], 1);
   }
   if (mode == kLastSmooth || mode == kLastEval) {
     double s = block_sum_d(loss_b, sm->redd);
     if (tid == 0) sm->loss_acc[kSmooth] = s;
+    cluster_allreduce_d(c, sm, &sm->loss_acc[kSmooth], 1);
   }
   if (want_bwd) {
     sm->red[ty][c4 + 0] = sg4[0]; sm->red[ty][c4 + 1] = sg4[1]; sm->red[ty][c4 + 2] = sg4[2]; sm->red[ty][c4 + 3] = sg4[3];
     __syncthreads();
-    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sg[tid] = s; }
+    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sg_dst[tid] = s; }
     __syncthreads();
     sm->red[ty][c4 + 0] = sgx4[0]; sm->red[ty][c4 + 1] = sgx4[1]; sm->red[ty][c4 + 2] = sgx4[2]; sm->red[ty][c4 + 3] = sgx4[3];
     __syncthreads();
-    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sgx[tid] = s; }
+    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sgx_dst[tid] = s; }
     float* gradW = Y;            // dense [N][64]
     float* gradb = At;           // [N]
     const int m0 = 8 * (tid >> 3), n0 = 8 * (tid & 7);
@@ -460,8 +464,10 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
         if (m0 + i < N) gradW[(m0 + i) * kH + n0 + j] = accW[i][j];
     if (tid < N) gradb[tid] = dbp;
     __syncthreads();
+    if (c.csize > 1) { cl::sync(); cluster_gather_sg(c, sm); }
     adam_apply(c, sm, o, kD, nl.w_off[l], N * kH, gradW);
     adam_apply(c, sm, o, kD, nl.b_off[l], N, gradb);
+    stage_sync(c);
   }
   __syncthreads();
 }
@@ -533,6 +539,8 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
   const int tiles_real = (c.Breal + kTM - 1) / kTM, tiles_fake = (c.B + kTM - 1) / kTM;
   for (int t = 0; t < tiles_real + tiles_fake; ++t) {
     const bool fake = t >= tiles_real;
+    // cluster per trial: tile tl of either half belongs to rank tl % csize (the fake rows follow the row ownership of zE / dz)
+    if (((fake ? t - tiles_real : t) % c.csize) != c.crank) continue;
     const int nrows = fake ? c.B : c.Breal;
     const int row0 = (fake ? t - tiles_real : t) * kTM, nv = min(kTM, nrows - row0);
     const MaskSrc mk0 = fake ? mk_fake0 : mk_real0;        // register copies
@@ -709,6 +717,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
   {
     double s = block_sum_d(lossp, sm->redd);
     if (tid == 0) sm->loss_acc[kAdv] = s;
+    cluster_allreduce_d(c, sm, &sm->loss_acc[kAdv], 1);
   }
   if (backward) {
     float* gW1 = arena;                // [64][64]
@@ -768,6 +777,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
     __syncthreads();
     if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb0[tid] = s; }
     __syncthreads();
+    if (c.csize > 1) cl::sync();
     adam_apply(c, sm, o, kS, nl.w_off[0], kH * ns, gW0);
     adam_apply(c, sm, o, kS, nl.b_off[0], kH, gb0);
     adam_apply(c, sm, o, kS, nl.a_off[0], kH, ga0);
@@ -776,6 +786,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
     adam_apply(c, sm, o, kS, nl.a_off[1], kH, ga1);
     adam_apply(c, sm, o, kS, nl.w_off[2], kH, gW2);
     adam_apply(c, sm, o, kS, nl.b_off[2], 1, gb2);
+    stage_sync(c);
   }
   __syncthreads();
 }
@@ -852,6 +863,11 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
 #pragma unroll
   for (int k = 0; k < kZ; ++k) { cs[k] = 0; co[k] = 0; sp[k] = 0.0; sn[k] = 0.0; }
   const int nchunks = (B + kKendallChunk - 1) / kKendallChunk;
+  // cluster per trial: a CTA pairs ITS rows i (slot -> row) with all rows j; the other CTAs' latents / descriptors must be
+  // visible (in eval mode the producing stage has no barrier of its own)
+  const int crank = c.crank, csize = c.csize;
+  const int nslots = csize == 1 ? B : cl::own_tiles(B, crank, csize) * kTM;
+  if (csize > 1) cl::sync();
   for (int ck = 0; ck < nchunks; ++ck) {
     const int j0 = ck * kKendallChunk, nj = min(kKendallChunk, B - j0);
     __syncthreads();
@@ -865,11 +881,13 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
       Ss[i] = s; Ds[i] = d;
     }
     __syncthreads();
-    for (int ib = 0; ib < B; ib += kThreads) {
+    for (int ib = 0; ib < nslots; ib += kThreads) {
       // without the gradient only the totals are needed and p_ij = p_ji: each unordered pair is visited once (j > i) and
       // the totals are doubled at the end; alternate passes run the rows in reverse so that every thread gets long and
       // short rows (row i has B - 1 - i partners)
-      const int i = (want_grad || !((ib / kThreads) & 1)) ? ib + tid : ib + kThreads - 1 - tid;
+      const int sl = (want_grad || !((ib / kThreads) & 1)) ? ib + tid : ib + kThreads - 1 - tid;
+      if (sl >= nslots) continue;
+      const int i = csize == 1 ? sl : cl::slot_row(sl, crank, csize);
       if (i >= B) continue;
       const int jb = want_grad ? 0 : max(0, i + 1 - j0);         // first staged row of this chunk that row i pairs with
       if (jb >= nj) continue;
@@ -903,15 +921,23 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
       }
     }
   }
-  // block totals per descriptor
+  // block totals per descriptor (cluster per trial: summed over the CTAs)
+  for (int k = 0; k < kZ; ++k) {
+    if (k >= K) break;
+    const double b0 = block_sum_d(sp[k], sm->redd), b1 = block_sum_d(sn[k], sm->redd);
+    const double b2 = block_sum_d((double)cs[k], sm->redd), b3 = block_sum_d((double)co[k], sm->redd);
+    if (tid == 0) { sm->ktot[4 * k] = b0; sm->ktot[4 * k + 1] = b1; sm->ktot[4 * k + 2] = b2; sm->ktot[4 * k + 3] = b3; }
+  }
+  cluster_allreduce_d(c, sm, sm->ktot, 4 * K);
+  __syncthreads();
   double loss = 0.0;
   for (int k = 0; k < kZ; ++k) {
     if (k >= K) break;
     const double sym = want_grad ? 1.0 : 2.0;             // ordered pairs = 2 x unordered pairs
-    double tsp = sym * block_sum_d(sp[k], sm->redd);
-    double tsn = sym * block_sum_d(sn[k], sm->redd);
-    double tcs = sym * block_sum_d((double)cs[k], sm->redd);
-    double tco = sym * block_sum_d((double)co[k], sm->redd);
+    double tsp = sym * sm->ktot[4 * k];
+    double tsn = sym * sm->ktot[4 * k + 1];
+    double tcs = sym * sm->ktot[4 * k + 2];
+    double tco = sym * sm->ktot[4 * k + 3];
     double w = 1.0;
     if (c.p->cfg.kendall_activation) {
       double n_same = tcs > 1.0 ? tcs : 1.0, n_opp = tco > 1.0 ? tco : 1.0;
@@ -925,11 +951,12 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
   __syncthreads();
   if (want_grad) {
     const float scale = (float)(-2.0 / norm);
-    for (int i = tid; i < B * kZ; i += kThreads) {
-      int r = i >> 3, k = i & 7;
+    for (int e = tid; e < nslots * kZ; e += kThreads) {
+      const int sl = e >> 3, k = e & 7, r = csize == 1 ? sl : cl::slot_row(sl, crank, csize);
+      if (r >= B) continue;
       float g = 0.f;
       if (k < K) g = scale * (sm->kw[k] * kacc[(size_t)r * 16 + k] + kacc[(size_t)r * 16 + 8 + k]);
-      dz[i] = g;
+      dz[(size_t)r * kZ + k] = g;
     }
   }
   __syncthreads();
@@ -947,16 +974,23 @@ __device__ __noinline__ void mi_mse_stage(const Ctx& c_ref, int want_grad) {
   float* dz = c.sc + c.p->sl.dz;
   const float cnt = (float)c.B * (float)ns;
   double lp = 0.0;
+  const int crank = c.crank, csize = c.csize;
+  const int nslots = csize == 1 ? c.B : cl::own_tiles(c.B, crank, csize) * kTM;      // cluster per trial: this CTA's rows
   __syncthreads();
-  for (int i = tid; i < c.B * kZ; i += kThreads) {
-    int k = i & 7;
+  for (int e = tid; e < nslots * kZ; e += kThreads) {
+    const int k = e & 7, r = csize == 1 ? (e >> 3) : cl::slot_row(e >> 3, crank, csize);
+    if (r >= c.B) continue;
+    const int i = r * kZ + k;
     float d = 0.f;
     if (k < ns) d = (zE[i] - sm->mean[kE][lE][k]) * sm->inv[kE][lE][k] - zs[i];
     lp += (double)(d * d);
     if (want_grad) dz[i] = 2.f * d / cnt;
   }
   double s = block_sum_d(lp, sm->redd);
-  if (tid == 0) sm->loss_acc[kMI] = s / (double)cnt;
+  if (tid == 0) sm->loss_acc[kMI] = s;
+  cluster_allreduce_d(c, sm, &sm->loss_acc[kMI], 1);
+  __syncthreads();
+  if (tid == 0) sm->loss_acc[kMI] = sm->loss_acc[kMI] / (double)cnt;
   __syncthreads();
 }
 

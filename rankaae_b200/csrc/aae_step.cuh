@@ -36,6 +36,14 @@ struct SmemFixed {
   uint32_t tc_phase2;                   // parity of the next completion of mbar2
   uint32_t tmem_base;                   // TMEM address returned by tcgen05.alloc
   uint32_t tc_phase;                    // parity of the next mbarrier completion
+  // thread-block cluster per trial (ctas_per_trial > 1): partial vectors the other CTAs of the trial read through
+  // distributed shared memory.  Double-buffered, so an all-reduce costs ONE cluster barrier: buffer b is rewritten by
+  // exchange k + 2, which a CTA can only reach through the barrier of exchange k + 1, i.e. after every reader of k is done.
+  uint32_t xpar;                        // buffer of the next exchange
+  float xchg[2][4][kH];
+  double xchgd[2][40];
+  float sgp[kH], sgxp[kH];              // this CTA's partial sums behind sg / sgx
+  double ktot[4 * kZ];                  // Kendall totals per descriptor: sum |p| over p > 0, -(sum |p| over p < 0), counts
 };
 
 enum StageId { kStBatch = 0, kStFwdWide, kStFwdHidden, kStFwdLatent, kStFwdEncLast, kStBwdWide, kStBwdHidden, kStBwdLatent,
@@ -70,6 +78,7 @@ struct Ctx {
   int trial;
   float drop_scale[2];     // [0] encoder / decoder, [1] discriminator: 1 / (1 - p), read once per kernel from the hp row
   uint32_t drop_thresh[2]; // round(p * 65536); 0 = no dropout
+  int crank, csize;        // rank of this CTA in the trial's thread-block cluster / cluster size (ctas_per_trial)
 };
 
 // Shared memory is always reached through the `extern __shared__` symbol (never through a pointer stored
@@ -88,6 +97,62 @@ constexpr int kWTile = kH * kLD;        // 4352 floats
 
 __device__ __forceinline__ const raae_net_layout& NL(const Ctx& c, int net) { return c.p->lay.net[net]; }
 __device__ __forceinline__ float* netp(const Ctx& c, int net) { return c.st + c.p->lay.net[net].param_off; }
+
+// ------------------------------------------------------------------------------------------
+// cluster collectives (no-ops for csize == 1).  Called by ALL threads of ALL CTAs of the trial, the same number of times.
+// ------------------------------------------------------------------------------------------
+// barrier between stages: orders this trial's global / shared writes before the reads of the next stage in every CTA
+__device__ __forceinline__ void stage_sync(const Ctx& c) {
+  if (c.csize > 1) cl::sync();
+  else __syncthreads();
+}
+// in-place sum over the cluster of vec[0..n) (shared memory, n <= 256); every CTA ends with the same bits (rank order)
+__device__ __forceinline__ void cluster_allreduce_f(const Ctx& c, SmemFixed* sm, float* vec, int n) {
+  if (c.csize == 1) return;
+  const int tid = threadIdx.x;
+  __syncthreads();
+  const uint32_t par = sm->xpar;
+  float* x = &sm->xchg[par][0][0];
+  if (tid < n) x[tid] = vec[tid];
+  cl::sync();
+  if (tid < n) {
+    float s = 0.f;
+    for (int r = 0; r < c.csize; ++r) s += cl::ld_f32(cl::map(x + tid, (uint32_t)r));
+    vec[tid] = s;
+  }
+  __syncthreads();
+  if (tid == 0) sm->xpar = par ^ 1u;
+  __syncthreads();
+}
+__device__ __forceinline__ void cluster_allreduce_d(const Ctx& c, SmemFixed* sm, double* vec, int n) {   // n <= 40
+  if (c.csize == 1) return;
+  const int tid = threadIdx.x;
+  __syncthreads();
+  const uint32_t par = sm->xpar;
+  double* x = &sm->xchgd[par][0];
+  if (tid < n) x[tid] = vec[tid];
+  cl::sync();
+  if (tid < n) {
+    double s = 0.0;
+    for (int r = 0; r < c.csize; ++r) s += cl::ld_f64(cl::map(x + tid, (uint32_t)r));
+    vec[tid] = s;
+  }
+  __syncthreads();
+  if (tid == 0) sm->xpar = par ^ 1u;
+  __syncthreads();
+}
+// totals of the BN-backward sums: the stage left this CTA's partials in sm->sgp / sgxp; call after the stage's first cluster
+// barrier (the partials stay untouched until the barrier that ends the stage)
+__device__ __forceinline__ void cluster_gather_sg(const Ctx& c, SmemFixed* sm) {
+  if (c.csize == 1) return;
+  const int tid = threadIdx.x;
+  if (tid < 2 * kH) {
+    const float* src = tid < kH ? &sm->sgp[tid] : &sm->sgxp[tid - kH];
+    float s = 0.f;
+    for (int r = 0; r < c.csize; ++r) s += cl::ld_f32(cl::map(src, (uint32_t)r));
+    if (tid < kH) sm->sg[tid] = s; else sm->sgx[tid - kH] = s;
+  }
+}
 
 __device__ inline MaskSrc make_mask(const Ctx& c, int net, int inst, int layer) {
   MaskSrc m;
@@ -298,13 +363,71 @@ __device__ __forceinline__ void adam_prepare(const Ctx& c, SmemFixed* sm, int o)
 
 // thread 0 only, after every parameter of the phase has been updated
 __device__ inline void adam_finish(const Ctx& c, int o) {
-  if (c.apply) c.st[c.p->lay.opt[o].scalar_off + 1] += 1.f;
+  if (c.apply && c.crank == 0) c.st[c.p->lay.opt[o].scalar_off + 1] += 1.f;
+}
+
+// Cluster variant of adam_apply: every CTA of the trial holds its PARTIAL gradient at the same shared-memory address `g`
+// (complete since the stage's first cluster barrier); rank r owns elements [r per, (r + 1) per), sums the partials of all
+// ranks for them through distributed shared memory (rank order) and applies / exports them.  The caller ends the stage
+// with another cluster barrier before `g` is reused and before any CTA reads the updated parameters.
+__device__ __noinline__ void adam_apply_cluster(const Ctx& c_ref, const SmemFixed* sm, int o, int net, int poff, int n,
+                                                const float* g) {
+  const Ctx c = c_ref;
+  const raae_opt_layout& ol = c.p->lay.opt[o];
+  if (ol.net_off[net] < 0) return;
+  float* dbg = c.a->debug ? c.a->dbg.grads[o]
+             : (c.a->grads_out[o] ? c.a->grads_out[o] + (size_t)c.trial * ol.n : nullptr);
+  if (!dbg && !c.apply) return;
+  const int C = c.csize;
+  const int per = (((n + C - 1) / C) + 3) & ~3;
+  const int i0 = min(n, c.crank * per), i1 = min(n, i0 + per);
+  uint32_t gbase[RAAE_MAX_CTAS];
+#pragma unroll
+  for (int r = 0; r < RAAE_MAX_CTAS; ++r) gbase[r] = cl::map(g, (uint32_t)min(r, C - 1));
+  float* P = c.st + c.p->lay.net[net].param_off + poff;
+  float* M = c.st + ol.m_off + ol.net_off[net] + poff;
+  float* V = c.st + ol.v_off + ol.net_off[net] + poff;
+  const float decay = sm->ad[0], w1 = sm->ad[1], b2 = sm->ad[2], w2 = sm->ad[3], ss = sm->ad[4], bc2s = sm->ad[5];
+  for (int base = i0 + threadIdx.x; base < i1; base += kThreads * 4) {
+    float pv[4], mv[4], vv[4], gv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = base + k * kThreads;
+      gv[k] = 0.f; pv[k] = 0.f; mv[k] = 0.f; vv[k] = 0.f;
+      if (i < i1) {
+        float sgrad = 0.f;
+#pragma unroll
+        for (int r = 0; r < RAAE_MAX_CTAS; ++r)
+          if (r < C) sgrad += cl::ld_f32(gbase[r] + 4u * (uint32_t)i);
+        gv[k] = sgrad;
+        if (c.apply) { pv[k] = P[i]; mv[k] = M[i]; vv[k] = V[i]; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = base + k * kThreads;
+      if (i < i1) {
+        const float gi = gv[k];
+        if (dbg) dbg[ol.net_off[net] + poff + i] = gi;
+        if (c.apply) {
+          float pp = pv[k] * decay;
+          float m = mv[k];
+          m = m + (gi - m) * w1;
+          float v = vv[k] * b2 + (w2 * gi) * gi;
+          float denom = sqrtf(v) / bc2s + kAdamEps;
+          pp = pp - ss * (m / denom);
+          P[i] = pp; M[i] = m; V[i] = v;
+        }
+      }
+    }
+  }
 }
 
 // all threads: update `n` parameters at offset `poff` of net `net` with gradient g (shared memory),
 // and/or export the gradient to the debug buffer.
 __device__ __forceinline__ void adam_apply(const Ctx& c, const SmemFixed* sm, int o, int net, int poff, int n,
                                            const float* __restrict__ g) {
+  if (c.csize > 1) { adam_apply_cluster(c, sm, o, net, poff, n, g); return; }
   const raae_opt_layout& ol = c.p->lay.opt[o];
   float* dbg = c.a->debug ? c.a->dbg.grads[o]
              : (c.a->grads_out[o] ? c.a->grads_out[o] + (size_t)c.trial * ol.n : nullptr);
@@ -360,7 +483,7 @@ struct LayerIn {
 
 // finalize BN statistics of channel c from the shifted sums; updates running buffers in train mode
 __device__ __forceinline__ void bn_finalize(const Ctx& c, SmemFixed* sm, int net, int l, int ch, float shift, float s1,
-                                            float s2, int nrows) {
+                                            float s2, int nrows, bool running = true) {
   const raae_net_layout& nl = NL(c, net);
   float n = (float)nrows;
   float d = s1 / n;
@@ -371,11 +494,51 @@ __device__ __forceinline__ void bn_finalize(const Ctx& c, SmemFixed* sm, int net
 #ifdef RAAE_DEBUG_STATS
   if (net == kE && l == 0) { float* dd = c.sc + c.p->sl.rank; dd[ch] = mean; dd[64 + ch] = var; }
 #endif
+  if (!running) return;
   float* rm = c.st + nl.rm_off[l];
   float* rv = c.st + nl.rv_off[l];
   float unb = nrows > 1 ? var * (n / (n - 1.f)) : var;
   rm[ch] = (1.f - kBnMomentum) * rm[ch] + kBnMomentum * mean;
   rv[ch] = (1.f - kBnMomentum) * rv[ch] + kBnMomentum * unb;
+}
+
+// Cluster merge of BatchNorm batch statistics (all threads; the values of threads tid < kH count): every CTA contributes the
+// mean and the centred sum of squares (M2) of ITS rows; exact parallel-variance merge in rank order, identical in every CTA;
+// rank 0 advances the running buffers.
+__device__ __forceinline__ void bn_merge_cluster(const Ctx& c, SmemFixed* sm, int net, int l, float mean_l, float m2_l) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  const uint32_t par = sm->xpar;
+  float* x = &sm->xchg[par][0][0];
+  if (tid < kH) { x[tid] = mean_l; x[kH + tid] = m2_l; }
+  cl::sync();
+  if (tid < kH) {
+    float mean = 0.f;
+    for (int r = 0; r < c.csize; ++r) mean += (float)cl::own_rows(c.B, r, c.csize) * cl::ld_f32(cl::map(x + tid, (uint32_t)r));
+    mean /= (float)c.B;
+    float m2 = 0.f;
+    for (int r = 0; r < c.csize; ++r) {
+      const float nr = (float)cl::own_rows(c.B, r, c.csize);
+      const float d = cl::ld_f32(cl::map(x + tid, (uint32_t)r)) - mean;
+      m2 += cl::ld_f32(cl::map(x + kH + tid, (uint32_t)r)) + nr * d * d;
+    }
+    bn_finalize(c, sm, net, l, tid, mean, 0.f, m2, c.B, c.crank == 0);
+  }
+  __syncthreads();
+  if (tid == 0) sm->xpar = par ^ 1u;
+  __syncthreads();
+}
+// end of a forward stage in train mode (all threads): shifted single-pass sums of this CTA's rows (threads tid < kH) ->
+// sm->mean / inv of the layer (+ running buffers)
+__device__ __forceinline__ void bn_stats_finish(const Ctx& c, SmemFixed* sm, int net, int l, float shift, float s1, float s2) {
+  if (c.csize == 1) {
+    if (threadIdx.x < kH) bn_finalize(c, sm, net, l, threadIdx.x, shift, s1, s2, c.B);
+    return;
+  }
+  const float nl = (float)cl::own_rows(c.B, c.crank, c.csize);
+  float mean_l = 0.f, m2_l = 0.f;
+  if (nl > 0.f) { const float d = s1 / nl; mean_l = shift + d; m2_l = fmaxf(s2 - s1 * d, 0.f); }
+  bn_merge_cluster(c, sm, net, l, mean_l, m2_l);
 }
 
 __device__ __noinline__ void fwd_hidden_edge(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
@@ -410,7 +573,7 @@ __device__ __noinline__ void fwd_hidden_edge(const Ctx& c_ref, int net, int l, c
   __syncthreads();
   float4 s1v = make_float4(0.f, 0.f, 0.f, 0.f), s2v = make_float4(0.f, 0.f, 0.f, 0.f);
   const int ntiles = (c.B + kTM - 1) / kTM;
-  for (int t = 0; t < ntiles; ++t) {
+  for (int t = c.crank; t < ntiles; t += c.csize) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     if (in.kind == kInLatent) {
       build_latent_tile(At, in.src, row0, nv, K, in.slayer >= 0 ? sm->mean[in.snet][in.slayer] : nullptr,
@@ -463,7 +626,7 @@ __device__ __noinline__ void fwd_hidden_edge(const Ctx& c_ref, int net, int l, c
     float4 uo[kTM / 16];
 #pragma unroll
     for (int i = 0; i < kTM / 16; ++i) uo[i] = *reinterpret_cast<const float4*>(Ot + (ty + 16 * i) * kLD + c4);
-    if (c.train && t == 0) {
+    if (c.train && t == c.crank) {
       float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < kTM / 16; ++i)
@@ -511,8 +674,8 @@ __device__ __noinline__ void fwd_hidden_edge(const Ctx& c_ref, int net, int l, c
     if (tid < kH) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) a2 += sm->red[i][tid];
-      bn_finalize(c, sm, net, l, tid, sm->shift[tid], a1, a2, c.B);
     }
+    bn_stats_finish(c, sm, net, l, tid < kH ? sm->shift[tid] : 0.f, a1, a2);
   }
   __syncthreads();
 }
@@ -535,7 +698,8 @@ __device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, cons
   const float* inv_in = sm->inv[in.snet][in.slayer];
   const int ntiles = (c.B + kTM - 1) / kTM;
   __syncthreads();
-  prefetch_panel_tile(Rb[0], in.src, 0, min(kTM, c.B));
+  const int t_first = c.crank, tstep = c.csize;
+  if (t_first < ntiles) prefetch_panel_tile(Rb[0], in.src, t_first * kTM, min(kTM, c.B - t_first * kTM));
   cp_async_commit();
   load_w_rows(Ws, kLD, Wg, kH, 0, kH);
   if (tid < kH) {
@@ -549,10 +713,10 @@ __device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, cons
   }
   __syncthreads();
   float4 s1v = make_float4(0.f, 0.f, 0.f, 0.f), s2v = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int t = 0; t < ntiles; ++t) {
+  for (int t = t_first, it = 0; t < ntiles; t += tstep, ++it) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
-    float* At = Rb[t & 1];
-    if (t + 1 < ntiles) prefetch_panel_tile(Rb[(t + 1) & 1], in.src, row0 + kTM, min(kTM, c.B - row0 - kTM));
+    float* At = Rb[it & 1];
+    if (t + tstep < ntiles) prefetch_panel_tile(Rb[(it + 1) & 1], in.src, row0 + tstep * kTM, min(kTM, c.B - row0 - tstep * kTM));
     cp_async_commit();
     cp_async_wait<1>();
     transform_act_tile(At, row0, nv, mean_in, inv_in, slope_in, in.mask);
@@ -572,7 +736,7 @@ __device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, cons
     float4 uo[kTM / 16];
 #pragma unroll
     for (int i = 0; i < kTM / 16; ++i) uo[i] = *reinterpret_cast<const float4*>(Ot + (ty + 16 * i) * kLD + c4);
-    if (c.train && t == 0) {
+    if (c.train && it == 0) {
       float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < kTM / 16; ++i)
@@ -622,8 +786,8 @@ __device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, cons
     if (tid < kH) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) a2 += sm->red[i][tid];
-      bn_finalize(c, sm, net, l, tid, sm->shift[tid], a1, a2, c.B);
     }
+    bn_stats_finish(c, sm, net, l, tid < kH ? sm->shift[tid] : 0.f, a1, a2);
   }
   __syncthreads();
 }
@@ -662,7 +826,8 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     }
     cp_async_commit();
   };
-  prefetch_raw(0);
+  const int t_first = c.crank, tstep = c.csize;      // this CTA's tiles: t_first, t_first + tstep, ... (cluster per trial)
+  if (t_first < ntiles) prefetch_raw(t_first);
   {
     // W_l [64 n][64 k] -> hi / lo, K-major SWIZZLE_128B
     float4 w[4];
@@ -686,16 +851,17 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   const float4 sl = *reinterpret_cast<const float4*>(slope_in + c4);
   const uint32_t offK = tc::sw128_chunk_off(ty, c4, tc::kABlockBytes);
   uint32_t ph0 = sm->tc_phase, ph1 = sm->tc_phase2;
-  // transform the raw tile t (own elements) into the hi / lo operands of buffer t & 1, then start its MMAs
-  auto stage = [&](int t) {
+  // transform the raw tile t (own elements) into the hi / lo operands of buffer it & 1 (it = index among this CTA's tiles),
+  // then start its MMAs
+  auto stage = [&](int t, int it) {
     const int row0 = t * kTM, nv = min(kTM, B - row0);
-    float* Ahi = A0 + (t & 1) * 2 * tc::kATileFloats;
+    float* Ahi = A0 + (it & 1) * 2 * tc::kATileFloats;
     float* Alo = Ahi + tc::kATileFloats;
     cp_async_wait<0>();
     float4 uu[kTM / 16];
 #pragma unroll
     for (int i = 0; i < kTM / 16; ++i) uu[i] = *reinterpret_cast<const float4*>(Raw + (ty + 16 * i) * kH + c4);
-    if (t + 1 < ntiles) prefetch_raw(t + 1);       // overwrites only this thread's own (already read) elements
+    if (t + tstep < ntiles) prefetch_raw(t + tstep);   // overwrites only this thread's own (already read) elements
 #pragma unroll
     for (int i = 0; i < kTM / 16; ++i) {
       const int r = ty + 16 * i;
@@ -708,37 +874,37 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       tc::split_store(Ahi, Alo, offK + (uint32_t)(i * 16 * 128), o);
     }
   };
-  auto issue = [&](int t) {              // after a barrier that follows stage(t) and every TMEM read of tile t-2
+  auto issue = [&](int it) {             // after a barrier that follows stage(.., it) and every TMEM read of item it-2
     if (tc::warp_uniform_id() == 0 && tc::elect_one()) {
-      float* Ahi = A0 + (t & 1) * 2 * tc::kATileFloats;
+      float* Ahi = A0 + (it & 1) * 2 * tc::kATileFloats;
       tc::fence_after_sync();
-      tc::issue_gemm_3xtf32(d_tmem + (uint32_t)(64 * (t & 1)), Ahi, Ahi + tc::kATileFloats, Whi, Wlo);
-      tc::mma_commit((t & 1) ? mbar1 : mbar0);
+      tc::issue_gemm_3xtf32(d_tmem + (uint32_t)(64 * (it & 1)), Ahi, Ahi + tc::kATileFloats, Whi, Wlo);
+      tc::mma_commit((it & 1) ? mbar1 : mbar0);
     }
   };
   float s1[32], s2[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   const int erow = 32 * (warp & 3) + lane, ecol0 = 32 * (warp >> 2);
-  stage(0);
+  if (t_first < ntiles) stage(t_first, 0);
   tc::fence_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
   __syncthreads();
-  issue(0);
-  for (int t = 0; t < ntiles; ++t) {
+  if (t_first < ntiles) issue(0);
+  for (int t = t_first, it = 0; t < ntiles; t += tstep, ++it) {
     const int row0 = t * kTM, nv = min(kTM, B - row0);
-    // operands of tile t+1 are staged while the MMAs of tile t run; the accumulator of tile t is read back BEFORE the
-    // MMAs of tile t+1 are queued (a tcgen05.ld issued behind a queued MMA batch waits for it), and the epilogue
+    // operands of the next tile are staged while the MMAs of tile t run; the accumulator of tile t is read back BEFORE the
+    // MMAs of the next tile are queued (a tcgen05.ld issued behind a queued MMA batch waits for it), and the epilogue
     // arithmetic then overlaps them
-    if (t + 1 < ntiles) stage(t + 1);
-    if (t & 1) { tc::mbar_wait(mbar1, ph1); ph1 ^= 1u; }
-    else       { tc::mbar_wait(mbar0, ph0); ph0 ^= 1u; }
+    if (t + tstep < ntiles) stage(t + tstep, it + 1);
+    if (it & 1) { tc::mbar_wait(mbar1, ph1); ph1 ^= 1u; }
+    else        { tc::mbar_wait(mbar0, ph0); ph0 ^= 1u; }
     tc::fence_after_sync();
     float v[32];
-    tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (t & 1) + ecol0), v);
+    tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (it & 1) + ecol0), v);
     tc::fence_before_sync();
     tc::fence_async_smem();              // late: the staging stores have drained behind the mbarrier wait and the TMEM load
     __syncthreads();
-    if (t + 1 < ntiles) issue(t + 1);
+    if (t + tstep < ntiles) issue(it + 1);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 bb = *reinterpret_cast<const float4*>(sm->bias + ecol0 + j);
@@ -750,7 +916,7 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(urow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
     if (train) {
-      if (t == 0) {
+      if (it == 0) {
         // shift of the single-pass variance: column means of PReLU(u) over the first tile (operand buffer 0 is free:
         // its MMAs have completed; buffer 1 may be in use by tile 1)
         float pv[32];
@@ -786,11 +952,12 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     sm->red[warp & 3][ecol0 + lane] = r1;
     sm->red[4 + (warp & 3)][ecol0 + lane] = r2;
     __syncthreads();
+    float a1 = 0.f, a2 = 0.f;
     if (tid < kH) {
-      const float a1 = sm->red[0][tid] + sm->red[1][tid] + sm->red[2][tid] + sm->red[3][tid];
-      const float a2 = sm->red[4][tid] + sm->red[5][tid] + sm->red[6][tid] + sm->red[7][tid];
-      bn_finalize(c, sm, net, l, tid, sm->shift[tid], a1, a2, B);
+      a1 = sm->red[0][tid] + sm->red[1][tid] + sm->red[2][tid] + sm->red[3][tid];
+      a2 = sm->red[4][tid] + sm->red[5][tid] + sm->red[6][tid] + sm->red[7][tid];
     }
+    bn_stats_finish(c, sm, net, l, tid < kH ? sm->shift[tid] : 0.f, a1, a2);
   }
   __syncthreads();
 }
@@ -820,7 +987,9 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, cons
   float* Araw = arena;                       // 2 x [8192] raw chunk, rounded in place (= hi operand)
   float* Alo = arena + 2 * 8192;             // 2 x [8192] lo plane
   float* Bbuf = arena + 4 * 8192;            // 2 x [hi 4096 | lo 4096] weight chunk (double-buffered over the chunks)
-  const int B = c.B, train = c.train, ntiles = (B + kTM - 1) / kTM, ngroups = (ntiles + 7) / 8;
+  // cluster per trial: this CTA walks ITS tiles (local index lt -> tile crank + lt * csize)
+  const int B = c.B, train = c.train, ntiles = cl::own_tiles(B, c.crank, c.csize), ngroups = (ntiles + 7) / 8;
+  const int crank = c.crank, csize = c.csize;
   const uint32_t d_tmem = sm->tmem_base;
   uint64_t* full = reinterpret_cast<uint64_t*>(&sm->pipe_bar[0]);      // [2] A chunk landed
   uint64_t* empty = reinterpret_cast<uint64_t*>(&sm->pipe_bar[2]);     // [2] MMAs of the A buffer completed
@@ -882,7 +1051,7 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, cons
       if (tc::elect_one()) {
         auto load_next = [&]() {
           if (lg >= ngroups) return;
-          const int b = lit & 1, tile = 8 * lg + ltl;
+          const int b = lit & 1, tile = crank + csize * (8 * lg + ltl);
           tc::mbar_expect_tx(&full[b], 32768u);
           tc::bulk_g2s(Araw + b * 8192, xk + ((size_t)tile * nch + lck) * 8192, 32768u, &full[b]);
           ++lit;
@@ -959,7 +1128,7 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, cons
     tc::mbar_wait(accfull, (uint32_t)(g & 1));
     tc::fence_after_sync();
     for (int tl = 0; tl < Tg; ++tl) {
-      const int t = 8 * g + tl;
+      const int t = crank + csize * (8 * g + tl);
       const int row0 = t * kTM, nv = min(kTM, B - row0);
       const int nvw = max(0, min(32, nv - 32 * (warp & 3)));                // valid rows of this warp in the tile
       float v[32];
@@ -1013,29 +1182,39 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, cons
     if (lane == 0 && eh == 0) sm->redw[warp & 3] = nw;
   }
   __syncthreads();
-  if (train && tid < kH) {
+  if (train) {
     // exact merge of the four row groups (parallel variance): mean = sum n_w mean_w / n, M2 = sum M2_w + n_w (mean_w - mean)^2
-    const float n = (float)B;
-    float mean = 0.f;
+    float mean = 0.f, m2 = 0.f;
+    if (tid < kH) {
+      const float n = csize == 1 ? (float)B : sm->redw[0] + sm->redw[1] + sm->redw[2] + sm->redw[3];   // rows of this CTA
+      if (n > 0.f) {
 #pragma unroll
-    for (int w = 0; w < 4; ++w) mean += sm->redw[w] * sm->red[w][tid];
-    mean /= n;
-    float m2 = 0.f;
+        for (int w = 0; w < 4; ++w) mean += sm->redw[w] * sm->red[w][tid];
+        mean /= n;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) { const float d = sm->red[w][tid] - mean; m2 += sm->red[4 + w][tid] + sm->redw[w] * d * d; }
-    bn_finalize(c, sm, net, l, tid, mean, 0.f, m2, B);
+        for (int w = 0; w < 4; ++w) { const float d = sm->red[w][tid] - mean; m2 += sm->red[4 + w][tid] + sm->redw[w] * d * d; }
+      }
+    }
+    if (csize == 1) { if (tid < kH) bn_finalize(c, sm, net, l, tid, mean, 0.f, m2, B); }
+    else bn_merge_cluster(c, sm, net, l, mean, m2);
   }
   __syncthreads();
 }
 
-// statistics of nstyle columns of a [rows][kZ] panel (two-pass); results in sm->zs[0] (mean), zs[1] (biased var)
-__device__ __forceinline__ void latent_colstats(SmemFixed* sm, const float* __restrict__ z, int nrows) {
+// statistics of nstyle columns of a [rows][kZ] panel (two-pass); results in sm->zs[0] (mean), zs[1] (biased var).
+// Cluster per trial: every CTA sums over ITS rows (slot -> row, cl::slot_row) and the sums are all-reduced.
+__device__ __forceinline__ void latent_colstats(const Ctx& c, SmemFixed* sm, const float* __restrict__ z, int nrows) {
   const int tid = threadIdx.x, k = tid & 7, g = tid >> 3;
+  const int crank = c.crank, csize = c.csize;
+  const int nslots = csize == 1 ? nrows : cl::own_tiles(nrows, crank, csize) * kTM;
   float s = 0.f;
-  for (int r0 = g; r0 < nrows; r0 += 32 * 8) {            // 8 loads in flight per thread
+  for (int r0 = g; r0 < nslots; r0 += 32 * 8) {            // 8 loads in flight per thread
     float zv[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { const int r = r0 + 32 * u; zv[u] = r < nrows ? z[(size_t)r * kZ + k] : 0.f; }
+    for (int u = 0; u < 8; ++u) {
+      const int sl = r0 + 32 * u, r = csize == 1 ? sl : cl::slot_row(sl, crank, csize);
+      zv[u] = (sl < nslots && r < nrows) ? z[(size_t)r * kZ + k] : 0.f;
+    }
 #pragma unroll
     for (int u = 0; u < 8; ++u) s += zv[u];
   }
@@ -1046,15 +1225,21 @@ __device__ __forceinline__ void latent_colstats(SmemFixed* sm, const float* __re
   if (tid < kZ) {
     float t = 0.f;
     for (int i = 0; i < 32; ++i) t += red[i * 8 + tid];
-    sm->zs[0][tid] = t / (float)nrows;
+    sm->zs[0][tid] = t;
   }
+  cluster_allreduce_f(c, sm, sm->zs[0], kZ);
+  __syncthreads();
+  if (tid < kZ) sm->zs[0][tid] = sm->zs[0][tid] / (float)nrows;
   __syncthreads();
   const float mu = sm->zs[0][k];
   s = 0.f;
-  for (int r0 = g; r0 < nrows; r0 += 32 * 8) {
+  for (int r0 = g; r0 < nslots; r0 += 32 * 8) {
     float zv[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { const int r = r0 + 32 * u; zv[u] = r < nrows ? z[(size_t)r * kZ + k] : mu; }
+    for (int u = 0; u < 8; ++u) {
+      const int sl = r0 + 32 * u, r = csize == 1 ? sl : cl::slot_row(sl, crank, csize);
+      zv[u] = (sl < nslots && r < nrows) ? z[(size_t)r * kZ + k] : mu;
+    }
 #pragma unroll
     for (int u = 0; u < 8; ++u) { const float d = zv[u] - mu; s = fmaf(d, d, s); }
   }
@@ -1064,8 +1249,11 @@ __device__ __forceinline__ void latent_colstats(SmemFixed* sm, const float* __re
   if (tid < kZ) {
     float t = 0.f;
     for (int i = 0; i < 32; ++i) t += red[i * 8 + tid];
-    sm->zs[1][tid] = t / (float)nrows;
+    sm->zs[1][tid] = t;
   }
+  cluster_allreduce_f(c, sm, sm->zs[1], kZ);
+  __syncthreads();
+  if (tid < kZ) sm->zs[1][tid] = sm->zs[1][tid] / (float)nrows;
   __syncthreads();
 }
 
@@ -1090,7 +1278,7 @@ __device__ __noinline__ void fwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
   if (tid < kZ) sm->bias[tid] = tid < ns ? netp(c, kE)[nl.b_off[l] + tid] : 0.f;
   __syncthreads();
   const int ntiles = (c.B + kTM - 1) / kTM;
-  for (int t = 0; t < ntiles; ++t) {
+  for (int t = c.crank; t < ntiles; t += c.csize) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
     __syncthreads();
@@ -1111,16 +1299,18 @@ __device__ __noinline__ void fwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
   }
   if (c.train) {
     __threadfence_block();
-    latent_colstats(sm, zE, c.B);
+    latent_colstats(c, sm, zE, c.B);
     if (tid < ns) {
       float mean = sm->zs[0][tid], var = sm->zs[1][tid], n = (float)c.B;
       sm->mean[kE][l][tid] = mean;
       sm->inv[kE][l][tid] = 1.f / sqrtf(var + kBnEps);
-      float* rm = c.st + nl.rm_off[l];
-      float* rv = c.st + nl.rv_off[l];
-      float unb = c.B > 1 ? var * (n / (n - 1.f)) : var;
-      rm[tid] = (1.f - kBnMomentum) * rm[tid] + kBnMomentum * mean;
-      rv[tid] = (1.f - kBnMomentum) * rv[tid] + kBnMomentum * unb;
+      if (c.crank == 0) {
+        float* rm = c.st + nl.rm_off[l];
+        float* rv = c.st + nl.rv_off[l];
+        float unb = c.B > 1 ? var * (n / (n - 1.f)) : var;
+        rm[tid] = (1.f - kBnMomentum) * rm[tid] + kBnMomentum * mean;
+        rv[tid] = (1.f - kBnMomentum) * rv[tid] + kBnMomentum * unb;
+      }
     }
   } else if (tid < ns) {
     sm->mean[kE][l][tid] = c.st[nl.rm_off[l] + tid];
@@ -1135,7 +1325,8 @@ __device__ __forceinline__ void fwd_hidden(const Ctx& c, int net, int l, const L
     if (c.p->cfg.tensor_cores & 1) fwd_hidden64_tc(c, net, l, in, u_out);
     else fwd_hidden64(c, net, l, in, u_out);
   } else if (in.kind == kInWide && (c.p->cfg.tensor_cores & 4) && in.img) {
-    fwd_wide_img(c, net, l, c.sc + (in.img == 2 ? c.p->sl.yk : c.p->sl.xk), c.sc + (in.img == 2 ? c.p->sl.yref : c.p->sl.xref), u_out);
+    fwd_wide_img(c, net, l, c.sc + (in.img == 2 ? c.p->sl.yk : c.p->sl.xk),
+                 c.sc + (in.img == 2 ? c.p->sl.yref : c.p->sl.xref) + c.crank * kMaxDim, u_out);
   } else {
     fwd_hidden_edge(c, net, l, in, u_out);
   }
@@ -1177,7 +1368,7 @@ __device__ __forceinline__ void encoder_forward(const Ctx& c, const LayerIn& x, 
   fwd_hidden(c, kE, 0, x, c.sc + c.p->sl.uE[0]);
   for (int l = 1; l < L - 1; ++l) fwd_hidden(c, kE, l, hidden_out(c, kE, l - 1, inst), c.sc + c.p->sl.uE[l]);
   fwd_enc_last(c, hidden_out(c, kE, L - 2, inst));
-  if (c.train && threadIdx.x == 0) c.st[nl.nbt_off] += 1.f;
+  if (c.train && threadIdx.x == 0 && c.crank == 0) c.st[nl.nbt_off] += 1.f;
 }
 
 // hidden blocks of FCDecoder.forward (model.py:518-570); the output Linear is a separate stage
@@ -1186,7 +1377,7 @@ __device__ __forceinline__ void decoder_forward_hidden(const Ctx& c, const Layer
   const int L = nl.n_linear;
   fwd_hidden(c, kD, 0, z, c.sc + c.p->sl.uD[0]);
   for (int l = 1; l < L - 1; ++l) fwd_hidden(c, kD, l, hidden_out(c, kD, l - 1, inst), c.sc + c.p->sl.uD[l]);
-  if (c.train && threadIdx.x == 0) c.st[nl.nbt_off] += 1.f;
+  if (c.train && threadIdx.x == 0 && c.crank == 0) c.st[nl.nbt_off] += 1.f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1244,7 +1435,9 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, c
     for (int j = 0; j < 8; ++j) accW[i][j] = 0.f;
   float accS[kZ] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // latent dW: (ch, row group) partials of dW[ch][:]
   const int ntiles = (c.B + kTM - 1) / kTM;
-  for (int t = 0; t < ntiles; ++t) {
+  float* const sg_dst = c.csize > 1 ? sm->sgp : sm->sg;         // cluster: partial sums, gathered after the barrier
+  float* const sgx_dst = c.csize > 1 ? sm->sgxp : sm->sgx;
+  for (int t = c.crank; t < ntiles; t += c.csize) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     // 1. du = PReLU'(u) * BN'(g); loads batched 4 rows (8 float4) at a time
 #pragma unroll
@@ -1415,11 +1608,11 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, c
   if (want_out && in.kind == kInHidden) {
     sm->red[ty][c4 + 0] = sg4[0]; sm->red[ty][c4 + 1] = sg4[1]; sm->red[ty][c4 + 2] = sg4[2]; sm->red[ty][c4 + 3] = sg4[3];
     __syncthreads();
-    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sg[tid] = s; }
+    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sg_dst[tid] = s; }
     __syncthreads();
     sm->red[ty][c4 + 0] = sgx4[0]; sm->red[ty][c4 + 1] = sgx4[1]; sm->red[ty][c4 + 2] = sgx4[2]; sm->red[ty][c4 + 3] = sgx4[3];
     __syncthreads();
-    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sgx[tid] = s; }
+    if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sgx_dst[tid] = s; }
     __syncthreads();
   }
   if (in.kind == kInHidden) {
@@ -1460,10 +1653,14 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, c
     }
     __syncthreads();
   }
+  if (c.csize > 1) {
+    cl::sync();                                // every CTA's partial gradients / sums are in place
+    if (want_out && in.kind == kInHidden) cluster_gather_sg(c, sm);
+  }
   adam_apply(c, sm, o, net, nl.w_off[l], kH * K, gradW);
   adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
   adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
-  __syncthreads();
+  stage_sync(c);
 }
 
 // backward of a hidden block whose input is another hidden block's panel (K = 64), software-pipelined: the raw
@@ -1485,12 +1682,17 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, cons
   const float* mean_in = sm->mean[in.snet][in.slayer];
   const float* inv_in = sm->inv[in.snet][in.slayer];
   const int ntiles = (c.B + kTM - 1) / kTM;
+  const int t_first = c.crank, tstep = c.csize;
+  float* const sg_dst = c.csize > 1 ? sm->sgp : sm->sg;
+  float* const sgx_dst = c.csize > 1 ? sm->sgxp : sm->sgx;
   __syncthreads();
   {
-    const int nv0 = min(kTM, c.B);
-    prefetch_panel_tile(Gb[0], g_in, 0, nv0);
-    prefetch_panel_tile(Ub, u_l, 0, nv0);
-    prefetch_panel_tile(Pb[0], in.src, 0, nv0);
+    if (t_first < ntiles) {
+      const int nv0 = min(kTM, c.B - t_first * kTM);
+      prefetch_panel_tile(Gb[0], g_in, t_first * kTM, nv0);
+      prefetch_panel_tile(Ub, u_l, t_first * kTM, nv0);
+      prefetch_panel_tile(Pb[0], in.src, t_first * kTM, nv0);
+    }
     cp_async_commit();
   }
   if (tid < kH) {
@@ -1514,10 +1716,10 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, cons
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) accW[i][j] = 0.f;
-  for (int t = 0; t < ntiles; ++t) {
+  for (int t = t_first, it = 0; t < ntiles; t += tstep, ++it) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
-    float* Dt = Gb[t & 1];
-    float* At = Pb[t & 1];
+    float* Dt = Gb[it & 1];
+    float* At = Pb[it & 1];
     cp_async_wait<0>();
     // 1. du = PReLU'(u) * BN'(g), in place over the g tile (own elements)
 #pragma unroll
@@ -1545,11 +1747,11 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, cons
     transform_act_tile(At, row0, nv, mean_in, inv_in, slope_in, in.mask);
     __syncthreads();
     // prefetch tile t+1 (Ub is free; the other two go to the alternate buffers)
-    if (t + 1 < ntiles) {
-      const int nvn = min(kTM, c.B - row0 - kTM);
-      prefetch_panel_tile(Gb[(t + 1) & 1], g_in, row0 + kTM, nvn);
-      prefetch_panel_tile(Ub, u_l, row0 + kTM, nvn);
-      prefetch_panel_tile(Pb[(t + 1) & 1], in.src, row0 + kTM, nvn);
+    if (t + tstep < ntiles) {
+      const int rown = row0 + tstep * kTM, nvn = min(kTM, c.B - rown);
+      prefetch_panel_tile(Gb[(it + 1) & 1], g_in, rown, nvn);
+      prefetch_panel_tile(Ub, u_l, rown, nvn);
+      prefetch_panel_tile(Pb[(it + 1) & 1], in.src, rown, nvn);
     }
     cp_async_commit();
     // 3. dW += du^T a
@@ -1600,11 +1802,11 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, cons
   __syncthreads();
   sm->red[ty][c4 + 0] = sg4[0]; sm->red[ty][c4 + 1] = sg4[1]; sm->red[ty][c4 + 2] = sg4[2]; sm->red[ty][c4 + 3] = sg4[3];
   __syncthreads();
-  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sg[tid] = s; }
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sg_dst[tid] = s; }
   __syncthreads();
   sm->red[ty][c4 + 0] = sgx4[0]; sm->red[ty][c4 + 1] = sgx4[1]; sm->red[ty][c4 + 2] = sgx4[2]; sm->red[ty][c4 + 3] = sgx4[3];
   __syncthreads();
-  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sgx[tid] = s; }
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sgx_dst[tid] = s; }
   {
     const int qq = tid >> 6, tt = tid & 63, m0 = 8 * (tt >> 3), n0 = 8 * (tt & 7);
     for (int pass = 0; pass < 4; ++pass) {
@@ -1620,10 +1822,11 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, cons
       __syncthreads();
     }
   }
+  if (c.csize > 1) { cl::sync(); cluster_gather_sg(c, sm); }
   adam_apply(c, sm, o, net, nl.w_off[l], kH * kH, gradW);
   adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
   adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
-  __syncthreads();
+  stage_sync(c);
 }
 
 // bwd_hidden64 with both contractions on the tensor core: g_prev = du W (128 x 64 x 64, read back every tile) and
@@ -1653,6 +1856,9 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   const float* u_prev = in.src;
   const MaskSrc mk = in.mask;
   const int B = c.B, ntiles = (B + kTM - 1) / kTM;
+  const int t_first = c.crank, tstep = c.csize;        // this CTA's tiles (cluster per trial)
+  float* const sg_dst = c.csize > 1 ? sm->sgp : sm->sg;
+  float* const sgx_dst = c.csize > 1 ? sm->sgxp : sm->sgx;
   const uint32_t d_tmem = sm->tmem_base;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(&sm->mbar);
   __syncthreads();
@@ -1722,8 +1928,8 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       }
     }
   };
-  load_gu(0);
-  for (int t = 0; t < ntiles; ++t) {
+  if (t_first < ntiles) load_gu(t_first);
+  for (int t = t_first, it = 0; t < ntiles; t += tstep, ++it) {
     const int row0 = t * kTM, nv = min(kTM, B - row0);
     float4 up[kTM / 16];
 #pragma unroll
@@ -1732,7 +1938,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       up[i] = r < nv ? *reinterpret_cast<const float4*>(u_prev + (size_t)(row0 + r) * kH + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     // the dW MMAs of the previous tile still read both operand buffers
-    if (t > 0) { tc::mbar_wait(mbar, phase); phase ^= 1u; }
+    if (it > 0) { tc::mbar_wait(mbar, phase); phase ^= 1u; }
     RAAE_PROBE(28);
     // ---- 1. du = PReLU'(u) BN'(g): kept in registers, staged K-major ----
     float4 dur[kTM / 16];
@@ -1800,10 +2006,10 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     __syncthreads();
     if (tc::warp_uniform_id() == 0 && tc::elect_one()) {
       tc::fence_after_sync();
-      tc::issue_gemm_tn_3xtf32(d_tmem + 64, Dhi, Dlo, Phi, Plo, t > 0 ? 1u : 0u);
+      tc::issue_gemm_tn_3xtf32(d_tmem + 64, Dhi, Dlo, Phi, Plo, it > 0 ? 1u : 0u);
       tc::mma_commit(mbar);
     }
-    if (t + 1 < ntiles) load_gu(t + 1);
+    if (t + tstep < ntiles) load_gu(t + tstep);
     // ---- 4. g_prev epilogue (overlaps the dW MMAs): dropout mask of the producing layer, BN-backward partial sums,
     //         coalesced store; a = hi + lo is read back from this thread's own staged chunks ----
 #pragma unroll
@@ -1831,8 +2037,8 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     // but its P stores must not overtake the P reads of this epilogue in other warps -> barrier
     __syncthreads();
   }
-  tc::mbar_wait(mbar, phase);      // last dW MMAs
-  phase ^= 1u;
+  const bool any_tile = t_first < ntiles;          // a CTA without rows (short batch, large cluster) contributes zeros
+  if (any_tile) { tc::mbar_wait(mbar, phase); phase ^= 1u; }      // last dW MMAs
   if (tid == 0) sm->tc_phase = phase;
   // ---- weight gradient: TMEM columns [64,128), M = 64 layout (row n -> lane 32 (n / 16) + n % 16) ----
   float* gradW = Phi;                 // dense [64][64]
@@ -1844,6 +2050,10 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       tc::tmem_ld32(d_tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(64 + 32 * h), v);
+      if (!any_tile) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
       if (lane < 16) {
         const int n = 16 * warp + lane;
 #pragma unroll
@@ -1862,17 +2072,18 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   __syncthreads();
   sm->red[ty][c4 + 0] = sg4[0]; sm->red[ty][c4 + 1] = sg4[1]; sm->red[ty][c4 + 2] = sg4[2]; sm->red[ty][c4 + 3] = sg4[3];
   __syncthreads();
-  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sg[tid] = s; }
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sg_dst[tid] = s; }
   __syncthreads();
   sm->red[ty][c4 + 0] = sgx4[0]; sm->red[ty][c4 + 1] = sgx4[1]; sm->red[ty][c4 + 2] = sgx4[2]; sm->red[ty][c4 + 3] = sgx4[3];
   __syncthreads();
-  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sm->sgx[tid] = s; }
+  if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sgx_dst[tid] = s; }
   __syncthreads();
   RAAE_PROBE(27);
+  if (c.csize > 1) { cl::sync(); cluster_gather_sg(c, sm); }
   adam_apply(c, sm, o, net, nl.w_off[l], kH * kH, gradW);
   adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
   adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
-  __syncthreads();
+  stage_sync(c);
   RAAE_PROBE(27);
 }
 
@@ -1930,7 +2141,7 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
 #pragma unroll
     for (int part = 0; part < 8; ++part) tc::bulk_g2s(Xhi + part * 2048, src + part * 2048, 8192u, full);
   };
-  for (int t = 0; t < ntiles; ++t) {
+  for (int t = c.crank, it = 0; t < ntiles; t += c.csize, ++it) {      // this CTA's tiles (cluster per trial)
     const int row0 = t * kTM, nv = min(kTM, B - row0);
     if (leader) {
       if (tc::elect_one()) load_chunk(t, 0);               // overlaps the du pass
@@ -2001,7 +2212,7 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
         if (tc::elect_one()) {
           tc::fence_after_sync();
           const uint32_t acc = d_tmem + (uint32_t)(64 * ck);
-          tc::issue_gemm_tn128_pass(acc, Xlo, tc::kABlockBytes, Dhi, tc::kABlockBytes, t > 0 ? 1u : 0u);
+          tc::issue_gemm_tn128_pass(acc, Xlo, tc::kABlockBytes, Dhi, tc::kABlockBytes, it > 0 ? 1u : 0u);
           tc::issue_gemm_tn128_pass(acc, Xhi, tc::kABlockBytes, Dlo, tc::kABlockBytes, 1u);
           tc::issue_gemm_tn128_pass(acc, Xhi, tc::kABlockBytes, Dhi, tc::kABlockBytes, 1u);
           tc::mma_commit(done);
@@ -2093,9 +2304,14 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
   {
     // warp w reads TMEM lanes 32 (w & 3) .. + 31 (input columns of the chunk) and output channels 32 (w >> 2) .. + 31
     const int n0 = 32 * (warp >> 2);
+    const bool any_tile = c.crank < ntiles;                // a CTA without rows contributes zeros
     for (int ck = 0; ck < nch; ++ck) {
       float v[32];
       tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * ck + n0), v);
+      if (!any_tile) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
       const int k = 128 * ck + 32 * (warp & 3) + lane;
       if (k < K) {
         const float xr = xref[k];
@@ -2106,10 +2322,11 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (c.csize > 1) cl::sync();
   adam_apply(c, sm, o, net, nl.w_off[l], kH * K, gradW);
   adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
   adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
-  __syncthreads();
+  stage_sync(c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2129,19 +2346,24 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
   float* At = Ws + kZ * kLD;           // [kTM][kLD]
   float* D5 = At + kTile;              // [kTM][kZ]
   float* gradW = D5 + kTM * kZ;        // [kZ][64] + [kZ]
+  float* const sg_dst = c.csize > 1 ? sm->sgp : sm->sg;
+  float* const sgx_dst = c.csize > 1 ? sm->sgxp : sm->sgx;
   __syncthreads();
-  // batch means of dz and dz * zhat
+  // batch means of dz and dz * zhat (cluster per trial: sums over this CTA's rows, all-reduced)
   {
     const int k = tid & 7, g = tid >> 3;
+    const int crank = c.crank, csize = c.csize;
+    const int nslots = csize == 1 ? c.B : cl::own_tiles(c.B, crank, csize) * kTM;
     const float mu = sm->mean[kE][l][k], is = sm->inv[kE][l][k];
     float s0 = 0.f, s1 = 0.f;
-    for (int r0 = g; r0 < c.B; r0 += 32 * 8) {          // 16 loads in flight per thread
+    for (int r0 = g; r0 < nslots; r0 += 32 * 8) {          // 16 loads in flight per thread
       float dv[8], zv[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int r = r0 + 32 * u;
-        dv[u] = r < c.B ? dz[(size_t)r * kZ + k] : 0.f;
-        zv[u] = r < c.B ? zE[(size_t)r * kZ + k] : mu;
+        const int sl = r0 + 32 * u, r = csize == 1 ? sl : cl::slot_row(sl, crank, csize);
+        const bool ok = sl < nslots && r < c.B;
+        dv[u] = ok ? dz[(size_t)r * kZ + k] : 0.f;
+        zv[u] = ok ? zE[(size_t)r * kZ + k] : mu;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -2156,9 +2378,12 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
     if (tid < kZ) {
       float t0 = 0.f, t1 = 0.f;
       for (int i = 0; i < 32; ++i) { t0 += red[i * 8 + tid]; t1 += red[256 + i * 8 + tid]; }
-      sm->zs[2][tid] = t0 / (float)c.B;
-      sm->zs[3][tid] = t1 / (float)c.B;
+      sm->zs[2][tid] = t0;
+      sm->zs[3][tid] = t1;
     }
+    cluster_allreduce_f(c, sm, &sm->zs[2][0], 2 * kZ);        // zs[2] and zs[3] are contiguous
+    __syncthreads();
+    if (tid < 2 * kZ) (&sm->zs[2][0])[tid] = (&sm->zs[2][0])[tid] / (float)c.B;
   }
   for (int i = tid; i < kZ * kH; i += kThreads) {
     int n = i >> 6, k = i & 63;
@@ -2171,7 +2396,7 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
   for (int n = 0; n < kZ; ++n) { accW8[n] = 0.f; wcol[n] = Ws[n * kLD + ch]; }
   float accB = 0.f, sgp = 0.f, sgxp = 0.f;
   const int ntiles = (c.B + kTM - 1) / kTM;
-  for (int t = 0; t < ntiles; ++t) {
+  for (int t = c.crank; t < ntiles; t += c.csize) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
     {
@@ -2234,13 +2459,14 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
   }
   if (tid < ns) gradW[kZ * kH + tid] = sm->red[8][tid] + sm->red[9][tid] + sm->red[10][tid] + sm->red[11][tid];
   if (q == 0) {
-    sm->sg[ch] = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
-    sm->sgx[ch] = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
+    sg_dst[ch] = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
+    sgx_dst[ch] = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
   }
   __syncthreads();
+  if (c.csize > 1) { cl::sync(); cluster_gather_sg(c, sm); }
   adam_apply(c, sm, o, kE, nl.w_off[l], ns * kH, gradW);
   adam_apply(c, sm, o, kE, nl.b_off[l], ns, gradW + kZ * kH);
-  __syncthreads();
+  stage_sync(c);
 }
 
 __device__ __forceinline__ void bwd_hidden(const Ctx& c, int net, int l, const LayerIn& in, const float* __restrict__ u_l,
@@ -2249,9 +2475,9 @@ __device__ __forceinline__ void bwd_hidden(const Ctx& c, int net, int l, const L
     if (c.p->cfg.tensor_cores & 2) bwd_hidden64_tc(c, net, l, in, u_l, g_in, g_out, o);
     else bwd_hidden64(c, net, l, in, u_l, g_in, g_out, o);
   } else if (in.kind == kInWide && in.img == 1 && g_out == nullptr && (c.p->cfg.tensor_cores & 4)) {
-    bwd_wide_img(c, net, l, u_l, g_in, o, c.sc + c.p->sl.xm, c.sc + c.p->sl.xref, nullptr, 0, 0);
+    bwd_wide_img(c, net, l, u_l, g_in, o, c.sc + c.p->sl.xm, c.sc + c.p->sl.xref + c.crank * kMaxDim, nullptr, 0, 0);
   } else if (in.kind == kInWide && in.img == 2 && g_out != nullptr && (c.p->cfg.tensor_cores & 4)) {
-    bwd_wide_img(c, net, l, u_l, g_in, o, c.sc + c.p->sl.ym, c.sc + c.p->sl.yref, g_out, in.ld, in.act);
+    bwd_wide_img(c, net, l, u_l, g_in, o, c.sc + c.p->sl.ym, c.sc + c.p->sl.yref + c.crank * kMaxDim, g_out, in.ld, in.act);
   } else {
     bwd_hidden_edge(c, net, l, in, u_l, g_in, g_out, o);
   }

@@ -37,7 +37,8 @@ int validate_config(const raae_config& c) {
   if (c.batch_size <= 1) return fail(-1, "batch_size must be > 1");
   if (c.n_trials <= 0) return fail(-1, "n_trials must be positive");
   if (c.max_rows < c.batch_size) return fail(-1, "max_rows must be >= batch_size");
-  if (c.ctas_per_trial != 1) return fail(-1, "ctas_per_trial must be 1 in this version");
+  if (c.ctas_per_trial != 1 && c.ctas_per_trial != 2 && c.ctas_per_trial != 4 && c.ctas_per_trial != RAAE_MAX_CTAS)
+    return fail(-1, "ctas_per_trial must be 1, 2, 4 or 8 (thread-block cluster size per trial)");
   if (c.tensor_cores & ~0x17)
     return fail(-1, "tensor_cores: bits 0 (hidden forward), 1 (hidden backward), 2 (input block from operand images), 4 (decoder output forward) are implemented");
   return 0;
@@ -138,8 +139,8 @@ void build_layout(const raae_config& c, raae_layout& L, raae::ScratchLayout& S) 
   S.ym = s; s += tiles * S.nch128 * 16384;
   S.wk = s; s += S.nch64 * 8192;
   S.wl = s; s += ((c.dim_out + 63) / 64) * 8192;
-  S.xref = s; s += 256;
-  S.yref = s; s += 256;
+  S.xref = s; s += 256 * RAAE_MAX_CTAS;                   // one reference row per CTA of the trial's cluster
+  S.yref = s; s += 256 * RAAE_MAX_CTAS;
   S.total = (s + 255) & ~255;
   L.scratch_floats = S.total;
 }
@@ -152,6 +153,7 @@ struct raae_handle {
   int64_t launches;
   bool bound_state, bound_data;
   int shapiro_n;
+  int max_clusters;                             // co-resident clusters of the train kernel (ctas_per_trial > 1), 0 otherwise
   long long* prof;
   // peer-memory exchange of the data-parallel mode (raae_peer_*)
   struct Peer {
@@ -166,6 +168,26 @@ struct raae_handle {
 };
 
 namespace {
+// one thread-block cluster of cfg.ctas_per_trial CTAs per trial
+cudaError_t launch_trials(void (*kernel)(const raae::KParams, const raae::RunArgs), const raae_handle* h, int n_trials,
+                          const raae::RunArgs& a, void* stream) {
+  const int ctas = h->kp.cfg.ctas_per_trial;
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(n_trials * ctas), 1, 1);
+  cfg.blockDim = dim3(raae::kThreads, 1, 1);
+  cfg.dynamicSmemBytes = raae::kSmemBytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctas > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, h->kp, a);
+}
+
 constexpr size_t kPeerHeaderBytes = 256;        // words [0, 8): flags, word 16: finished-block counter, word 17: pre-reduction arrivals
 int peer_release(raae_handle* h) {
   if (!h->peer.local) return 0;
@@ -211,10 +233,34 @@ int raae_create(const raae_config* cfg, int device, raae_handle** out) {
   h->launches = 0;
   h->bound_state = h->bound_data = false;
   h->shapiro_n = 0;
+  h->max_clusters = 0;
   h->prof = nullptr;
   std::memset(&h->peer, 0, sizeof(h->peer));
   RAAE_CUDA(cudaFuncSetAttribute(raae::raae_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raae::kSmemBytes));
   RAAE_CUDA(cudaFuncSetAttribute(raae::raae_val_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raae::kSmemBytes));
+  if (cfg->ctas_per_trial > 1) {
+    // a cluster needs ctas_per_trial SMs of one GPC with the kernel's whole shared-memory footprint free at the same time
+    cudaLaunchConfig_t lc;
+    std::memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)cfg->ctas_per_trial, 1, 1);
+    lc.blockDim = dim3(raae::kThreads, 1, 1);
+    lc.dynamicSmemBytes = raae::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cfg->ctas_per_trial;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    int nclusters = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, raae::raae_train_kernel, &lc);
+    if (e != cudaSuccess || nclusters < 1) {
+      delete h;
+      return fail(-2, std::string("ctas_per_trial = ") + std::to_string(cfg->ctas_per_trial) + " cannot be scheduled on this device" +
+                          (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : std::string()));
+    }
+    h->max_clusters = nclusters;
+  }
   *out = h;
   return 0;
 }
@@ -282,7 +328,7 @@ int raae_step_debug(raae_handle* h, int trial, const raae_debug_io* io, void* st
   a.debug = 1;
   a.epoch = io->epoch;
   a.dbg = *io;
-  raae::raae_train_kernel<<<1, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+  RAAE_CUDA(launch_trials(raae::raae_train_kernel, h, 1, a, stream));
   RAAE_CUDA(cudaGetLastError());
   h->launches++;
   return 0;
@@ -301,7 +347,7 @@ int raae_validate(raae_handle* h, int trial, const raae_val_io* io, void* stream
   a.debug = 1;
   a.epoch = io->epoch;
   a.val = *io;
-  raae::raae_val_kernel<<<1, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+  RAAE_CUDA(launch_trials(raae::raae_val_kernel, h, 1, a, stream));
   RAAE_CUDA(cudaGetLastError());
   h->launches++;
   return 0;
@@ -330,11 +376,11 @@ int raae_train_epochs(raae_handle* h, int epoch_begin, int n_epochs, const int32
     a.out_metrics = out_metrics ? out_metrics + (size_t)e * nt * 6 : nullptr;
     a.val.avg_mutual_info = -INFINITY;
     a.prof = h->prof;
-    raae::raae_train_kernel<<<nt, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+    RAAE_CUDA(launch_trials(raae::raae_train_kernel, h, nt, a, stream));
     RAAE_CUDA(cudaGetLastError());
     h->launches++;
     if (h->kp.n_val >= 3) {
-      raae::raae_val_kernel<<<nt, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+      RAAE_CUDA(launch_trials(raae::raae_val_kernel, h, nt, a, stream));
       RAAE_CUDA(cudaGetLastError());
       h->launches++;
     }
@@ -361,7 +407,7 @@ int raae_train_phase(raae_handle* h, int epoch, int step, int phase_mask, const 
   a.phase_mask = phase_mask;
   for (int o = 0; o < RAAE_NUM_PHASES; ++o) a.grads_out[o] = grads[o];
   a.val.avg_mutual_info = -INFINITY;
-  raae::raae_train_kernel<<<nt, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+  RAAE_CUDA(launch_trials(raae::raae_train_kernel, h, nt, a, stream));
   RAAE_CUDA(cudaGetLastError());
   h->launches++;
   return 0;
@@ -393,7 +439,7 @@ int raae_validate_epoch(raae_handle* h, int epoch, float* out_losses, float* out
   a.out_losses = out_losses;
   a.out_metrics = out_metrics;
   a.val.avg_mutual_info = -INFINITY;
-  raae::raae_val_kernel<<<h->kp.cfg.n_trials, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+  RAAE_CUDA(launch_trials(raae::raae_val_kernel, h, h->kp.cfg.n_trials, a, stream));
   RAAE_CUDA(cudaGetLastError());
   h->launches++;
   return 0;

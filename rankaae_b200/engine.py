@@ -104,7 +104,8 @@ def make_config(cfg, n_trials, max_rows=None):
         n_aux=int(g("n_aux", 0)), n_layers=int(g("n_layers", 3)), dis_layers=int(g("FC_discriminator_layers", 3)),
         batch_size=bs, n_trials=int(n_trials), kendall_activation=int(bool(g("kendall_activation", False))),
         use_flex_spec_target=int(bool(g("use_flex_spec_target", False))), decoder_softplus=int(act == "Softplus"),
-        max_rows=int(max_rows if max_rows is not None else bs), ctas_per_trial=1,
+        max_rows=int(max_rows if max_rows is not None else bs),
+        ctas_per_trial=int(g("ctas_per_trial", int(os.environ.get("RAAE_CTAS_PER_TRIAL", "1")))),
         tensor_cores=int(g("tensor_cores", int(os.environ.get("RAAE_TENSOR_CORES", str(DEFAULT_TENSOR_CORES))))))
 
 
