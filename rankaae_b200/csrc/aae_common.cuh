@@ -8,6 +8,16 @@
 
 #include "rankaae_b200.h"
 
+// The device code is compiled twice: RAAE_CLUSTER == 0 (rankaae_b200.cu: one CTA per trial, the ensemble path - cluster rank 0
+// and size 1 are compile-time constants, so none of the cluster code exists there) and RAAE_CLUSTER == 1
+// (kernels_cluster.cu: ctas_per_trial 2 / 4 / 8, namespace raae_cn).
+#ifndef RAAE_CLUSTER
+#define RAAE_CLUSTER 0
+#endif
+#if RAAE_CLUSTER
+#define raae raae_cn
+#endif
+
 namespace raae {
 
 constexpr int kH = RAAE_HIDDEN;   // hidden width
@@ -316,9 +326,11 @@ __device__ __forceinline__ int own_tiles(int B, int crank, int csize) {
   return nt > crank ? (nt - crank + csize - 1) / csize : 0;
 }
 __device__ __forceinline__ int own_rows(int B, int crank, int csize) {
-  int n = 0;
-  for (int t = crank; t * kTM < B; t += csize) n += min(kTM, B - t * kTM);
-  return n;
+  const int nt = (B + kTM - 1) / kTM;
+  if (crank >= nt) return 0;
+  int rows = ((nt - 1 - crank) / csize + 1) * kTM;
+  if ((nt - 1) % csize == crank) rows -= nt * kTM - B;          // the short last tile is this rank's
+  return rows;
 }
 // row of own-row slot s (slots of a CTA: own_tiles x 128; the row may be >= B in the last tile)
 __device__ __forceinline__ int slot_row(int s, int crank, int csize) { return ((s >> 7) * csize + crank) * kTM + (s & (kTM - 1)); }

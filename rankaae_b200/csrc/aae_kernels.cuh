@@ -244,8 +244,10 @@ __device__ __forceinline__ void init_ctx(Ctx& c, const KParams& p, const RunArgs
   c.train = 1;
   c.x = c.sc + p.sl.xn;
   c.xld = p.sl.xld;
+#if RAAE_CLUSTER
   c.crank = (int)cl::ctarank();
   c.csize = (int)cl::nctarank();
+#endif
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     const double pd = c.hp[g ? RAAE_HP_DIS_DROPOUT : RAAE_HP_DROPOUT];
@@ -259,9 +261,10 @@ constexpr size_t kSmemBytes = kArenaOffset + (size_t)kArenaFloats * sizeof(float
 // TMEM accumulator + mbarrier for the tcgen05 path (one CTA per SM, so the allocation never contends)
 __device__ __forceinline__ void tc_setup(const KParams& p, SmemFixed* sm) {
   // cluster per trial: no CTA may touch a peer's shared memory before that peer runs, nor exit while a peer may still read its own
+#if RAAE_CLUSTER
   if (threadIdx.x == 0) sm->xpar = 0u;
-  if (cl::nctarank() > 1) cl::sync();
-  else __syncthreads();
+  cl::sync();
+#endif
   if (!p.cfg.tensor_cores) return;
   if (threadIdx.x < 32) tc::tmem_alloc(&sm->tmem_base, tc::kTmemCols);
   if (threadIdx.x == 0) {
@@ -275,7 +278,9 @@ __device__ __forceinline__ void tc_setup(const KParams& p, SmemFixed* sm) {
   tc::fence_after_sync();
 }
 __device__ __forceinline__ void tc_teardown(const KParams& p, SmemFixed* sm) {
-  if (cl::nctarank() > 1) cl::sync();
+#if RAAE_CLUSTER
+  cl::sync();
+#endif
   if (!p.cfg.tensor_cores) return;
   tc::fence_before_sync();
   __syncthreads();
@@ -285,7 +290,11 @@ __device__ __forceinline__ void tc_teardown(const KParams& p, SmemFixed* sm) {
 __global__ void __launch_bounds__(kThreads, 1)
 raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunArgs a) {
   RAAE_SMEM();
+#if RAAE_CLUSTER
   const int trial = a.trial0 + (int)(blockIdx.x / cl::nctarank());     // one thread-block cluster (ctas_per_trial CTAs) per trial
+#else
+  const int trial = a.trial0 + blockIdx.x;
+#endif
   Ctx c;
   init_ctx(c, p, a, trial);
   if (threadIdx.x < 32) sm->prof[threadIdx.x] = 0;
@@ -463,7 +472,11 @@ __device__ inline void plateau_step(const Ctx& c, double metric) {
 __global__ void __launch_bounds__(kThreads, 1)
 raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunArgs a) {
   RAAE_SMEM();
+#if RAAE_CLUSTER
   const int trial = a.trial0 + (int)(blockIdx.x / cl::nctarank());
+#else
+  const int trial = a.trial0 + blockIdx.x;
+#endif
   Ctx c;
   init_ctx(c, p, a, trial);
   const int tid = threadIdx.x, ns = p.cfg.nstyle, K = p.cfg.n_aux;

@@ -85,7 +85,8 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
   const int ntiles = (c.B + kTM - 1) / kTM;
   float* const sg_dst = c.csize > 1 ? sm->sgp : sm->sg;         // cluster per trial: partial sums, gathered after the barrier
   float* const sgx_dst = c.csize > 1 ? sm->sgxp : sm->sgx;
-  for (int t = c.crank, it = 0; t < ntiles; t += c.csize, ++it) {      // this CTA's tiles; `it` counts them
+  for (int t = c.crank; t < ntiles; t += c.csize) {      // this CTA's tiles; `it` counts them
+    const int it = tile_iter(c, t);
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     const long long q0 = clock64();
     auto load_w = [&](int ck) {             // elected thread only
@@ -389,7 +390,7 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
       __syncthreads();
     }
     const long long q2 = clock64();
-    if (tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) { sm->prof[16] += q1 - q0; sm->prof[17 + (mode == kLastSmooth)] += q2 - q1; }
+    if (!RAAE_PROF_FWD && tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) { sm->prof[16] += q1 - q0; sm->prof[17 + (mode == kLastSmooth)] += q2 - q1; }
     if (want_bwd) {
       // db, dW += dv^T a, g = (dv @ W) * dropout
       {
@@ -400,7 +401,7 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
       const long long q3 = clock64();
       mma_tn8(Y, kLDW, 8 * (tid >> 3), At, kLD, 8 * (tid & 7), 0, kTM, accW);
       const long long q4 = clock64();
-      if (tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) { sm->prof[19] += q3 - q2; sm->prof[20] += q4 - q3; }
+      if (!RAAE_PROF_FWD && tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) { sm->prof[19] += q3 - q2; sm->prof[20] += q4 - q3; }
       float acc[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -432,7 +433,7 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
           *reinterpret_cast<float4*>(c.sc + c.p->sl.g[0] + (size_t)(row0 + r) * kH + c4) = gm;
         }
       }
-      if (tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) sm->prof[21] += clock64() - q4;
+      if (!RAAE_PROF_FWD && tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) sm->prof[21] += clock64() - q4;
     }
     __syncthreads();
   }
@@ -455,7 +456,7 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
     __syncthreads();
     if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sgx_dst[tid] = s; }
     float* gradW = Y;            // dense [N][64]
-    float* gradb = At;           // [N]
+    float* gradb = Y + N * kH;   // [N], right behind dW: [W | b] is one run of the parameter vector
     const int m0 = 8 * (tid >> 3), n0 = 8 * (tid & 7);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -465,8 +466,7 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
     if (tid < N) gradb[tid] = dbp;
     __syncthreads();
     if (c.csize > 1) { cl::sync(); cluster_gather_sg(c, sm); }
-    adam_apply(c, sm, o, kD, nl.w_off[l], N * kH, gradW);
-    adam_apply(c, sm, o, kD, nl.b_off[l], N, gradb);
+    adam_apply(c, sm, o, kD, nl.w_off[l], N * kH + N, gradW);
     stage_sync(c);
   }
   __syncthreads();
@@ -720,15 +720,16 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
     cluster_allreduce_d(c, sm, &sm->loss_acc[kAdv], 1);
   }
   if (backward) {
-    float* gW1 = arena;                // [64][64]
-    float* gsm = gW1 + kH * kH;        // W0 [64*ns] | b0 64 | a0 64 | b1 64 | a1 64 | W2 64 | b2 1
-    float* gW0 = gsm;
-    float* gb0 = gW0 + kH * kZ;
+    // the whole discriminator gradient in parameter order (one AdamW pass): W0 [64 ns] | b0 | a0 | W1 [64][64] | b1 | a1 | W2 | b2
+    float* gW0 = arena;
+    float* gb0 = gW0 + kH * ns;
     float* ga0 = gb0 + kH;
-    float* gb1 = ga0 + kH;
+    float* gW1 = ga0 + kH;
+    float* gb1 = gW1 + kH * kH;
     float* ga1 = gb1 + kH;
     float* gW2 = ga1 + kH;
     float* gb2 = gW2 + kH;
+    float* gsm = arena + 8192;         // scratch for the dW0 row groups, behind the gradient vector
     __syncthreads();
     {
       const int qq = tid >> 6, tt = tid & 63, m0 = 8 * (tt >> 3), n0 = 8 * (tt & 7);
@@ -747,7 +748,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
     }
     {
       // reduce the four row groups of dW0 through the (free) tile area behind the gradient vectors
-      float* part = gsm + 1024;              // [4][64][8]
+      float* part = gsm;                     // [4][64][8]
 #pragma unroll
       for (int k = 0; k < kZ; ++k) part[(q * kH + ch) * kZ + k] = accW0[k];
     }
@@ -755,7 +756,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const float* part = gsm + 1024;
+      const float* part = gsm;
       int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
       if (k < ns) gW0[n * ns + k] = part[(0 * kH + n) * kZ + k] + part[(1 * kH + n) * kZ + k] + part[(2 * kH + n) * kZ + k] + part[(3 * kH + n) * kZ + k];
     }
@@ -778,14 +779,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
     if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb0[tid] = s; }
     __syncthreads();
     if (c.csize > 1) cl::sync();
-    adam_apply(c, sm, o, kS, nl.w_off[0], kH * ns, gW0);
-    adam_apply(c, sm, o, kS, nl.b_off[0], kH, gb0);
-    adam_apply(c, sm, o, kS, nl.a_off[0], kH, ga0);
-    adam_apply(c, sm, o, kS, nl.w_off[1], kH * kH, gW1);
-    adam_apply(c, sm, o, kS, nl.b_off[1], kH, gb1);
-    adam_apply(c, sm, o, kS, nl.a_off[1], kH, ga1);
-    adam_apply(c, sm, o, kS, nl.w_off[2], kH, gW2);
-    adam_apply(c, sm, o, kS, nl.b_off[2], 1, gb2);
+    adam_apply(c, sm, o, kS, nl.w_off[0], nl.n_params, gW0);
     stage_sync(c);
   }
   __syncthreads();

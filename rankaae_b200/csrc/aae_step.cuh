@@ -58,6 +58,10 @@ struct StageTimer {
 };
 
 // sub-stage probe: thread 0 adds the cycles since the previous probe to sm->prof[slot]
+#ifndef RAAE_PROF_FWD
+#define RAAE_PROF_FWD 0                 // 1: sub-stage probes of fwd_hidden64_tc in slots 16..22 (tools/stage_profile.py raw)
+#endif
+#define RAAE_FPROBE(slot) do { if (RAAE_PROF_FWD) RAAE_PROBE(slot); } while (0)
 #define RAAE_PROBE_INIT() long long probe_t_ = clock64()
 #define RAAE_PROBE(slot) do { if (threadIdx.x == 0) { long long now_ = clock64(); sm->prof[slot] += now_ - probe_t_; probe_t_ = now_; } } while (0)
 
@@ -78,7 +82,12 @@ struct Ctx {
   int trial;
   float drop_scale[2];     // [0] encoder / decoder, [1] discriminator: 1 / (1 - p), read once per kernel from the hp row
   uint32_t drop_thresh[2]; // round(p * 65536); 0 = no dropout
+#if RAAE_CLUSTER
   int crank, csize;        // rank of this CTA in the trial's thread-block cluster / cluster size (ctas_per_trial)
+#else
+  // one CTA per trial (this translation unit): every cluster branch folds away at compile time
+  static constexpr int crank = 0, csize = 1;
+#endif
 };
 
 // Shared memory is always reached through the `extern __shared__` symbol (never through a pointer stored
@@ -101,6 +110,22 @@ __device__ __forceinline__ float* netp(const Ctx& c, int net) { return c.st + c.
 // ------------------------------------------------------------------------------------------
 // cluster collectives (no-ops for csize == 1).  Called by ALL threads of ALL CTAs of the trial, the same number of times.
 // ------------------------------------------------------------------------------------------
+// index of tile t among this CTA's tiles (t = crank, crank + csize, ...); with one CTA per trial it IS the tile index
+__device__ __forceinline__ int tile_iter(const Ctx& c, int t) {
+#if RAAE_CLUSTER
+  return (t - c.crank) / c.csize;
+#else
+  return t;
+#endif
+}
+// does this CTA own any tile of a batch of ntiles tiles?  (always, with one CTA per trial: ntiles >= 1)
+__device__ __forceinline__ bool has_tiles(const Ctx& c, int ntiles) {
+#if RAAE_CLUSTER
+  return c.crank < ntiles;
+#else
+  return true;
+#endif
+}
 // barrier between stages: orders this trial's global / shared writes before the reads of the next stage in every CTA
 __device__ __forceinline__ void stage_sync(const Ctx& c) {
   if (c.csize > 1) cl::sync();
@@ -116,8 +141,12 @@ __device__ __forceinline__ void cluster_allreduce_f(const Ctx& c, SmemFixed* sm,
   if (tid < n) x[tid] = vec[tid];
   cl::sync();
   if (tid < n) {
+    float v[RAAE_MAX_CTAS];
+#pragma unroll
+    for (int r = 0; r < RAAE_MAX_CTAS; ++r) v[r] = r < c.csize ? cl::ld_f32(cl::map(x + tid, (uint32_t)r)) : 0.f;   // all loads in flight
     float s = 0.f;
-    for (int r = 0; r < c.csize; ++r) s += cl::ld_f32(cl::map(x + tid, (uint32_t)r));
+#pragma unroll
+    for (int r = 0; r < RAAE_MAX_CTAS; ++r) s += v[r];
     vec[tid] = s;
   }
   __syncthreads();
@@ -133,8 +162,12 @@ __device__ __forceinline__ void cluster_allreduce_d(const Ctx& c, SmemFixed* sm,
   if (tid < n) x[tid] = vec[tid];
   cl::sync();
   if (tid < n) {
+    double v[RAAE_MAX_CTAS];
+#pragma unroll
+    for (int r = 0; r < RAAE_MAX_CTAS; ++r) v[r] = r < c.csize ? cl::ld_f64(cl::map(x + tid, (uint32_t)r)) : 0.0;
     double s = 0.0;
-    for (int r = 0; r < c.csize; ++r) s += cl::ld_f64(cl::map(x + tid, (uint32_t)r));
+#pragma unroll
+    for (int r = 0; r < RAAE_MAX_CTAS; ++r) s += v[r];
     vec[tid] = s;
   }
   __syncthreads();
@@ -148,8 +181,12 @@ __device__ __forceinline__ void cluster_gather_sg(const Ctx& c, SmemFixed* sm) {
   const int tid = threadIdx.x;
   if (tid < 2 * kH) {
     const float* src = tid < kH ? &sm->sgp[tid] : &sm->sgxp[tid - kH];
+    float v[RAAE_MAX_CTAS];
+#pragma unroll
+    for (int r = 0; r < RAAE_MAX_CTAS; ++r) v[r] = r < c.csize ? cl::ld_f32(cl::map(src, (uint32_t)r)) : 0.f;
     float s = 0.f;
-    for (int r = 0; r < c.csize; ++r) s += cl::ld_f32(cl::map(src, (uint32_t)r));
+#pragma unroll
+    for (int r = 0; r < RAAE_MAX_CTAS; ++r) s += v[r];
     if (tid < kH) sm->sg[tid] = s; else sm->sgx[tid - kH] = s;
   }
 }
@@ -513,15 +550,21 @@ __device__ __forceinline__ void bn_merge_cluster(const Ctx& c, SmemFixed* sm, in
   if (tid < kH) { x[tid] = mean_l; x[kH + tid] = m2_l; }
   cl::sync();
   if (tid < kH) {
+    float mr[RAAE_MAX_CTAS], qr[RAAE_MAX_CTAS], nr[RAAE_MAX_CTAS];
+#pragma unroll
+    for (int r = 0; r < RAAE_MAX_CTAS; ++r) {            // all loads in flight before the first use
+      const bool on = r < c.csize;
+      mr[r] = on ? cl::ld_f32(cl::map(x + tid, (uint32_t)r)) : 0.f;
+      qr[r] = on ? cl::ld_f32(cl::map(x + kH + tid, (uint32_t)r)) : 0.f;
+      nr[r] = on ? (float)cl::own_rows(c.B, r, c.csize) : 0.f;
+    }
     float mean = 0.f;
-    for (int r = 0; r < c.csize; ++r) mean += (float)cl::own_rows(c.B, r, c.csize) * cl::ld_f32(cl::map(x + tid, (uint32_t)r));
+#pragma unroll
+    for (int r = 0; r < RAAE_MAX_CTAS; ++r) mean += nr[r] * mr[r];
     mean /= (float)c.B;
     float m2 = 0.f;
-    for (int r = 0; r < c.csize; ++r) {
-      const float nr = (float)cl::own_rows(c.B, r, c.csize);
-      const float d = cl::ld_f32(cl::map(x + tid, (uint32_t)r)) - mean;
-      m2 += cl::ld_f32(cl::map(x + kH + tid, (uint32_t)r)) + nr * d * d;
-    }
+#pragma unroll
+    for (int r = 0; r < RAAE_MAX_CTAS; ++r) { const float d = mr[r] - mean; m2 += qr[r] + nr[r] * d * d; }
     bn_finalize(c, sm, net, l, tid, mean, 0.f, m2, c.B, c.crank == 0);
   }
   __syncthreads();
@@ -699,7 +742,7 @@ __device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, cons
   const int ntiles = (c.B + kTM - 1) / kTM;
   __syncthreads();
   const int t_first = c.crank, tstep = c.csize;
-  if (t_first < ntiles) prefetch_panel_tile(Rb[0], in.src, t_first * kTM, min(kTM, c.B - t_first * kTM));
+  if (has_tiles(c, ntiles)) prefetch_panel_tile(Rb[0], in.src, t_first * kTM, min(kTM, c.B - t_first * kTM));
   cp_async_commit();
   load_w_rows(Ws, kLD, Wg, kH, 0, kH);
   if (tid < kH) {
@@ -713,7 +756,8 @@ __device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, cons
   }
   __syncthreads();
   float4 s1v = make_float4(0.f, 0.f, 0.f, 0.f), s2v = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int t = t_first, it = 0; t < ntiles; t += tstep, ++it) {
+  for (int t = t_first; t < ntiles; t += tstep) {
+    const int it = tile_iter(c, t);
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     float* At = Rb[it & 1];
     if (t + tstep < ntiles) prefetch_panel_tile(Rb[(it + 1) & 1], in.src, row0 + tstep * kTM, min(kTM, c.B - row0 - tstep * kTM));
@@ -827,7 +871,8 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     cp_async_commit();
   };
   const int t_first = c.crank, tstep = c.csize;      // this CTA's tiles: t_first, t_first + tstep, ... (cluster per trial)
-  if (t_first < ntiles) prefetch_raw(t_first);
+  RAAE_PROBE_INIT();
+  if (has_tiles(c, ntiles)) prefetch_raw(t_first);
   {
     // W_l [64 n][64 k] -> hi / lo, K-major SWIZZLE_128B
     float4 w[4];
@@ -886,11 +931,14 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
 #pragma unroll
   for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   const int erow = 32 * (warp & 3) + lane, ecol0 = 32 * (warp >> 2);
-  if (t_first < ntiles) stage(t_first, 0);
+  RAAE_FPROBE(16);                       // weights staged, constants loaded
+  if (has_tiles(c, ntiles)) stage(t_first, 0);
   tc::fence_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
   __syncthreads();
-  if (t_first < ntiles) issue(0);
-  for (int t = t_first, it = 0; t < ntiles; t += tstep, ++it) {
+  RAAE_FPROBE(17);                       // first tile landed and staged
+  if (has_tiles(c, ntiles)) issue(0);
+  for (int t = t_first; t < ntiles; t += tstep) {
+    const int it = tile_iter(c, t);
     const int row0 = t * kTM, nv = min(kTM, B - row0);
     // operands of the next tile are staged while the MMAs of tile t run; the accumulator of tile t is read back BEFORE the
     // MMAs of the next tile are queued (a tcgen05.ld issued behind a queued MMA batch waits for it), and the epilogue
@@ -904,6 +952,7 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     tc::fence_before_sync();
     tc::fence_async_smem();              // late: the staging stores have drained behind the mbarrier wait and the TMEM load
     __syncthreads();
+    RAAE_FPROBE(18);                     // MMAs + accumulator read-back (+ staging of the next tile)
     if (t + tstep < ntiles) issue(it + 1);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -941,6 +990,7 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       }
     }
   }
+  RAAE_FPROBE(19);                       // epilogues (stores, shift, partial sums)
   tc::fence_before_sync();
   __syncthreads();
   if (tid == 0) { sm->tc_phase = ph0; sm->tc_phase2 = ph1; }
@@ -957,7 +1007,9 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       a1 = sm->red[0][tid] + sm->red[1][tid] + sm->red[2][tid] + sm->red[3][tid];
       a2 = sm->red[4][tid] + sm->red[5][tid] + sm->red[6][tid] + sm->red[7][tid];
     }
+    RAAE_FPROBE(20);                     // column reductions
     bn_stats_finish(c, sm, net, l, tid < kH ? sm->shift[tid] : 0.f, a1, a2);
+    RAAE_FPROBE(21);                     // statistics (cluster: exchange + merge)
   }
   __syncthreads();
 }
@@ -1596,7 +1648,7 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, c
     __syncthreads();
   }
   // ---- reductions, gradient export, AdamW ----
-  float* gb = Dt;                // [64] db | [64] dslope
+  float* gb = gradW + kH * K;    // [64] db | [64] dslope, right behind dW: [W | b | a] is one run of the parameter vector
   sm->red[ty][c4 + 0] = db4[0]; sm->red[ty][c4 + 1] = db4[1]; sm->red[ty][c4 + 2] = db4[2]; sm->red[ty][c4 + 3] = db4[3];
   __syncthreads();
   if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[tid] = s; }
@@ -1657,9 +1709,7 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, c
     cl::sync();                                // every CTA's partial gradients / sums are in place
     if (want_out && in.kind == kInHidden) cluster_gather_sg(c, sm);
   }
-  adam_apply(c, sm, o, net, nl.w_off[l], kH * K, gradW);
-  adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
-  adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
+  adam_apply(c, sm, o, net, nl.w_off[l], kH * K + 2 * kH, gradW);
   stage_sync(c);
 }
 
@@ -1687,7 +1737,7 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, cons
   float* const sgx_dst = c.csize > 1 ? sm->sgxp : sm->sgx;
   __syncthreads();
   {
-    if (t_first < ntiles) {
+    if (has_tiles(c, ntiles)) {
       const int nv0 = min(kTM, c.B - t_first * kTM);
       prefetch_panel_tile(Gb[0], g_in, t_first * kTM, nv0);
       prefetch_panel_tile(Ub, u_l, t_first * kTM, nv0);
@@ -1716,7 +1766,8 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, cons
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) accW[i][j] = 0.f;
-  for (int t = t_first, it = 0; t < ntiles; t += tstep, ++it) {
+  for (int t = t_first; t < ntiles; t += tstep) {
+    const int it = tile_iter(c, t);
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     float* Dt = Gb[it & 1];
     float* At = Pb[it & 1];
@@ -1790,8 +1841,8 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, cons
   cp_async_wait<0>();
   __syncthreads();
   // ---- reductions, gradient export, AdamW ----
-  float* gb = Gb[0];               // [64] db | [64] dslope
   float* gradW = Pb[0];            // dense [64][64]
+  float* gb = gradW + kH * kH;     // [64] db | [64] dslope, right behind dW (one AdamW pass over [W | b | a])
   sm->red[ty][c4 + 0] = db4[0]; sm->red[ty][c4 + 1] = db4[1]; sm->red[ty][c4 + 2] = db4[2]; sm->red[ty][c4 + 3] = db4[3];
   __syncthreads();
   if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; gb[tid] = s; }
@@ -1823,9 +1874,7 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, cons
     }
   }
   if (c.csize > 1) { cl::sync(); cluster_gather_sg(c, sm); }
-  adam_apply(c, sm, o, net, nl.w_off[l], kH * kH, gradW);
-  adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
-  adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
+  adam_apply(c, sm, o, net, nl.w_off[l], kH * kH + 2 * kH, gradW);
   stage_sync(c);
 }
 
@@ -1928,8 +1977,9 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       }
     }
   };
-  if (t_first < ntiles) load_gu(t_first);
-  for (int t = t_first, it = 0; t < ntiles; t += tstep, ++it) {
+  if (has_tiles(c, ntiles)) load_gu(t_first);
+  for (int t = t_first; t < ntiles; t += tstep) {
+    const int it = tile_iter(c, t);
     const int row0 = t * kTM, nv = min(kTM, B - row0);
     float4 up[kTM / 16];
 #pragma unroll
@@ -2037,12 +2087,12 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
     // but its P stores must not overtake the P reads of this epilogue in other warps -> barrier
     __syncthreads();
   }
-  const bool any_tile = t_first < ntiles;          // a CTA without rows (short batch, large cluster) contributes zeros
+  const bool any_tile = has_tiles(c, ntiles);      // a CTA without rows (short batch, large cluster) contributes zeros
   if (any_tile) { tc::mbar_wait(mbar, phase); phase ^= 1u; }      // last dW MMAs
   if (tid == 0) sm->tc_phase = phase;
   // ---- weight gradient: TMEM columns [64,128), M = 64 layout (row n -> lane 32 (n / 16) + n % 16) ----
   float* gradW = Phi;                 // dense [64][64]
-  float* gb = Dhi;                    // [64] db | [64] dslope
+  float* gb = gradW + kH * kH;        // [64] db | [64] dslope, right behind dW (one AdamW pass over [W | b | a])
   tc::fence_after_sync();
   __syncthreads();
   if (warp < 4) {
@@ -2080,9 +2130,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   __syncthreads();
   RAAE_PROBE(27);
   if (c.csize > 1) { cl::sync(); cluster_gather_sg(c, sm); }
-  adam_apply(c, sm, o, net, nl.w_off[l], kH * kH, gradW);
-  adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
-  adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
+  adam_apply(c, sm, o, net, nl.w_off[l], kH * kH + 2 * kH, gradW);
   stage_sync(c);
   RAAE_PROBE(27);
 }
@@ -2141,7 +2189,8 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
 #pragma unroll
     for (int part = 0; part < 8; ++part) tc::bulk_g2s(Xhi + part * 2048, src + part * 2048, 8192u, full);
   };
-  for (int t = c.crank, it = 0; t < ntiles; t += c.csize, ++it) {      // this CTA's tiles (cluster per trial)
+  for (int t = c.crank; t < ntiles; t += c.csize) {      // this CTA's tiles (cluster per trial)
+    const int it = tile_iter(c, t);
     const int row0 = t * kTM, nv = min(kTM, B - row0);
     if (leader) {
       if (tc::elect_one()) load_chunk(t, 0);               // overlaps the du pass
@@ -2290,7 +2339,7 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
   }
   // ---- weight gradient from the TMEM accumulators: lane = input column of the chunk, column = output channel ----
   float* gradW = Xhi;                 // dense [64][K]
-  float* gb = Dhi;                    // [64] db | [64] dslope
+  float* gb = gradW + kH * K;         // [64] db | [64] dslope, right behind dW (K = 256: the first floats of the idle Xlo)
   tc::fence_after_sync();
   __syncthreads();
   sm->red[ty][c4 + 0] = db4[0]; sm->red[ty][c4 + 1] = db4[1]; sm->red[ty][c4 + 2] = db4[2]; sm->red[ty][c4 + 3] = db4[3];
@@ -2304,7 +2353,7 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
   {
     // warp w reads TMEM lanes 32 (w & 3) .. + 31 (input columns of the chunk) and output channels 32 (w >> 2) .. + 31
     const int n0 = 32 * (warp >> 2);
-    const bool any_tile = c.crank < ntiles;                // a CTA without rows contributes zeros
+    const bool any_tile = has_tiles(c, ntiles);            // a CTA without rows contributes zeros
     for (int ck = 0; ck < nch; ++ck) {
       float v[32];
       tc::tmem_ld32(d_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * ck + n0), v);
@@ -2323,9 +2372,7 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
   tc::fence_before_sync();
   __syncthreads();
   if (c.csize > 1) cl::sync();
-  adam_apply(c, sm, o, net, nl.w_off[l], kH * K, gradW);
-  adam_apply(c, sm, o, net, nl.b_off[l], kH, gb);
-  adam_apply(c, sm, o, net, nl.a_off[l], kH, gb + kH);
+  adam_apply(c, sm, o, net, nl.w_off[l], kH * K + 2 * kH, gradW);
   stage_sync(c);
 }
 
@@ -2457,15 +2504,14 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
     int oo = tid + kThreads * e, n = oo >> 6, k = oo & 63;
     if (n < ns) gradW[n * kH + k] = part[(0 * kZ + n) * kH + k] + part[(1 * kZ + n) * kH + k] + part[(2 * kZ + n) * kH + k] + part[(3 * kZ + n) * kH + k];
   }
-  if (tid < ns) gradW[kZ * kH + tid] = sm->red[8][tid] + sm->red[9][tid] + sm->red[10][tid] + sm->red[11][tid];
+  if (tid < ns) gradW[ns * kH + tid] = sm->red[8][tid] + sm->red[9][tid] + sm->red[10][tid] + sm->red[11][tid];   // [W | b] contiguous
   if (q == 0) {
     sg_dst[ch] = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
     sgx_dst[ch] = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
   }
   __syncthreads();
   if (c.csize > 1) { cl::sync(); cluster_gather_sg(c, sm); }
-  adam_apply(c, sm, o, kE, nl.w_off[l], ns * kH, gradW);
-  adam_apply(c, sm, o, kE, nl.b_off[l], ns, gradW + kZ * kH);
+  adam_apply(c, sm, o, kE, nl.w_off[l], ns * kH + ns, gradW);
   stage_sync(c);
 }
 

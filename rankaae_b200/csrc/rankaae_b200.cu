@@ -9,6 +9,10 @@
 
 #include "aae_kernels.cuh"
 
+// kernels_cluster.cu
+cudaError_t raae_cluster_setup(int ctas, int* max_clusters);
+cudaError_t raae_cluster_launch(int which, const void* kparams, const void* run_args, int n_trials, int ctas, void* stream);
+
 namespace {
 
 thread_local std::string g_err;
@@ -168,25 +172,16 @@ struct raae_handle {
 };
 
 namespace {
-// one thread-block cluster of cfg.ctas_per_trial CTAs per trial
-cudaError_t launch_trials(void (*kernel)(const raae::KParams, const raae::RunArgs), const raae_handle* h, int n_trials,
-                          const raae::RunArgs& a, void* stream) {
+// One CTA per trial: the kernels of this translation unit.  ctas_per_trial > 1: the cluster build of the same device code
+// (kernels_cluster.cu, namespace raae_cn), one thread-block cluster per trial.
+cudaError_t launch_trials(int which, const raae_handle* h, int n_trials, const raae::RunArgs& a, void* stream) {
   const int ctas = h->kp.cfg.ctas_per_trial;
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(n_trials * ctas), 1, 1);
-  cfg.blockDim = dim3(raae::kThreads, 1, 1);
-  cfg.dynamicSmemBytes = raae::kSmemBytes;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)ctas;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = ctas > 1 ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, h->kp, a);
+  if (ctas > 1) return raae_cluster_launch(which, &h->kp, &a, n_trials, ctas, stream);
+  if (which == 0) raae::raae_train_kernel<<<n_trials, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+  else raae::raae_val_kernel<<<n_trials, raae::kThreads, raae::kSmemBytes, (cudaStream_t)stream>>>(h->kp, a);
+  return cudaGetLastError();
 }
+constexpr int kTrainKernel = 0, kValKernel = 1;
 
 constexpr size_t kPeerHeaderBytes = 256;        // words [0, 8): flags, word 16: finished-block counter, word 17: pre-reduction arrivals
 int peer_release(raae_handle* h) {
@@ -240,20 +235,8 @@ int raae_create(const raae_config* cfg, int device, raae_handle** out) {
   RAAE_CUDA(cudaFuncSetAttribute(raae::raae_val_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raae::kSmemBytes));
   if (cfg->ctas_per_trial > 1) {
     // a cluster needs ctas_per_trial SMs of one GPC with the kernel's whole shared-memory footprint free at the same time
-    cudaLaunchConfig_t lc;
-    std::memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3((unsigned)cfg->ctas_per_trial, 1, 1);
-    lc.blockDim = dim3(raae::kThreads, 1, 1);
-    lc.dynamicSmemBytes = raae::kSmemBytes;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cfg->ctas_per_trial;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    lc.attrs = attr;
-    lc.numAttrs = 1;
     int nclusters = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, raae::raae_train_kernel, &lc);
+    cudaError_t e = raae_cluster_setup(cfg->ctas_per_trial, &nclusters);
     if (e != cudaSuccess || nclusters < 1) {
       delete h;
       return fail(-2, std::string("ctas_per_trial = ") + std::to_string(cfg->ctas_per_trial) + " cannot be scheduled on this device" +
@@ -328,7 +311,7 @@ int raae_step_debug(raae_handle* h, int trial, const raae_debug_io* io, void* st
   a.debug = 1;
   a.epoch = io->epoch;
   a.dbg = *io;
-  RAAE_CUDA(launch_trials(raae::raae_train_kernel, h, 1, a, stream));
+  RAAE_CUDA(launch_trials(kTrainKernel, h, 1, a, stream));
   RAAE_CUDA(cudaGetLastError());
   h->launches++;
   return 0;
@@ -347,7 +330,7 @@ int raae_validate(raae_handle* h, int trial, const raae_val_io* io, void* stream
   a.debug = 1;
   a.epoch = io->epoch;
   a.val = *io;
-  RAAE_CUDA(launch_trials(raae::raae_val_kernel, h, 1, a, stream));
+  RAAE_CUDA(launch_trials(kValKernel, h, 1, a, stream));
   RAAE_CUDA(cudaGetLastError());
   h->launches++;
   return 0;
@@ -376,11 +359,11 @@ int raae_train_epochs(raae_handle* h, int epoch_begin, int n_epochs, const int32
     a.out_metrics = out_metrics ? out_metrics + (size_t)e * nt * 6 : nullptr;
     a.val.avg_mutual_info = -INFINITY;
     a.prof = h->prof;
-    RAAE_CUDA(launch_trials(raae::raae_train_kernel, h, nt, a, stream));
+    RAAE_CUDA(launch_trials(kTrainKernel, h, nt, a, stream));
     RAAE_CUDA(cudaGetLastError());
     h->launches++;
     if (h->kp.n_val >= 3) {
-      RAAE_CUDA(launch_trials(raae::raae_val_kernel, h, nt, a, stream));
+      RAAE_CUDA(launch_trials(kValKernel, h, nt, a, stream));
       RAAE_CUDA(cudaGetLastError());
       h->launches++;
     }
@@ -407,7 +390,7 @@ int raae_train_phase(raae_handle* h, int epoch, int step, int phase_mask, const 
   a.phase_mask = phase_mask;
   for (int o = 0; o < RAAE_NUM_PHASES; ++o) a.grads_out[o] = grads[o];
   a.val.avg_mutual_info = -INFINITY;
-  RAAE_CUDA(launch_trials(raae::raae_train_kernel, h, nt, a, stream));
+  RAAE_CUDA(launch_trials(kTrainKernel, h, nt, a, stream));
   RAAE_CUDA(cudaGetLastError());
   h->launches++;
   return 0;
@@ -439,7 +422,7 @@ int raae_validate_epoch(raae_handle* h, int epoch, float* out_losses, float* out
   a.out_losses = out_losses;
   a.out_metrics = out_metrics;
   a.val.avg_mutual_info = -INFINITY;
-  RAAE_CUDA(launch_trials(raae::raae_val_kernel, h, h->kp.cfg.n_trials, a, stream));
+  RAAE_CUDA(launch_trials(kValKernel, h, h->kp.cfg.n_trials, a, stream));
   RAAE_CUDA(cudaGetLastError());
   h->launches++;
   return 0;

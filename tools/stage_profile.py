@@ -51,3 +51,5 @@ for i, n in [(23, "dis: input rows + noise"), (24, "dis: layer 0"), (25, "dis: l
     calls_tiles = (16 if (22 <= i < 27 or i in (16, 17)) else 21 * 8)
     print(f"    probe {n:50s} {v/1e3:10.1f} kcyc  per item/tile {v/calls_tiles:8.0f} cyc")
 print(f"  {'(unaccounted)':22s} {(tot - p[:, :15].sum(1).mean())/1e3:10.1f} kcyc")
+if os.environ.get("RAAE_RAW_PROBES"):
+    print("raw probe slots 16..31 (kcyc per step):", " ".join(f"{i}:{p[:, i].mean()/1e3:.1f}" for i in range(16, 32)))
