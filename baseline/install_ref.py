@@ -5,7 +5,7 @@ Recipe (recorded in DESIGN.md §8): `pip install --no-index --no-build-isolation
 --target baseline/_ref <copy of /root/reference under /tmp>` (the source tree is read-only and dependency resolution
 fails offline: torch_optimizer, ipyparallel, seaborn ... are not in the wheelhouse).  The reference's setup.py lists
 `packages=['sc']` only, so pip installs `sc/__init__.py` without the sub-packages; the install is completed by copying the
-reference's own `sc/{clustering,utils,cmd}` modules and `example/fix_config.yaml` next to it, byte for byte.  Nothing of it
+reference's own `sc/{clustering,utils,cmd,report}` modules and `example/fix_config.yaml` next to it, byte for byte.  Nothing of it
 is tracked by git and nothing in the product imports it.
 """
 import os
@@ -18,7 +18,7 @@ REF = os.environ.get("RANKAAE_REFERENCE", "/root/reference")
 DST = os.path.join(HERE, "_ref")
 NEEDED = ["sc/__init__.py", "sc/clustering/__init__.py", "sc/clustering/trainer.py", "sc/clustering/model.py",
           "sc/clustering/dataloader.py", "sc/utils/__init__.py", "sc/utils/functions.py", "sc/utils/parameter.py",
-          "sc/utils/logger.py", "example/fix_config.yaml"]
+          "sc/utils/logger.py", "sc/report/analysis.py", "example/fix_config.yaml"]
 
 
 def installed():
@@ -35,7 +35,7 @@ def install(force=False):
     shutil.copytree(REF, tmp)
     subprocess.run([sys.executable, "-m", "pip", "install", "-q", "--no-index", "--no-build-isolation", "--no-deps",
                     "--find-links", "/opt/wheelhouse", "--upgrade", "--target", DST, tmp], check=False)
-    for sub in ("clustering", "utils", "cmd"):
+    for sub in ("clustering", "utils", "cmd", "report"):
         src = os.path.join(REF, "sc", sub)
         dst = os.path.join(DST, "sc", sub)
         os.makedirs(dst, exist_ok=True)

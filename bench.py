@@ -45,11 +45,50 @@ UNIT = "samples/s"
 
 
 def synthetic_arrays():
-    """Seeded synthetic spectra in the reference CSV's schema/value range (oracle.synthetic_dataset is the
-    generator used by every test as well; it is data generation, not the path being measured)."""
-    from oracle.aae_oracle import Config, synthetic_dataset
-    spec, aux = synthetic_dataset(N_ROWS, Config.from_dict(EXAMPLE), seed=0, dtype=np.float32)
+    """Seeded synthetic spectra in the reference CSV's schema / value range (rankaae_b200/synthetic.py; data generation,
+    not the path being measured)."""
+    from rankaae_b200.synthetic import synthetic_dataset
+    spec, aux = synthetic_dataset(N_ROWS, EXAMPLE["n_aux"], EXAMPLE["dim_in"], seed=0, dtype=np.float32)
     return (spec[:N_TRAIN], aux[:N_TRAIN], spec[N_TRAIN:N_TRAIN + N_VAL], aux[N_TRAIN:N_TRAIN + N_VAL])
+
+
+# keys the reference's Trainer reads beyond EXAMPLE (trainer.py:333-408; never stepped in the gradient-reversal branch)
+REFERENCE_ONLY_KEYS = dict(gen_beta=1.1, lr_ratio_gen=10, data_file="synthetic.csv", trials=1, timeout=10, verbose=False)
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+
+
+def reference_csv():
+    """The bench dataset in the reference's CSV schema (sc/clustering/dataloader.py:12-25), written once per run."""
+    import tempfile
+    from rankaae_b200.synthetic import synthetic_dataset, write_csv
+    spec, aux = synthetic_dataset(N_ROWS, EXAMPLE["n_aux"], EXAMPLE["dim_in"], seed=0, dtype=np.float32)
+    path = os.path.join(tempfile.mkdtemp(prefix="raae_bench_"), "synthetic.csv")
+    write_csv(path, spec, aux)
+    return path
+
+
+def reference_epochs(csv, n_procs, n_epochs, threads=1, anomaly=True, timeout=3000):
+    """Per-process epoch wall times [n_procs][n_epochs] of the UNMODIFIED reference trainer (baseline/ref_runner.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_runner
+    res = ref_runner.run(csv, dict(EXAMPLE, **REFERENCE_ONLY_KEYS), n_procs, n_epochs, threads=threads, anomaly=anomaly,
+                         timeout=timeout)
+    return np.array([r["epoch_s"] for r in res])
+
+
+def reference_installed():
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_runner
+    return ref_runner.available()
+
+
+def throughput(epoch_s, warm):
+    """Aggregate samples/s of concurrent independent trials: the sum of the processes' own steady-state rates."""
+    t = epoch_s[:, warm:]
+    return float(np.sum(t.shape[1] * N_TRAIN / t.sum(axis=1))), float(np.mean(t) * 1e3)
 
 
 class ClockSampler(threading.Thread):
@@ -143,27 +182,69 @@ def cpu_epochs(n_proc, n_epochs):
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores - the unmodified
+    `Trainer.from_data(...).train()` from baseline/_ref, one single-thread trial per core (sc/cmd/run_training.sh:3-9), as
+    shipped (autograd anomaly mode on, trainer.py:11).  One step = one epoch of every trial, like the GPU arm.  Falls back
+    to the numpy oracle port only if baseline/_ref is missing."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    cores = host_cores()
     n_epochs = args.warmup + args.steps
-    t = cpu_epochs(cores, n_epochs)[args.warmup:]
-    ms = float(np.mean(t) * 1e3)
-    value = cores * N_TRAIN / float(np.mean(t))
+    if reference_installed():
+        t = reference_epochs(reference_csv(), cores, n_epochs, threads=1, anomaly=True)
+        value, ms = throughput(t, args.warmup)
+        kind = "reference"
+        sample = (f"{args.steps} epochs (after {args.warmup} warm-up) x {cores} concurrent single-thread trials of the unmodified "
+                  "reference Trainer.train() (baseline/_ref, CPU, anomaly mode on as shipped), same dataset and config")
+        dtype = "f32"
+    else:
+        t = cpu_epochs(cores, n_epochs)[None, :]
+        value, ms = cores * N_TRAIN / float(np.mean(t[:, args.warmup:])), float(np.mean(t[:, args.warmup:]) * 1e3)
+        kind = "port"
+        sample = f"{args.steps} epochs x {cores} single-thread trials of the numpy oracle port (baseline/_ref not installed)"
+        dtype = "f64"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": dtype, "data": "synthetic",
         "config": {"workload": f"example fix_config ensemble, synthetic 7000x256 (4900 train/1050 val), batch 1024, "
-                               f"{cores} trials (one per host core), 1 step = 1 epoch of every trial incl. validation"},
-        "trials_per_hour_2000_epochs": cores * 3600.0 / (np.mean(t) * 2000.0),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} epochs x {cores} single-thread trials of the numpy oracle port "
-                                   "(the reference is Python/PyTorch and cannot travel to the GPU box)"},
+                               f"{cores} trials (one per host core), 1 step = 1 epoch of every trial incl. validation + metrics"},
+        "trials_per_hour_2000_epochs": value / N_TRAIN * 3600.0 / 2000.0,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def cpu_baseline_leg():
+    """cpu_baseline of the GPU arm (rank 0, N = 1): bounded samples of the unmodified reference on the host cores -
+    (i) one single-thread trial per core, anomaly mode on (as shipped) and off; (ii) all cores on one trial; beside them the
+    numpy oracle port as a second figure."""
+    cores = host_cores()
+    out = {"unit": UNIT, "cores": cores}
+    if reference_installed():
+        csv = reference_csv()
+        t_on = reference_epochs(csv, cores, 3, threads=1, anomaly=True)
+        v_on, ms_on = throughput(t_on, 1)
+        out.update(value=v_on, kind="reference", ms_per_epoch=ms_on,
+                   sample=f"2 timed epochs (after 1 warm-up) x {cores} concurrent single-thread trials of the unmodified reference "
+                          "Trainer.train() (baseline/_ref, CPU, autograd anomaly mode on as shipped), same dataset and config")
+        t_off = reference_epochs(csv, cores, 3, threads=1, anomaly=False)
+        out["anomaly_off"] = {"value": throughput(t_off, 1)[0], "ms_per_epoch": throughput(t_off, 1)[1]}
+        try:
+            t_all = reference_epochs(csv, 1, 2, threads=cores, anomaly=True, timeout=150)
+            out["all_cores_one_trial"] = {"value": throughput(t_all, 1)[0], "threads": cores, "ms_per_epoch": throughput(t_all, 1)[1]}
+        except Exception as e:                        # oversubscribed MKL can take minutes per epoch (SURVEY.md §6)
+            out["all_cores_one_trial"] = {"value": None, "note": f"not finished within 150 s ({type(e).__name__})"}
+    t = cpu_epochs(cores, 3)[1:]
+    port = {"value": cores * N_TRAIN / float(np.mean(t)), "kind": "port",
+            "sample": f"2 timed epochs x {cores} single-thread trials of the numpy float64 oracle port of trainer.py:89-307"}
+    if "value" in out:
+        out["port"] = port
+    else:
+        out.update(port)
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -305,29 +386,34 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "finite": finite,
     }
-    if rank == 0 and world == 1 and not args.no_single:
-        # BASELINE.json configs[1]: the same example config with ONE trial resident (one CTA on one SM): what a single
-        # `Trainer.train()` call costs per epoch; reported beside the ensemble number, not as the headline
-        eng1 = Engine(EXAMPLE, n_trials=1, device=dev, max_rows=1056, seeds=[12345])
-        init_trial_state(eng1, 0, EXAMPLE, seed=12345)
-        eng1.bind_dataset(*dset)
-        eng1.train_epochs(0, W)
-        torch.cuda.synchronize(dev)
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        eng1.train_epochs(W, K)
-        s1.record()
-        torch.cuda.synchronize(dev)
-        ms1 = s0.elapsed_time(s1) / K
-        line["single_trial"] = {"workload": "BASELINE configs[1]: example config, trials=1 (1 of 148 SMs busy)", "ms_per_epoch": ms1,
-                                "samples_per_sec": N_TRAIN / (ms1 * 1e-3), "hours_per_2000_epochs": ms1 * 2000.0 / 3.6e6}
-        eng1.close()
+    eng.close()
+    # ---- the other BASELINE.json configurations, as sub-records (tools/bench_configs.py) ----
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs as BC
+    configs = {}
+    if not args.no_configs:
+        if world == 1 and not args.no_single:
+            # configs[1]: one trial resident, as a cluster of 8 CTAs (and as one CTA)
+            rec = BC.single_trial(EXAMPLE, dset, dev, W, K, N_TRAIN)
+            if rank == 0:
+                line["single_trial"] = rec
+        if world == 1 and not args.no_single:
+            # the reference-facing calls, CSV on disk -> final.pt on disk, by wall clock
+            configs["reference_api"] = BC.reference_api(EXAMPLE, N_ROWS, local, epochs=40)
+        # configs[2] as written: 64 trials partitioned over the GPUs of this run (strong scaling)
+        configs["strong_64"] = BC.strong_64(EXAMPLE, dset, dev, rank, world, W, K, N_TRAIN)
+        # configs[3]: one trial data-parallel over the GPUs of this run on the 1 M-row set
+        try:
+            configs["dp_single_trial"] = BC.dp_single_trial(dev, rank, world, steps=max(10, 2 * K))
+        except Exception as e:                   # e.g. no P2P between the GPUs of this box: reported, not fatal for the headline
+            configs["dp_single_trial"] = {"error": f"{type(e).__name__}: {e}"}
+        # configs[4]: the 1024-trial sweep (8 GPUs; smaller runs scale the trial count to 128 per GPU)
+        if world == 8 or args.sweep:
+            configs["sweep_1024"] = BC.sweep_1024(dev, rank, world, trials=128 * world, epochs=2)
+    if rank == 0:
+        line["configs"] = configs
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-        t = cpu_epochs(cores, 3)[1:]
-        line["cpu_baseline"] = {"value": cores * N_TRAIN / float(np.mean(t)), "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"2 timed epochs (after 1 warm-up) x {cores} single-thread trials of the numpy "
-                                          "float64 oracle port of trainer.py:89-307, same dataset and config"}
+        line["cpu_baseline"] = cpu_baseline_leg()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -343,6 +429,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-single", action="store_true", help="skip the single-trial (configs[1]) leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the strong_64 / dp_single_trial / sweep sub-records")
+    ap.add_argument("--sweep", action="store_true", help="run the sweep sub-record (128 trials per GPU) also below 8 GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

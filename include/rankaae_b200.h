@@ -143,6 +143,9 @@ typedef struct raae_val_io {
   float* losses;                          /* [5] phase order: val adversarial, Kendall, recon, MI, smooth */
   float* metrics;                         /* [6]: min Shapiro W, recon, avg MI, max |Spearman|, Kendall, combined */
   float* z;                               /* [n_val][nstyle] or NULL                                  */
+  float* row_mae;                         /* [n_val] or NULL: mean |D(E(x)) - x| of every row (sc/report/analysis.py:425-428) */
+  int32_t per_trial;                      /* 1: losses / metrics / z / row_mae hold one block per resident trial (raae_evaluate_trials) */
+  int32_t reserved;
 } raae_val_io;
 
 typedef struct raae_handle raae_handle;
@@ -205,6 +208,17 @@ int raae_train_phase(raae_handle* h, int epoch, int step, int phase_mask, const 
 int raae_apply_adam(raae_handle* h, int phase, const float* grads, void* stream);
 int raae_validate_epoch(raae_handle* h, int epoch, float* out_losses, float* out_metrics, void* stream);
 
+/* Parity hook of the in-kernel ReduceLROnPlateau (trainer.py:303-304, 400-408): steps the schedulers of `trial` with the
+ * scripted sequence metrics[0..n) (float64, device) and records (lr, best, num_bad_epochs) of the five optimizers after
+ * every step in out [n][5][3] (float32, device).  The trial's scheduler state advances as in training. */
+int raae_debug_plateau(raae_handle* h, int trial, const double* metrics, int n, float* out, void* stream);
+
+/* Batched, side-effect-free evaluation of EVERY resident trial on the bound validation rows (bind the test split with
+ * raae_bind_dataset to rank trials the way sc/report/analysis.py:394-450 `evaluate_model` does): eval-mode forward of the
+ * encoder and decoder, the five validation losses and the metric vector - no scheduler step, no state change.
+ * z [n_trials][n_val][nstyle], row_mae [n_trials][n_val], losses [n_trials][5], metrics [n_trials][6]; any may be NULL. */
+int raae_evaluate_trials(raae_handle* h, int epoch, float* z, float* row_mae, float* losses, float* metrics, void* stream);
+
 /* Peer-memory gradient exchange for the data-parallel mode ("one-shot ... fused into the phase epilogue"):
  * replaces `all_reduce(grads) ; grads /= world ; raae_apply_adam` by ONE launch that signals the peers, waits for their
  * gradient vectors, sums them in rank order straight out of the peers' HBM over NVLink (P2P loads, no NCCL call, no
@@ -229,6 +243,10 @@ int raae_peer_alloc(raae_handle* h, int world, int rank, unsigned char* ipc_hand
 int raae_peer_connect(raae_handle* h, const unsigned char* all_handles);
 int raae_peer_grad_ptr(raae_handle* h, int phase, float** out);
 int raae_apply_adam_peer(raae_handle* h, int phase, void* stream);
+/* 0 in *failed_seq: every exchange so far met all its peers; otherwise the call number of the last exchange that gave up
+ * waiting (RAAE_PEER_TIMEOUT_S seconds, default 120) and skipped its update - the job is then inconsistent and must stop.
+ * Synchronises the device. */
+int raae_peer_status(raae_handle* h, unsigned* failed_seq);
 int raae_peer_free(raae_handle* h);
 
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */

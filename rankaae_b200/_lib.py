@@ -61,14 +61,16 @@ class DebugIO(C.Structure):
 
 class ValIO(C.Structure):
     _fields_ = [("z_sample", _p), ("z_real", _p), ("epoch", _i32), ("avg_mutual_info", C.c_float),
-                ("losses", _p), ("metrics", _p), ("z", _p)]
+                ("losses", _p), ("metrics", _p), ("z", _p), ("row_mae", _p), ("per_trial", _i32), ("reserved", _i32)]
 
 
 EXPORTS = ("raae_last_error", "raae_version", "raae_query_layout", "raae_create", "raae_destroy", "raae_bind_state",
            "raae_bind_dataset", "raae_bind_shapiro_weights", "raae_reset_optimizers", "raae_step_debug",
            "raae_validate", "raae_train_epochs", "raae_launch_count", "raae_set_profile_buffer",
-           "raae_train_phase", "raae_apply_adam", "raae_validate_epoch",
-           "raae_peer_alloc", "raae_peer_connect", "raae_peer_grad_ptr", "raae_apply_adam_peer", "raae_peer_free")
+           "raae_train_phase", "raae_apply_adam", "raae_validate_epoch", "raae_evaluate_trials",
+           "raae_debug_plateau",
+           "raae_peer_alloc", "raae_peer_connect", "raae_peer_grad_ptr", "raae_apply_adam_peer", "raae_peer_status",
+           "raae_peer_free")
 MAX_PEERS = 8
 IPC_HANDLE_BYTES = 64
 
@@ -106,10 +108,13 @@ def load():
     lib.raae_train_phase.argtypes = [_p, C.c_int, C.c_int, C.c_int, _p, C.POINTER(_p), _p]
     lib.raae_apply_adam.argtypes = [_p, C.c_int, _p, _p]
     lib.raae_validate_epoch.argtypes = [_p, C.c_int, _p, _p, _p]
+    lib.raae_evaluate_trials.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p]
+    lib.raae_debug_plateau.argtypes = [_p, C.c_int, _p, C.c_int, _p, _p]
     lib.raae_peer_alloc.argtypes = [_p, C.c_int, C.c_int, C.c_char_p]
     lib.raae_peer_connect.argtypes = [_p, C.c_char_p]
     lib.raae_peer_grad_ptr.argtypes = [_p, C.c_int, C.POINTER(_p)]
     lib.raae_apply_adam_peer.argtypes = [_p, C.c_int, _p]
+    lib.raae_peer_status.argtypes = [_p, C.POINTER(C.c_uint)]
     lib.raae_peer_free.argtypes = [_p]
     _lib = lib
     return lib

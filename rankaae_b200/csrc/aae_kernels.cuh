@@ -487,7 +487,13 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
   c.x = p.spec_val;
   c.xld = p.cfg.dim_in;
   c.step_id = 0x40000000u + (uint32_t)a.epoch;
-  const raae_val_io& io = a.val;
+  raae_val_io io = a.val;
+  if (io.per_trial) {                    // raae_evaluate_trials: one output block per trial
+    const size_t tb = (size_t)(trial - a.trial0);
+    if (io.losses) io.losses += tb * RAAE_NUM_PHASES;
+    if (io.metrics) io.metrics += tb * 6;
+    if (io.z) io.z += tb * (size_t)p.n_val * ns;
+  }
   tc_setup(p, sm);
   if (tid == 0) {
     sm->alpha = alpha_schedule(c);
@@ -624,6 +630,8 @@ struct PeerArgs {
   int world, rank;
   int replicas;                          // trials resident per rank (identical weights, one shard each)
   unsigned seq;
+  unsigned long long timeout_ns;         // how long a rank waits for its peers before it gives up (RAAE_PEER_TIMEOUT_S)
+  unsigned* error;                       // local: set to `seq` when a peer did not arrive in time (the update is skipped)
 };
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -673,15 +681,24 @@ __global__ void raae_adam_peer_kernel(const __grid_constant__ KParams p, int o, 
       st_release_sys(pa.flags[threadIdx.x] + pa.rank, pa.seq);
     }
   }
+  __shared__ int s_late;
+  if (threadIdx.x == 0) s_late = 0;
+  __syncthreads();
   if (threadIdx.x < pa.world) {
     const unsigned* f = pa.flags[pa.rank] + threadIdx.x;
     const unsigned long long t0 = global_ns();
     while ((int)(ld_acquire_sys(f) - pa.seq) < 0) {
       __nanosleep(64);
-      if (global_ns() - t0 > 10000000000ull) __trap();      // a peer never arrived: fail the launch instead of hanging
+      // a peer never arrived: give up WITHOUT trapping (a trap poisons the CUDA context of the whole job); the update of this
+      // exchange is skipped everywhere the wait failed and the error word tells the host (raae_peer_status)
+      if (global_ns() - t0 > pa.timeout_ns) { s_late = 1; break; }
     }
   }
   __syncthreads();
+  if (s_late) {
+    if (threadIdx.x == 0) { *pa.error = pa.seq; __threadfence_system(); }
+    return;
+  }
   // `replicas` = the trials resident on every rank: they hold the SAME weights and act as further data-parallel ranks
   // (one CTA each in raae_train_phase), so the mean runs over world x replicas vectors - the ranks' pre-reduced sums added in
   // rank order - and the one update is applied to every local replica's state
@@ -740,6 +757,25 @@ __global__ void raae_adam_peer_kernel(const __grid_constant__ KParams p, int o, 
 __global__ void raae_adam_tick_kernel(const __grid_constant__ KParams p, int o, int n_trials) {
   int trial = blockIdx.x * blockDim.x + threadIdx.x;
   if (trial < n_trials) p.state[(size_t)trial * p.lay.state_floats + p.lay.opt[o].scalar_off + 1] += 1.f;
+}
+
+// parity hook of the scheduler: feeds metrics[0..n) to plateau_step of `trial` and records (lr, best, num_bad) of every
+// optimizer after each step (out [n][RAAE_NUM_PHASES][3]); single thread
+__global__ void raae_plateau_debug_kernel(const __grid_constant__ KParams p, int trial, const double* __restrict__ metrics, int n,
+                                          float* __restrict__ out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Ctx c;
+  c.p = &p;
+  c.st = p.state + (size_t)trial * p.lay.state_floats;
+  c.hp = p.hp + (size_t)trial * RAAE_HP_COUNT;
+  for (int e = 0; e < n; ++e) {
+    plateau_step(c, metrics[e]);
+    for (int o = 0; o < RAAE_NUM_PHASES; ++o) {
+      const float* s = c.st + p.lay.opt[o].scalar_off;
+      float* d = out + ((size_t)e * RAAE_NUM_PHASES + o) * 3;
+      d[0] = s[0]; d[1] = s[2]; d[2] = s[3];
+    }
+  }
 }
 
 // lr <- hp, t <- 0, best <- +inf, bad <- 0; misc zeroed

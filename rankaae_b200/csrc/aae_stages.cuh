@@ -83,6 +83,8 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
     for (int j = 0; j < 8; ++j) { acc += kGauss17[j]; tapP[j] = acc; }
   }
   const int ntiles = (c.B + kTM - 1) / kTM;
+  float* const row_mae = (mode == kLastEval && c.a->val.row_mae)
+                             ? c.a->val.row_mae + (c.a->val.per_trial ? (size_t)(c.trial - c.a->trial0) * c.p->n_val : 0) : nullptr;
   float* const sg_dst = c.csize > 1 ? sm->sgp : sm->sg;         // cluster per trial: partial sums, gathered after the barrier
   float* const sgx_dst = c.csize > 1 ? sm->sgxp : sm->sgx;
   for (int t = c.crank; t < ntiles; t += c.csize) {      // this CTA's tiles; `it` counts them
@@ -292,6 +294,16 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
               }
             }
             loss_a += (double)sq * inv_BN;
+            if ((MODE == kLastEval) && row_mae != nullptr) {
+              // mean absolute error of the row (report tooling: sc/report/analysis.py:425-428)
+              float sa = 0.f;
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (FULL || col0 + e < N) sa += fabsf(y[e] - x[e]);
+#pragma unroll
+              for (int of = 16; of > 0; of >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, of);
+              if (lane == 0) row_mae[row0 + r] = sa / nN;
+            }
           }
           if ((MODE == kLastSmooth) || (MODE == kLastEval)) {
             // replicate-padded copy of the row

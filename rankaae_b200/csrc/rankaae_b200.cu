@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -164,6 +165,8 @@ struct raae_handle {
     int world, rank;
     bool connected;
     unsigned seq;
+    int last_phase;                             // phase of the previous exchange (-1: none)
+    bool rewritten[RAAE_NUM_PHASES];            // raae_train_phase wrote the phase's vector since its last exchange
     int max_blocks;                             // co-resident blocks of the exchange kernel on this device (0 = not queried yet)
     size_t bytes, grad_off[RAAE_NUM_PHASES], sum_off[RAAE_NUM_PHASES];   // sum_off == grad_off when n_trials == 1
     unsigned char* local;                       // cudaMalloc: [256 B flags + done counter][gradient vector per phase]
@@ -183,7 +186,7 @@ cudaError_t launch_trials(int which, const raae_handle* h, int n_trials, const r
 }
 constexpr int kTrainKernel = 0, kValKernel = 1;
 
-constexpr size_t kPeerHeaderBytes = 256;        // words [0, 8): flags, word 16: finished-block counter, word 17: pre-reduction arrivals
+constexpr size_t kPeerHeaderBytes = 256;        // words [0, 8): flags, word 16: finished-block counter, word 17: pre-reduction arrivals, word 18: error
 int peer_release(raae_handle* h) {
   if (!h->peer.local) return 0;
   cudaSetDevice(h->device);
@@ -388,7 +391,10 @@ int raae_train_phase(raae_handle* h, int epoch, int step, int phase_mask, const 
   a.split = 1;
   a.step0 = step;
   a.phase_mask = phase_mask;
-  for (int o = 0; o < RAAE_NUM_PHASES; ++o) a.grads_out[o] = grads[o];
+  for (int o = 0; o < RAAE_NUM_PHASES; ++o) {
+    a.grads_out[o] = grads[o];
+    if (h->peer.local && grads[o] && (phase_mask & (1 << o))) h->peer.rewritten[o] = true;
+  }
   a.val.avg_mutual_info = -INFINITY;
   RAAE_CUDA(launch_trials(kTrainKernel, h, nt, a, stream));
   RAAE_CUDA(cudaGetLastError());
@@ -428,6 +434,38 @@ int raae_validate_epoch(raae_handle* h, int epoch, float* out_losses, float* out
   return 0;
 }
 
+int raae_debug_plateau(raae_handle* h, int trial, const double* metrics, int n, float* out, void* stream) {
+  if (!h || !metrics || !out) return fail(-1, "null argument");
+  if (!h->bound_state) return fail(-1, "state not bound");
+  if (trial < 0 || trial >= h->kp.cfg.n_trials || n < 0) return fail(-1, "trial / n out of range");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  raae::raae_plateau_debug_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->kp, trial, metrics, n, out);
+  RAAE_CUDA(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int raae_evaluate_trials(raae_handle* h, int epoch, float* z, float* row_mae, float* losses, float* metrics, void* stream) {
+  if (!h) return fail(-1, "null handle");
+  if (!h->bound_state || !h->bound_data) return fail(-1, "state / dataset not bound");
+  if (h->kp.n_val < 3 || h->shapiro_n != h->kp.n_val) return fail(-1, "validation split / Shapiro-Wilk weights not bound");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  raae::RunArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.epoch = epoch;
+  a.debug = 1;                                   // no scheduler step, no losses.csv row
+  a.val.epoch = epoch;
+  a.val.avg_mutual_info = -INFINITY;
+  a.val.z = z;
+  a.val.row_mae = row_mae;
+  a.val.losses = losses;
+  a.val.metrics = metrics;
+  a.val.per_trial = 1;
+  RAAE_CUDA(launch_trials(kValKernel, h, h->kp.cfg.n_trials, a, stream));
+  h->launches++;
+  return 0;
+}
+
 int raae_peer_alloc(raae_handle* h, int world, int rank, unsigned char* ipc_handle_out) {
   if (!h || !ipc_handle_out) return fail(-1, "null argument");
   if (world < 1 || world > RAAE_MAX_PEERS || rank < 0 || rank >= world) return fail(-1, "world must be in [1, 8] and rank in [0, world)");
@@ -457,6 +495,7 @@ int raae_peer_alloc(raae_handle* h, int world, int rank, unsigned char* ipc_hand
   h->peer.local = (unsigned char*)ptr;
   h->peer.mapped[rank] = h->peer.local;
   h->peer.seq = 0;
+  h->peer.last_phase = -1;
   h->peer.connected = false;
   return 0;
 }
@@ -494,6 +533,14 @@ int raae_apply_adam_peer(raae_handle* h, int phase, void* stream) {
   if (phase < 0 || phase >= RAAE_NUM_PHASES) return fail(-1, "phase out of range");
   if (!h->bound_state) return fail(-1, "state not bound");
   if (!h->peer.connected) return fail(-1, "peer exchange not connected (raae_peer_alloc / raae_peer_connect)");
+  // Buffer reuse: a rank may still be reading this rank's vector of exchange k when this rank has already left it.  The
+  // vector is safe because it is only rewritten by the NEXT raae_train_phase of the same phase, and every rank enters an
+  // exchange only after its previous one (the reader) has finished - which needs at least one OTHER exchange in between.
+  if (h->peer.world > 1 && h->peer.last_phase == phase && h->peer.rewritten[phase])
+    return fail(-1, "raae_apply_adam_peer: the same phase twice in a row with a rewritten gradient vector - a peer may still "
+                    "read the previous one; interleave at least two phases (the trainer cycles through five)");
+  h->peer.last_phase = phase;
+  h->peer.rewritten[phase] = false;
   RAAE_CUDA(cudaSetDevice(h->device));
   raae::PeerArgs pa;
   std::memset(&pa, 0, sizeof(pa));
@@ -505,6 +552,13 @@ int raae_apply_adam_peer(raae_handle* h, int phase, void* stream) {
   pa.lsum = (float*)(h->peer.local + h->peer.sum_off[phase]);
   pa.done = (unsigned*)h->peer.local + 16;
   pa.arrive = (unsigned*)h->peer.local + 17;
+  pa.error = (unsigned*)h->peer.local + 18;
+  {
+    const char* ts = std::getenv("RAAE_PEER_TIMEOUT_S");
+    double sec = ts ? std::atof(ts) : 120.0;
+    if (!(sec > 0.0)) sec = 120.0;
+    pa.timeout_ns = (unsigned long long)(sec * 1e9);
+  }
   pa.world = h->peer.world;
   pa.rank = h->peer.rank;
   pa.replicas = h->kp.cfg.n_trials;
@@ -519,9 +573,23 @@ int raae_apply_adam_peer(raae_handle* h, int phase, void* stream) {
   }
   int bx = (h->kp.lay.opt[phase].n + 255) / 256;
   if (bx > h->peer.max_blocks) bx = h->peer.max_blocks;
-  raae::raae_adam_peer_kernel<<<bx, 256, 0, (cudaStream_t)stream>>>(h->kp, phase, pa);
+  // cooperative launch: the grid starts only when ALL its blocks can be resident at once (block 0 waits for the others'
+  // slices and every block waits on the peers' flags), whatever else shares the GPU
+  {
+    void* kargs[3] = {(void*)&h->kp, (void*)&phase, (void*)&pa};
+    RAAE_CUDA(cudaLaunchCooperativeKernel((const void*)raae::raae_adam_peer_kernel, dim3((unsigned)bx), dim3(256), kargs, 0,
+                                          (cudaStream_t)stream));
+  }
   RAAE_CUDA(cudaGetLastError());
   h->launches++;
+  return 0;
+}
+
+int raae_peer_status(raae_handle* h, unsigned* failed_seq) {
+  if (!h || !failed_seq) return fail(-1, "null argument");
+  if (!h->peer.local) return fail(-1, "raae_peer_alloc has not been called");
+  RAAE_CUDA(cudaSetDevice(h->device));
+  RAAE_CUDA(cudaMemcpy(failed_seq, (unsigned*)h->peer.local + 18, sizeof(unsigned), cudaMemcpyDeviceToHost));
   return 0;
 }
 

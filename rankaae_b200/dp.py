@@ -46,7 +46,9 @@ class DataParallelTrainer:
     replicas = 1 is BASELINE.json configs[3] as written (one 512-row batch per GPU, one SM busy per GPU)."""
 
     def __init__(self, cfg, spec_train, aux_train, spec_val, aux_val, device, rank=0, world=1, seed=0, exchange=None,
-                 replicas=1, shard_seeds=None):
+                 replicas=1, shard_seeds=None, presharded=False):
+        """`presharded`: spec_train / aux_train are already THIS rank's rows (e.g. generated or loaded per rank); otherwise
+        they are the whole training split and the rank takes its contiguous share (shard_layout)."""
         self.rank, self.world, self.replicas = rank, world, int(replicas)
         V = self.replicas
         if exchange is None:
@@ -58,7 +60,10 @@ class DataParallelTrainer:
         self.exchange = exchange
         self.cfg = dict(cfg)
         self.cfg.setdefault("epoch_stop_smooth", 500)
-        self.per, lo, hi = shard_layout(len(spec_train), world, rank, V)     # rows of one shard; shard q = rank * V + replica
+        if presharded:
+            self.per, lo, hi = len(spec_train) // V, 0, (len(spec_train) // V) * V
+        else:
+            self.per, lo, hi = shard_layout(len(spec_train), world, rank, V)  # rows of one shard; shard q = rank * V + replica
         self.engine = Engine(self.cfg, n_trials=V, device=device, max_rows=max(int(cfg["batch_size"]), len(spec_val)),
                              seeds=shard_seeds if shard_seeds is not None else
                              [seed * 1000 + rank * V + v for v in range(V)])         # shard-local noise / dropout streams
@@ -102,8 +107,27 @@ class DataParallelTrainer:
             torch.distributed.all_reduce(torch.zeros(1, device=eng.device))
             torch.cuda.synchronize(eng.device)
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        # a trainer dropped without close(): still barrier + unmap before the engine frees the exported block, so that no
+        # peer polls or reads freed memory (skipped when the process group is already gone)
+        try:
+            if self.world == 1 or torch.distributed.is_initialized():
+                self.close()
+        except Exception:
+            pass
+
     def close(self):
         """Barrier + unmap (no rank may free its block while a peer can still read it), then the engine."""
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
         if self.exchange == "peer" and self.engine.handle:
             torch.cuda.synchronize(self.engine.device)
             if self.world > 1:
@@ -174,15 +198,33 @@ class DataParallelTrainer:
         return losses[0], metrics[0]
 
     def train(self, max_epoch=None, callback=None):
-        max_epoch = int(self.cfg["max_epoch"] if max_epoch is None else max_epoch)
+        if max_epoch is not None and int(max_epoch) != int(self.cfg["max_epoch"]):
+            # the in-kernel alpha schedule divides by the hp row's max_epoch (functions.py:214-219): keep it in step
+            self.engine.hp[:, L.HP_MAX_EPOCH] = float(max_epoch)
+            self.cfg["max_epoch"] = int(max_epoch)
+        max_epoch = int(self.cfg["max_epoch"])
         out = None
         for e in range(max_epoch):
             losses, metrics = self.train_epoch(e)
             out = metrics
             if callback is not None:
                 callback(e, [float(v) for v in metrics[:5].cpu()])
+                if self.world > 1 and self.exchange == "peer":
+                    # a slow callback on one rank (checkpoint I/O) must not run into the exchange kernel's arrival timeout
+                    torch.distributed.barrier()
         torch.cuda.synchronize(self.engine.device)
+        self.check_exchange()
         return [float(v) for v in out[:5].cpu()]
+
+    def check_exchange(self):
+        """Raises if an exchange gave up waiting for a peer (the kernel skips that update instead of trapping; the job is
+        inconsistent from then on).  Synchronises the device."""
+        if self.exchange != "peer":
+            return
+        failed = C.c_uint(0)
+        L.check(self.engine.lib.raae_peer_status(self.engine.handle, C.byref(failed)))
+        if failed.value:
+            raise L.RaaeError(f"peer exchange #{failed.value} timed out waiting for a rank (RAAE_PEER_TIMEOUT_S)")
 
     def state_vector(self):
         """Parameters of the three networks (for cross-rank consistency checks)."""

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from .logger import create_logger
-from .trainer import LOSS_HEADER, build_modules
+from .trainer import LOSS_HEADER, build_modules, save_final
 
 
 def shard_trials(trials, world=1, rank=0):
@@ -49,23 +49,32 @@ def gather_results(local, trials, world=1, rank=0, device=None):
 
 
 def run_ensemble(work_dir, train_config, data_file, trials, verbose=False, device="cuda:0", rank=0, world=1,
-                 timeout_hours=0, base_seed=0, epochs_per_call=25, write_artifacts=True, logger=None):
+                 timeout_hours=0, base_seed=0, epochs_per_call=25, write_artifacts=True, logger=None, raise_on_timeout=False):
     """Trains this rank's share of `trials` trials concurrently.  Returns [(metrics, time_used)] in the order of
     shard_trials(trials, world, rank) — the same tuples the reference's run_training returns (train_sc.py:102)."""
-    from .dataloader import get_datasets
+    from .dataloader import load_splits, to_device_pinned
     from .engine import Engine
 
     p = train_config
     mine = shard_trials(trials, world, rank)
-    if not mine:
-        return []
     start = time.time()
-    ds_train, ds_val, _ = get_datasets(data_file, n_aux=p.n_aux)       # parsed once for all trials of the rank
+    # one CSV parse per node (rank 0, binary cache next to the file), memory-mapped by every rank, pinned staging
+    (st, at), (sv, av), _ = load_splits(data_file, n_aux=p.n_aux, rank=rank, world=world)
+    max_epoch = int(p.max_epoch)
+    if not mine:
+        if world > 1 and timeout_hours:                             # keep the timeout agreement collective (see below)
+            import torch.distributed as dist
+            for _ in range(0, max_epoch, epochs_per_call):
+                flag = torch.zeros(1, device=device if dist.get_backend() == "nccl" else "cpu")
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                if flag.item() > 0:
+                    break
+        return []
     cfg = dict(p.to_dict())
     cfg.setdefault("epoch_stop_smooth", 500)
-    (st, at), (sv, av) = ds_train.tensors(), ds_val.tensors()
     eng = Engine(cfg, n_trials=len(mine), device=device, max_rows=max(int(p.batch_size), sv.shape[0]),
                  seeds=[base_seed + t for t in mine])
+    st, at, sv, av = (to_device_pinned(a, eng.device) for a in (st, at, sv, av))
     modules, loggers = [], []
     for i, t in enumerate(mine):
         job_dir = f"{work_dir}/training/job_{t + 1}"
@@ -82,8 +91,9 @@ def run_ensemble(work_dir, train_config, data_file, trials, verbose=False, devic
         eng.load_modules(i, *mods)
         modules.append(mods)
     eng.bind_dataset(st, at, sv, av)
-    max_epoch = int(p.max_epoch)
     metrics = np.zeros((len(mine), 6))
+    failed = np.zeros(len(mine), dtype=bool)
+    timed_out = False
     epoch = 0
     while epoch < max_epoch:
         n = min(epochs_per_call, max_epoch - epoch)
@@ -96,19 +106,39 @@ def run_ensemble(work_dir, train_config, data_file, trials, verbose=False, devic
                     for i in range(len(mine)):
                         loggers[i][1].info(format_loss_row(epoch + e, losses[e, i]))
         metrics = mets[-1]
+        # per-trial failure isolation (the reference aborts the whole map_sync when one engine raises, train_sc.py:91-97):
+        # a trial whose metrics went non-finite is flagged and keeps its slot; the others are unaffected (independent CTAs)
+        failed |= ~np.isfinite(mets[:, :, :6]).all(axis=(0, 2))
         epoch += n
-        if timeout_hours and time.time() - start > timeout_hours * 3600:
-            raise Exception("Training Overtime!")            # train_sc.py:21-22
+        over = bool(timeout_hours and time.time() - start > timeout_hours * 3600)
+        if world > 1 and timeout_hours:
+            # the ranks agree on the decision (one flag per chunk): a rank that raised alone would leave the others
+            # hanging in the final gather
+            import torch.distributed as dist
+            flag = torch.tensor([1.0 if over else 0.0], device=eng.device if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            over = bool(flag.item() > 0)
+        if over:
+            timed_out = True
+            break
     time_used = time.time() - start
     out = []
     for i, t in enumerate(mine):
         m = [float(v) for v in metrics[i, :5]]
+        if failed[i]:
+            m = [float("nan")] * 5                                  # flagged: the gather and the report see NaN, not garbage
         if write_artifacts:
-            eng.store_modules(i, *modules[i])
-            torch.save({"Encoder": modules[i][0], "Decoder": modules[i][1], "Style Discriminator": modules[i][2]},
-                       f"{work_dir}/training/job_{t + 1}/final.pt")
+            if timed_out:
+                loggers[i][0].warning(f"Training Overtime! Stopped after epoch {epoch} of {max_epoch}.")   # train_sc.py:21-22
+            if failed[i]:
+                loggers[i][0].warning("Trial failed: non-finite losses / metrics; no final.pt written.")
+            else:
+                eng.store_modules(i, *modules[i])
+                save_final(modules[i], f"{work_dir}/training/job_{t + 1}/final.pt")
             loggers[i][0].info(m)
             loggers[i][0].info(f"Training finished. Time used: {time_used:.2f}s.\n\n")
         out.append((m, time_used))
     eng.close()
+    if timed_out and raise_on_timeout:
+        raise Exception("Training Overtime!")                   # after every rank has left the loop together
     return out

@@ -50,6 +50,7 @@ class FCEncoder(nn.Module):
             seq += _hidden_block(hidden_size, hidden_size, dropout_rate)
         seq += [nn.Linear(hidden_size, nstyle), nn.BatchNorm1d(nstyle, affine=False)]
         self.main = nn.Sequential(*seq)
+        self._ctor = dict(dropout_rate=dropout_rate, nstyle=nstyle, dim_in=dim_in, n_layers=n_layers)
 
     def forward(self, spec):
         return self.main(spec)
@@ -75,6 +76,8 @@ class FCDecoder(nn.Module):
         self.main = nn.Sequential(*seq)
         self.nstyle = nstyle
         self.debug = debug
+        self._ctor = dict(dropout_rate=dropout_rate, nstyle=nstyle, dim_out=dim_out, last_layer_activation=last_layer_activation,
+                          n_layers=n_layers)
 
     def forward(self, z_gauss):
         return self.main(z_gauss)
@@ -92,6 +95,7 @@ class DiscriminatorFC(nn.Module):
         self.main = nn.Sequential(*seq)
         self.nstyle = nstyle
         self.noise = noise
+        self._ctor = dict(dropout_rate=dropout_rate, nstyle=nstyle, noise=noise, layers=layers)
 
     def forward(self, x, beta):
         if self.training:

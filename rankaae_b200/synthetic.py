@@ -43,6 +43,30 @@ def synthetic_dataset_chunked(n, n_aux=5, dim=256, seed=0, dtype=np.float32, chu
     return np.concatenate(specs), np.concatenate(auxs)
 
 
+def synthetic_dataset_torch(n, n_aux=5, dim=256, seed=0, device="cuda:0"):
+    """The same generator evaluated on the device with torch's generator (float32; the draws differ from the numpy
+    version): for the 1 M-row data-parallel configuration, where a host-side float64 pass would dominate the set-up."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    K = int(n_aux)
+    d = torch.randn(n, max(K, 1), device=device, generator=g)
+    if K > 1:
+        d[:, 1] = torch.randint(4, 7, (n,), device=device, generator=g).float()
+    grid = torch.linspace(0.0, 1.0, dim, device=device)[None, :]
+    dd = d.clone()
+    if K > 1:
+        dd[:, 1] -= 5.0
+    gk = lambda k: dd[:, k % max(K, 1)][:, None]
+    edge = torch.sigmoid((grid - 0.18 - 0.02 * gk(0)) * 40.0)
+    peak1 = (0.9 + 0.25 * gk(1)) * torch.exp(-0.5 * ((grid - 0.27) / 0.035) ** 2)
+    peak2 = 0.35 * torch.exp(-0.5 * ((grid - 0.5 - 0.04 * gk(2)) / 0.06) ** 2)
+    osc = (0.12 + 0.04 * gk(3)) * torch.sin(2 * torch.pi * (grid - 0.3) * (3.0 + 0.3 * gk(4))) * (grid > 0.3)
+    spec = edge * (1.0 + osc) + peak1 * (grid > 0.1) + peak2
+    spec = spec + 0.02 * torch.randn(spec.shape, device=device, generator=g)
+    return spec.clamp_(min=0.0).contiguous(), d[:, :K].contiguous()
+
+
 AUX_NAMES = ["AUX_CT", "AUX_CN", "AUX_OCN", "AUX_RSTD", "AUX_MOOD", "AUX_X5", "AUX_X6", "AUX_X7"]
 
 

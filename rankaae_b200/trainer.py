@@ -46,6 +46,40 @@ def build_modules(p, seed=None):
     return encoder, decoder, discriminator
 
 
+REFERENCE_CLASSES = {"FCEncoder": "FCEncoder", "FCDecoder": "FCDecoder", "DiscriminatorFC": "DiscriminatorFC"}
+
+
+def as_reference_modules(modules):
+    """The reference's own `sc.clustering.model` classes carrying the same parameters / buffers, or None when the
+    reference package is not importable.  `sc/report/analysis.py:115-121` unpickles final.pt with only the reference on
+    the path, so the pickle must name `sc.clustering.model.*` classes."""
+    try:
+        import sc.clustering.model as ref_model
+    except Exception:
+        return None
+    out = []
+    for m in modules:
+        cls = getattr(ref_model, REFERENCE_CLASSES[type(m).__name__])
+        r = cls(**m._ctor)
+        r.load_state_dict(m.state_dict())
+        out.append(r.eval())
+    return tuple(out)
+
+
+def save_final(modules, path, reference_classes=None):
+    """Writes {"Encoder", "Decoder", "Style Discriminator"} as the reference does (trainer.py:281-283, 310), in eval mode
+    (what a consumer that forgets .eval() expects from a finished model).  With the reference importable (or
+    `reference_classes=True`) the pickled objects are the reference's own classes, so `sc_generate_report` loads the file
+    unchanged; otherwise they are rankaae_b200.model classes and `tools/convert_final_pt.py` converts the file later."""
+    enc, dec, dis = (m.eval() for m in modules)
+    ref = as_reference_modules((enc, dec, dis)) if reference_classes in (None, True) else None
+    if ref is None and reference_classes is True:
+        raise RuntimeError("the reference package `sc` is not importable: cannot pickle its classes")
+    enc, dec, dis = ref if ref is not None else (enc, dec, dis)
+    torch.save({"Encoder": enc, "Decoder": dec, "Style Discriminator": dis}, path)
+    return ref is not None
+
+
 def init_trial_state(engine, trial, cfg, seed=None):
     """Fresh PyTorch-default initialisation of trial `trial` (what every reference engine process does
     on its own, train_sc.py:82-90)."""
@@ -106,21 +140,28 @@ class Trainer:
                     self.loss_logger.info(f"{e:d},\t" + "".join(f"{v:.6f},\t" for v in losses[i]))
                 metrics = [float(v) for v in mets[i, :5]]
                 combined_metric = float(mets[i, 5])
-                if combined_metric > best_combined_metric:  # trainer.py:298-301 (state at the end of the chunk)
+                if combined_metric > best_combined_metric:  # trainer.py:298-301
+                    # the checkpoint holds the state at the END of this chunk of epochs (the fused kernels run a chunk per
+                    # call; with a callback the chunk is one epoch and the file is the epoch's own state, as in the reference):
+                    # the file is named after the epoch it was taken at
                     best_combined_metric = combined_metric
-                    best_chpt_file = f"{chkpt_dir}/epoch_{e:06d}_loss_{combined_metric:07.6g}.pt"
-                    torch.save(self._model_dict(), best_chpt_file)
+                    best_chpt_file = f"{chkpt_dir}/epoch_{epoch + n - 1:06d}_loss_{combined_metric:07.6g}.pt"
+                    save_final(self._modules(), best_chpt_file)
                 if callback is not None:
                     callback(e, metrics)
             epoch += n
-        torch.save(self._model_dict(), f'{self.work_dir}/final.pt')      # trainer.py:310
+        save_final(self._modules(), f'{self.work_dir}/final.pt')          # trainer.py:310
         if best_chpt_file is not None:
             shutil.copy2(best_chpt_file, f'{self.work_dir}/best.pt')
         return metrics
 
-    def _model_dict(self):
+    def _modules(self):
         self.engine.store_modules(0, self.encoder, self.decoder, self.discriminator)
-        return {"Encoder": self.encoder, "Decoder": self.decoder, "Style Discriminator": self.discriminator}
+        return self.encoder, self.decoder, self.discriminator
+
+    def _model_dict(self):
+        enc, dec, dis = self._modules()
+        return {"Encoder": enc, "Decoder": dec, "Style Discriminator": dis}
 
     @classmethod
     def from_data(cls, csv_fn, igpu=0, verbose=True, work_dir='.', train_ratio=0.7, validation_ratio=0.15,

@@ -246,3 +246,163 @@ def test_sweep_points_are_deterministic_and_in_range():
     from rankaae_b200.ensemble import shard_trials
     assert sorted(sum((shard_trials(1024, 8, r) for r in range(8)), [])) == list(range(1024))
     assert all(len(shard_trials(1024, 8, r)) == 128 for r in range(8))
+
+
+# ------------------------------------------------------------------------------------------
+# round 2: loader front end, report compatibility, generator, scheduler restatement, reference install
+# ------------------------------------------------------------------------------------------
+def test_package_generator_is_the_oracle_generator():
+    """bench.py and the tools draw their data from rankaae_b200.synthetic (no oracle import on the product side); it must be
+    the generator the tests use."""
+    from oracle import aae_oracle as O
+    from rankaae_b200.synthetic import synthetic_dataset
+    cfg = O.Config.from_dict(dict(n_aux=5, dim_in=256, dim_out=256, nstyle=6))
+    a = O.synthetic_dataset(300, cfg, seed=7, dtype=np.float32)
+    b = synthetic_dataset(300, 5, 256, seed=7, dtype=np.float32)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_binary_cache_loader_one_parse(tmp_path, monkeypatch):
+    """load_splits == the reference-rule splits of the direct parse; the second call maps the cache without touching the CSV
+    parser; a stale cache (file changed) is rebuilt; the schema asserts of dataloader.py:21-25 still fire."""
+    import pandas as pd
+    from rankaae_b200 import dataloader as D
+    from rankaae_b200.synthetic import synthetic_dataset, write_csv
+    spec, aux = synthetic_dataset(203, 5, 256, seed=1)
+    csv = str(tmp_path / "data.csv")
+    write_csv(csv, spec, aux)
+    splits = D.load_splits(csv, n_aux=5)
+    for (s1, a1), ds in zip(splits, D.get_datasets(csv, n_aux=5)):
+        s2, a2 = ds.tensors()
+        assert np.array_equal(np.asarray(s1), s2) and np.array_equal(np.asarray(a1), a2)
+    assert [len(s) for s, _ in splits] == [142, 30, 31]
+    real = pd.read_csv
+    monkeypatch.setattr(pd, "read_csv", lambda *a, **k: (_ for _ in ()).throw(AssertionError("parsed twice")))
+    again = D.load_splits(csv, n_aux=5)
+    assert np.array_equal(np.asarray(again[0][0]), np.asarray(splits[0][0]))
+    monkeypatch.setattr(pd, "read_csv", real)
+    write_csv(csv, spec[:100], aux[:100])                       # the file changed: size / mtime differ -> rebuilt
+    assert [len(s) for s, _ in D.load_splits(csv, n_aux=5)] == [70, 15, 15]
+    with pytest.raises(AssertionError):
+        D.load_splits(csv, n_aux=6, cache_dir=str(tmp_path))   # column 5 is an ENE_ column, not AUX_
+    t = D.to_device_pinned(splits[0][1], "cpu", chunk_bytes=256)
+    assert np.array_equal(t.numpy(), np.asarray(splits[0][1]))
+
+
+LOADER_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, {root!r})
+import pandas as pd
+from rankaae_b200 import dataloader as D
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo")
+real = pd.read_csv
+def counted(*a, **k):
+    open({marker!r} + f".{{rank}}", "a").write("x")
+    return real(*a, **k)
+pd.read_csv = counted
+splits = D.load_splits({csv!r}, n_aux=5, rank=rank, world=2)
+assert [len(s) for s, _ in splits] == [140, 30, 30]
+dist.destroy_process_group()
+"""
+
+
+def test_loader_parses_once_for_two_ranks_gloo(tmp_path):
+    from rankaae_b200.synthetic import synthetic_dataset, write_csv
+    spec, aux = synthetic_dataset(200, 5, 256, seed=2)
+    csv = str(tmp_path / "data.csv")
+    write_csv(csv, spec, aux)
+    script = tmp_path / "w.py"
+    script.write_text(LOADER_WORKER.format(root=ROOT, marker=str(tmp_path / "parsed"), csv=csv))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert os.path.exists(str(tmp_path / "parsed") + ".0") and not os.path.exists(str(tmp_path / "parsed") + ".1")
+
+
+def _reference_dir():
+    for d in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.exists(os.path.join(d, "sc", "clustering", "model.py")):
+            return d
+    return None
+
+
+def test_final_pt_loads_with_only_the_reference_importable(tmp_path):
+    """sc/report/analysis.py:115-121 unpickles final.pt with the reference on the path and nothing else: the pickle must
+    name sc.clustering.model classes, be in eval mode and reproduce the encoder / decoder outputs."""
+    ref = _reference_dir()
+    if ref is None:
+        pytest.skip("reference sources not available")
+    from rankaae_b200.trainer import build_modules, save_final
+    cfg = dict(ae_form="FC", nstyle=6, dropout_rate=0.04, dim_in=256, dim_out=256, n_layers=5, decoder_activation="Softplus",
+               dis_dropout_rate=0.05, dis_noise=0.5, FC_discriminator_layers=3)
+    mods = build_modules(cfg, seed=1)
+    for m in mods[:2]:                                          # non-trivial BatchNorm buffers
+        for b in m.modules():
+            if isinstance(b, torch.nn.BatchNorm1d):
+                b.running_mean.uniform_(-0.3, 0.3)
+                b.running_var.uniform_(0.5, 1.5)
+    sys.path.insert(0, ref)
+    try:
+        assert save_final(mods, str(tmp_path / "final.pt")) is True
+    finally:
+        sys.path.remove(ref)
+        for k in [k for k in sys.modules if k == "sc" or k.startswith("sc.")]:
+            del sys.modules[k]
+    x = torch.randn(7, 256, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        z = mods[0].eval()(x)
+        y = mods[1].eval()(z)
+    torch.save({"x": x, "z": z, "y": y}, str(tmp_path / "io.pt"))
+    code = (f"import sys, torch\nsys.path.insert(0, {ref!r})\n"
+            f"m = torch.load({str(tmp_path / 'final.pt')!r}, weights_only=False)\n"
+            f"io = torch.load({str(tmp_path / 'io.pt')!r})\n"
+            "assert 'rankaae_b200' not in sys.modules\n"
+            "assert type(m['Encoder']).__module__ == 'sc.clustering.model' and not m['Encoder'].training\n"
+            "assert m['Decoder'].nstyle == 6\n"
+            "with torch.no_grad():\n    z = m['Encoder'](io['x']); y = m['Decoder'](z)\n"
+            "assert torch.equal(z, io['z']) and torch.equal(y, io['y'])\nprint('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_oracle_plateau_scheduler_matches_torch():
+    """The oracle's ReduceLROnPlateau restatement (and with it the in-kernel one, checked on the GPU) against torch's on
+    scripted sequences: plateaus longer than the patience, negative metrics (relative threshold quirk), the 1e-8 rule."""
+    from oracle import aae_oracle as O
+    rng = np.random.default_rng(0)
+    seqs = [np.concatenate([np.linspace(1.0, 0.5, 12), np.full(9, 0.499), np.linspace(0.45, 0.2, 6), np.full(14, 0.21)]),
+            np.concatenate([np.linspace(-0.1, -0.6, 15), np.full(8, -0.6), -0.6 - 0.001 * np.arange(10)]),
+            0.3 + 0.05 * rng.standard_normal(80)]
+    for seq in seqs:
+        for lr0, factor, patience in ((1e-2, 0.1, 3), (1e-3, 0.5, 5), (3e-8, 0.1, 2), (1e-3, 0.1, 100)):
+            par = torch.nn.Parameter(torch.zeros(1))
+            opt = torch.optim.AdamW([par], lr=lr0)
+            sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=factor, patience=patience, cooldown=0,
+                                                             threshold=0.01)
+            orc = O.ReduceLROnPlateau(lr0, factor=factor, patience=patience)
+            for v in seq:
+                sch.step(float(v))
+                orc.step(float(v))
+                assert orc.lr == pytest.approx(opt.param_groups[0]["lr"], rel=1e-12)
+                assert orc.num_bad_epochs == sch.num_bad_epochs and (orc.best == sch.best or (np.isinf(orc.best) and np.isinf(sch.best)))
+
+
+def test_reference_runner_times_the_unmodified_trainer(tmp_path):
+    """bench.py's reference arm: baseline/ref_runner.py drives the reference's own Trainer.from_data(...).train() (from
+    baseline/_ref) on a small CSV, on the CPU, with the reference's callback hook delimiting the epochs."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_runner
+    if not ref_runner.available():
+        pytest.skip("baseline/_ref not installed (build() installs it where /root/reference exists)")
+    import bench
+    from rankaae_b200.synthetic import synthetic_dataset, write_csv
+    spec, aux = synthetic_dataset(400, 5, 256, seed=3)
+    csv = str(tmp_path / "data.csv")
+    write_csv(csv, spec, aux)
+    cfg = dict(bench.EXAMPLE, **bench.REFERENCE_ONLY_KEYS, batch_size=128)
+    res = ref_runner.run(csv, cfg, n_procs=2, n_epochs=2, threads=1, anomaly=True, timeout=600)
+    assert len(res) == 2 and all(len(r["epoch_s"]) == 2 and all(t > 0 for t in r["epoch_s"]) for r in res)
+    assert all(len(r["metrics"]) == 5 and np.isfinite(r["metrics"]).all() for r in res)
