@@ -90,7 +90,7 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
   for (int t = c.crank; t < ntiles; t += c.csize) {      // this CTA's tiles; `it` counts them
     const int it = tile_iter(c, t);
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
-    const long long q0 = clock64();
+    const long long q0 = RAAE_PROFILE ? clock64() : 0ll;
     auto load_w = [&](int ck) {             // elected thread only
       const int b = ck & 1;
       tc::mbar_expect_tx(&wfull[b], 32768u);
@@ -177,7 +177,7 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
       build_wide_tile(Y, vpanel, vld, N, row0, nv, 0);
     }
     __syncthreads();
-    const long long q1 = clock64();
+    const long long q1 = RAAE_PROFILE ? clock64() : 0ll;
     if (mode == kLastStoreV) {
       // v -> panel (the MI backward needs act'(v) and overwrites it with dL/dv); y = act(v) - xref -> K-major operand image
       // of the re-encoding forward (same layout and reference row as the batch image, ScratchLayout::yk)
@@ -401,8 +401,8 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
       }
       __syncthreads();
     }
-    const long long q2 = clock64();
-    if (!RAAE_PROF_FWD && tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) { sm->prof[16] += q1 - q0; sm->prof[17 + (mode == kLastSmooth)] += q2 - q1; }
+    const long long q2 = RAAE_PROFILE ? clock64() : 0ll;
+    if (RAAE_PROFILE && !RAAE_PROF_FWD && tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) { sm->prof[16] += q1 - q0; sm->prof[17 + (mode == kLastSmooth)] += q2 - q1; }
     if (want_bwd) {
       // db, dW += dv^T a, g = (dv @ W) * dropout
       {
@@ -410,10 +410,10 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
         for (int r = 0; r < kTM; ++r) s += Y[r * kLDW + tid];
         dbp = s;
       }
-      const long long q3 = clock64();
+      const long long q3 = RAAE_PROFILE ? clock64() : 0ll;
       mma_tn8(Y, kLDW, 8 * (tid >> 3), At, kLD, 8 * (tid & 7), 0, kTM, accW);
-      const long long q4 = clock64();
-      if (!RAAE_PROF_FWD && tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) { sm->prof[19] += q3 - q2; sm->prof[20] += q4 - q3; }
+      const long long q4 = RAAE_PROFILE ? clock64() : 0ll;
+      if (RAAE_PROFILE && !RAAE_PROF_FWD && tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) { sm->prof[19] += q3 - q2; sm->prof[20] += q4 - q3; }
       float acc[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -445,7 +445,7 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
           *reinterpret_cast<float4*>(c.sc + c.p->sl.g[0] + (size_t)(row0 + r) * kH + c4) = gm;
         }
       }
-      if (!RAAE_PROF_FWD && tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) sm->prof[21] += clock64() - q4;
+      if (RAAE_PROFILE && !RAAE_PROF_FWD && tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) sm->prof[21] += clock64() - q4;
     }
     __syncthreads();
   }
@@ -862,13 +862,16 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
   float* Ss = arena;                          // [chunk][kZ] styles
   float* Ds = Ss + kKendallChunk * kZ;        // [chunk][kZ] descriptors
   const float* zE = c.sc + c.p->sl.zE;
-  float* kacc = c.sc + c.p->sl.g[0];          // [rows][16] per-row A | Bn (spill for multi-chunk batches)
+  float* kacc = c.sc + c.p->sl.g[0];          // [rows][32] per-row A | Bn per partner half (spill for multi-chunk batches)
   float* dz = c.sc + c.p->sl.dz;
   int cs[kZ], co[kZ];
   double sp[kZ], sn[kZ];
 #pragma unroll
   for (int k = 0; k < kZ; ++k) { cs[k] = 0; co[k] = 0; sp[k] = 0.0; sn[k] = 0.0; }
   const int nchunks = (B + kKendallChunk - 1) / kKendallChunk;
+  // cluster per trial: a CTA owns few rows (128 at 8 CTAs and 1024 rows), so two threads share a row and split its partners
+  constexpr int JS = RAAE_CLUSTER ? 2 : 1;
+  constexpr int rpp = kThreads / JS;                              // rows per pass
   // cluster per trial: a CTA pairs ITS rows i (slot -> row) with all rows j; the other CTAs' latents / descriptors must be
   // visible (in eval mode the producing stage has no barrier of its own)
   const int crank = c.crank, csize = c.csize;
@@ -887,16 +890,19 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
       Ss[i] = s; Ds[i] = d;
     }
     __syncthreads();
-    for (int ib = 0; ib < nslots; ib += kThreads) {
+    const int lrow = tid % rpp, half = tid / rpp;
+    for (int ib = 0; ib < nslots; ib += rpp) {
       // without the gradient only the totals are needed and p_ij = p_ji: each unordered pair is visited once (j > i) and
       // the totals are doubled at the end; alternate passes run the rows in reverse so that every thread gets long and
       // short rows (row i has B - 1 - i partners)
-      const int sl = (want_grad || !((ib / kThreads) & 1)) ? ib + tid : ib + kThreads - 1 - tid;
+      const int sl = (want_grad || !((ib / rpp) & 1)) ? ib + lrow : ib + rpp - 1 - lrow;
       if (sl >= nslots) continue;
       const int i = csize == 1 ? sl : cl::slot_row(sl, crank, csize);
       if (i >= B) continue;
-      const int jb = want_grad ? 0 : max(0, i + 1 - j0);         // first staged row of this chunk that row i pairs with
+      int jb = want_grad ? 0 : max(0, i + 1 - j0);               // first staged row of this chunk that row i pairs with
       if (jb >= nj) continue;
+      int je = nj;
+      if (JS > 1) { const int len = nj - jb; je = jb + (len * (half + 1)) / JS; jb = jb + (len * half) / JS; }
       float si[kZ], di[kZ], A[kZ], T[kZ], fp[kZ], fn[kZ];
 #pragma unroll
       for (int k = 0; k < kZ; ++k) {
@@ -905,24 +911,25 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
         A[k] = 0.f; T[k] = 0.f; fp[k] = 0.f; fn[k] = 0.f;
       }
       switch (K) {
-        case 1: kendall_row<1>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
-        case 2: kendall_row<2>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
-        case 3: kendall_row<3>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
-        case 4: kendall_row<4>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
-        case 5: kendall_row<5>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
-        case 6: kendall_row<6>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
-        case 7: kendall_row<7>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
-        default: kendall_row<8>(Ss + jb * kZ, Ds + jb * kZ, nj - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 1: kendall_row<1>(Ss + jb * kZ, Ds + jb * kZ, je - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 2: kendall_row<2>(Ss + jb * kZ, Ds + jb * kZ, je - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 3: kendall_row<3>(Ss + jb * kZ, Ds + jb * kZ, je - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 4: kendall_row<4>(Ss + jb * kZ, Ds + jb * kZ, je - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 5: kendall_row<5>(Ss + jb * kZ, Ds + jb * kZ, je - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 6: kendall_row<6>(Ss + jb * kZ, Ds + jb * kZ, je - jb, si, di, A, T, fp, fn, cs, co); break;
+        case 7: kendall_row<7>(Ss + jb * kZ, Ds + jb * kZ, je - jb, si, di, A, T, fp, fn, cs, co); break;
+        default: kendall_row<8>(Ss + jb * kZ, Ds + jb * kZ, je - jb, si, di, A, T, fp, fn, cs, co); break;
       }
 #pragma unroll
       for (int k = 0; k < kZ; ++k) { sp[k] += (double)fp[k]; sn[k] -= (double)fn[k]; }
       if (want_grad) {
         // A = sum [p > 0] t, Bn = sum [p <= 0] t = T - A, accumulated over the chunks of a large batch
 #pragma unroll
-        for (int k = 0; k < kZ; ++k) {
+        for (int k = 0; k < kZ; ++k) {            // row i: [half 0: A | Bn][half 1: A | Bn]
           float a = A[k], bn = T[k] - A[k];
-          if (ck > 0) { a += kacc[(size_t)i * 16 + k]; bn += kacc[(size_t)i * 16 + 8 + k]; }
-          kacc[(size_t)i * 16 + k] = a; kacc[(size_t)i * 16 + 8 + k] = bn;
+          float* ka = kacc + (size_t)i * 32 + 16 * half;
+          if (ck > 0) { a += ka[k]; bn += ka[8 + k]; }
+          ka[k] = a; ka[8 + k] = bn;
         }
       }
     }
@@ -961,7 +968,11 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
       const int sl = e >> 3, k = e & 7, r = csize == 1 ? sl : cl::slot_row(sl, crank, csize);
       if (r >= B) continue;
       float g = 0.f;
-      if (k < K) g = scale * (sm->kw[k] * kacc[(size_t)r * 16 + k] + kacc[(size_t)r * 16 + 8 + k]);
+      if (k < K) {
+        float a = kacc[(size_t)r * 32 + k], bn = kacc[(size_t)r * 32 + 8 + k];
+        if (JS > 1) { a += kacc[(size_t)r * 32 + 16 + k]; bn += kacc[(size_t)r * 32 + 24 + k]; }
+        g = scale * (sm->kw[k] * a + bn);
+      }
       dz[(size_t)r * kZ + k] = g;
     }
   }

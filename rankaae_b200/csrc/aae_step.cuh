@@ -62,8 +62,18 @@ struct StageTimer {
 #define RAAE_PROF_FWD 0                 // 1: sub-stage probes of fwd_hidden64_tc in slots 16..22 (tools/stage_profile.py raw)
 #endif
 #define RAAE_FPROBE(slot) do { if (RAAE_PROF_FWD) RAAE_PROBE(slot); } while (0)
+// sub-stage probes cost a clock read + a shared-memory update per tile: compiled in only for profiling builds
+// (RAAE_NVCC_EXTRA="-DRAAE_PROFILE=1"); the per-stage StageTimer (one read per stage) is always on
+#ifndef RAAE_PROFILE
+#define RAAE_PROFILE RAAE_PROF_FWD
+#endif
+#if RAAE_PROFILE
 #define RAAE_PROBE_INIT() long long probe_t_ = clock64()
 #define RAAE_PROBE(slot) do { if (threadIdx.x == 0) { long long now_ = clock64(); sm->prof[slot] += now_ - probe_t_; probe_t_ = now_; } } while (0)
+#else
+#define RAAE_PROBE_INIT() do { } while (0)
+#define RAAE_PROBE(slot) do { } while (0)
+#endif
 
 struct Ctx {
   const KParams* p;

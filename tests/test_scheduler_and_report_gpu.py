@@ -118,6 +118,9 @@ def _reference_analysis():
     if ref not in sys.path:
         sys.path.insert(0, ref)
     import sc.report.analysis as A
+    import sklearn.metrics
+    # scikit-learn >= 1.x returns a Python float from f1_score; the reference calls .tolist() on it (analysis.py:267)
+    A.f1_score = lambda *a, **k: np.float64(sklearn.metrics.f1_score(*a, **k))
     return A
 
 

@@ -26,6 +26,7 @@ traffic = {"kernel": "raae_train_kernel",
            "duration_ms": g("gpu__time_duration.sum"), "dram_bytes_read": g("dram__bytes_read.sum") * 1e9,
            "dram_bytes_write": g("dram__bytes_write.sum") * 1e9,
            "dram_pct_of_peak": g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+           "dram_gbs": (g("dram__bytes_read.sum") + g("dram__bytes_write.sum")) * 1e9 / (g("gpu__time_duration.sum") * 1e-3) / 1e9,
            "tensor_pipe_pct_active": g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
            "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
            "warps_active_pct": g("sm__warps_active.avg.pct_of_peak_sustained_active"),
