@@ -159,6 +159,9 @@ int raae_query_layout(const raae_config* cfg, raae_layout* out);
 /* Handle life cycle.  `device` is the CUDA ordinal. */
 int raae_create(const raae_config* cfg, int device, raae_handle** out);
 int raae_destroy(raae_handle* h);
+/* Clusters of `ctas_per_trial` CTAs of the train kernel that fit the device at once (a cluster lives inside one GPC and
+ * every CTA needs a whole SM): more trials than this per launch run in waves. */
+int raae_max_clusters(int ctas_per_trial, int device, int* out);
 
 /* state: [n_trials][layout.state_floats]; scratch: [n_trials][layout.scratch_floats];
  * float32 device memory, 16-byte aligned; hp: [n_trials][RAAE_HP_COUNT] float64 device memory. */

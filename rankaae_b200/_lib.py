@@ -64,7 +64,7 @@ class ValIO(C.Structure):
                 ("losses", _p), ("metrics", _p), ("z", _p), ("row_mae", _p), ("per_trial", _i32), ("reserved", _i32)]
 
 
-EXPORTS = ("raae_last_error", "raae_version", "raae_query_layout", "raae_create", "raae_destroy", "raae_bind_state",
+EXPORTS = ("raae_last_error", "raae_version", "raae_query_layout", "raae_create", "raae_destroy", "raae_max_clusters", "raae_bind_state",
            "raae_bind_dataset", "raae_bind_shapiro_weights", "raae_reset_optimizers", "raae_step_debug",
            "raae_validate", "raae_train_epochs", "raae_launch_count", "raae_set_profile_buffer",
            "raae_train_phase", "raae_apply_adam", "raae_validate_epoch", "raae_evaluate_trials",
@@ -95,6 +95,7 @@ def load():
     lib.raae_query_layout.argtypes = [C.POINTER(Config), C.POINTER(Layout)]
     lib.raae_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(_p)]
     lib.raae_destroy.argtypes = [_p]
+    lib.raae_max_clusters.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.raae_bind_state.argtypes = [_p, _p, _p, _p]
     lib.raae_bind_dataset.argtypes = [_p, _p, _p, C.c_int, _p, _p, C.c_int]
     lib.raae_bind_shapiro_weights.argtypes = [_p, _p, C.c_int]
@@ -118,6 +119,16 @@ def load():
     lib.raae_peer_free.argtypes = [_p]
     _lib = lib
     return lib
+
+
+def max_clusters(ctas_per_trial, device=0):
+    """Co-resident clusters of `ctas_per_trial` CTAs of the train kernel on `device` (148 for one CTA per trial on a B200)."""
+    if ctas_per_trial == 1:
+        import torch
+        return torch.cuda.get_device_properties(device).multi_processor_count
+    n = C.c_int(0)
+    check(load().raae_max_clusters(int(ctas_per_trial), int(device), C.byref(n)))
+    return n.value
 
 
 def check(rc):

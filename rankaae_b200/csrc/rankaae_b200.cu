@@ -251,6 +251,16 @@ int raae_create(const raae_config* cfg, int device, raae_handle** out) {
   return 0;
 }
 
+int raae_max_clusters(int ctas_per_trial, int device, int* out) {
+  if (!out) return fail(-1, "null argument");
+  if (ctas_per_trial != 2 && ctas_per_trial != 4 && ctas_per_trial != RAAE_MAX_CTAS) return fail(-1, "ctas_per_trial must be 2, 4 or 8");
+  RAAE_CUDA(cudaSetDevice(device));
+  int n = 0;
+  RAAE_CUDA(raae_cluster_setup(ctas_per_trial, &n));
+  *out = n;
+  return 0;
+}
+
 int raae_destroy(raae_handle* h) {
   if (h) peer_release(h);
   delete h;

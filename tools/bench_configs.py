@@ -46,12 +46,11 @@ def _timed(fn, dev, world):
     return float(t.item()), out
 
 
-def pick_cluster(trials_on_rank, n_sms=148):
-    """Largest cluster size whose CTAs (one cluster per trial) still fit the GPU in one wave.  Clusters are confined to a GPC
-    (16-20 SMs on B200), so 8-CTA clusters leave at most 16 per GPU and 4-CTA clusters 33."""
-    fit = {8: 16, 4: 33, 2: 74, 1: n_sms}
-    for c in (8, 4, 2, 1):
-        if trials_on_rank <= fit[c]:
+def pick_cluster(trials_on_rank, dev_index=0):
+    """Largest cluster size whose clusters (one per trial) still fit the GPU in ONE wave: a cluster lives inside a GPC and
+    every CTA takes a whole SM, so the driver's occupancy query (raae_max_clusters) decides, not 148 / C."""
+    for c in (8, 4, 2):
+        if trials_on_rank <= L.max_clusters(c, dev_index):
             return c
     return 1
 
@@ -77,7 +76,7 @@ def single_trial(cfg, data, dev, warmup, steps, n_train):
 
 def strong_64(cfg, data, dev, rank, world, warmup, steps, n_train, trials=64):
     mine = shard_trials(trials, world, rank)
-    c = pick_cluster((trials + world - 1) // world)
+    c = pick_cluster((trials + world - 1) // world, dev.index or 0)
     eng = Engine(dict(cfg, ctas_per_trial=c), n_trials=len(mine), device=dev, max_rows=1056, seeds=mine)
     for i, t in enumerate(mine):
         init_trial_state(eng, i, cfg, seed=t)
@@ -89,7 +88,8 @@ def strong_64(cfg, data, dev, rank, world, warmup, steps, n_train, trials=64):
     eng.close()
     return {"workload": f"BASELINE configs[2] as written: {trials} trials of the example config partitioned over {world} GPU(s) "
                         f"(trial t -> rank t % world, no data-path collective), one {c}-CTA cluster per trial",
-            "scaling": "strong", "trials": trials, "trials_per_gpu": len(mine), "ctas_per_trial": c, "ms_per_epoch": ms,
+            "scaling": "strong", "trials": trials, "trials_per_gpu": len(mine), "ctas_per_trial": c,
+            "co_resident_clusters": {str(k): L.max_clusters(k, dev.index or 0) for k in (2, 4, 8)}, "ms_per_epoch": ms,
             "samples_per_sec": trials * n_train / (ms * 1e-3), "trials_per_hour_2000_epochs": trials * 3600.0 / (ms * 1e-3 * 2000.0),
             "finite": finite,
             "limiter": "raae_train_kernel: every stage of a trial is a dependent chain (load -> MMA -> BatchNorm reduction -> "
