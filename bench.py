@@ -456,7 +456,7 @@ def run_ours(args):
                 line["single_trial"] = rec
         if world == 1 and not args.no_single:
             # the reference-facing calls, CSV on disk -> final.pt on disk, by wall clock
-            configs["reference_api"] = BC.reference_api(EXAMPLE, N_ROWS, local, epochs=40)
+            configs["reference_api"] = BC.reference_api(EXAMPLE, N_ROWS, local, epochs=200)
         # configs[2] as written: 64 trials partitioned over the GPUs of this run (strong scaling)
         configs["strong_64"] = BC.strong_64(EXAMPLE, dset, dev, rank, world, W, K, N_TRAIN)
         # configs[3]: one trial data-parallel over the GPUs of this run on the 1 M-row set

@@ -241,3 +241,84 @@ def test_data_parallel_two_gpus(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+DP_TIMEOUT_WORKER = r"""
+import os, sys, time
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+os.environ["RAAE_PEER_TIMEOUT_S"] = "2"
+from oracle import aae_oracle as O
+from rankaae_b200 import _lib as L
+from rankaae_b200.dp import DataParallelTrainer
+from tests.test_parity_gpu import EXAMPLE
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{{local}}"))
+cfg = dict(EXAMPLE, batch_size=128, max_epoch=4)
+spec, aux = O.synthetic_dataset(600, O.Config.from_dict(cfg), seed=8, dtype=np.float32)
+dp = DataParallelTrainer(cfg, spec[:420], aux[:420], spec[420:510], aux[420:510], f"cuda:{{local}}", rank, world, seed=2, exchange="peer")
+dp.train_epoch(0)
+torch.cuda.synchronize()
+dp.check_exchange()                                   # a healthy epoch: no error word
+# rank 1 arrives 5 s late at the next exchange: rank 0 gives up after 2 s WITHOUT trapping (the context stays usable),
+# skips the update and reports the call number; rank 1 then finds nobody waiting and times out as well
+for k in range(L.NUM_PHASES):
+    dp._gptr[k] = dp._grad_ptrs[k] if k == 0 else None
+perm = dp.make_perm()
+L.check(dp.engine.lib.raae_train_phase(dp.engine.handle, 1, 0, 1, perm.data_ptr(), dp._gptr, dp.engine.stream))
+if rank == 1:
+    time.sleep(5.0)
+dp._exchange_update(0)
+torch.cuda.synchronize()                              # would raise "unspecified launch failure" after a trap
+try:
+    dp.check_exchange()
+    failed = False
+except L.RaaeError as e:
+    failed = "timed out" in str(e)
+x = torch.ones(4, device=f"cuda:{{local}}") * 2         # the CUDA context is alive
+assert float(x.sum()) == 8.0
+assert failed if rank == 0 else True
+open(os.path.join({out!r}, f"ok{{rank}}"), "w").write(str(failed))
+dist.barrier()
+dp.close()
+dist.destroy_process_group()
+"""
+
+
+def test_peer_exchange_timeout_does_not_trap(tmp_path):
+    """A rank that never meets its peers in the fused exchange gives up after RAAE_PEER_TIMEOUT_S, skips the update and
+    reports it to the host; the CUDA context survives (round 1 trapped, which kills every later call of the job)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "w.py"
+    script.write_text(DP_TIMEOUT_WORKER.format(root=root, out=str(tmp_path)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29537", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert (tmp_path / "ok0").read_text() == "True"
+
+
+def test_peer_exchange_rejects_unsafe_buffer_reuse():
+    """The buffer-reuse argument of the exchange needs another exchange between two uses of a phase's vector; the host
+    refuses the same phase twice in a row after the vector was rewritten (world > 1 only; at world 1 nobody else reads)."""
+    import ctypes as C
+    import torch
+    from rankaae_b200 import _lib as L
+    from rankaae_b200.dp import DataParallelTrainer
+    cfg = dict(EXAMPLE, batch_size=128, max_epoch=4)
+    spec, aux = O.synthetic_dataset(600, O.Config.from_dict(cfg), seed=8, dtype=np.float32)
+    dp = DataParallelTrainer(cfg, spec[:420], aux[:420], spec[420:510], aux[420:510], "cuda:0", rank=0, world=1, seed=2, exchange="peer")
+    perm = dp.make_perm()
+    for _ in range(2):                                   # world 1: allowed (and exercised by dp_bench-style loops)
+        for k in range(L.NUM_PHASES):
+            dp._gptr[k] = dp._grad_ptrs[k] if k == 0 else None
+        L.check(dp.engine.lib.raae_train_phase(dp.engine.handle, 0, 0, 1, perm.data_ptr(), dp._gptr, dp.engine.stream))
+        dp._exchange_update(0)
+    torch.cuda.synchronize()
+    dp.check_exchange()
+    dp.close()
