@@ -7,9 +7,9 @@ mkdir -p $O
 python bench.py --steps 10 --warmup 3 > $O/bench_$TAG.json 2> $O/bench_$TAG.err || exit 1
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_$TAG.json 2> $O/bench_ref_$TAG.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu --no-single > $O/ncu_launches_$TAG.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu --no-single --no-configs --no-peak > $O/ncu_launches_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:raae_train_kernel -s 3 -c 1 -f -o $O/prof_${TAG}_final \
-    python bench.py --steps 1 --warmup 3 --trials 148 --no-cpu --no-single --no-configs > $O/ncu_full_$TAG.log 2>&1
+    python bench.py --steps 1 --warmup 3 --trials 148 --no-cpu --no-single --no-configs --no-peak > $O/ncu_full_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:raae_train_kernel -s 4 -c 1 -f -o $O/prof_${TAG}_cluster8 \
     python tools/cluster_bench.py "1:8" 3 > $O/ncu_cluster_$TAG.log 2>&1
 python tools/stage_profile.py 148 3 > $O/stage_profile_t148.txt 2>&1

@@ -22,7 +22,7 @@ hdr, units, vals = rows[0], rows[1], rows[2]
 d = {h: vals[i] for i, h in enumerate(hdr)}
 g = lambda k: float(d[k].replace(",", ""))
 traffic = {"kernel": "raae_train_kernel",
-           "launch": "5 train batches x 148 trials (bench.py --steps 1 --warmup 3 --trials 148 --no-cpu --no-single, 4th launch)",
+           "launch": "5 train batches x 148 trials (bench.py --steps 1 --warmup 3 --trials 148 --no-cpu --no-single --no-configs, 4th launch)",
            "duration_ms": g("gpu__time_duration.sum"), "dram_bytes_read": g("dram__bytes_read.sum") * 1e9,
            "dram_bytes_write": g("dram__bytes_write.sum") * 1e9,
            "dram_pct_of_peak": g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
@@ -50,11 +50,30 @@ with open(os.path.join(P, f"ncu_train_{tag}_lines.txt"), "w") as f:
     f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, "40"], capture_output=True, text=True).stdout)
 b = json.load(open(os.path.join(G, f"bench_{tag}.json")))
 b["roofline"]["traffic"] = traffic["dram_bytes_read"] + traffic["dram_bytes_write"]
+b["roofline"].update(tensor_pipe_pct=traffic["tensor_pipe_pct_active"], dram_gbs=traffic["dram_gbs"],
+                     dram_pct_of_peak=traffic["dram_pct_of_peak"], occupancy_warps_active_pct=traffic["warps_active_pct"],
+                     issue_active_pct=traffic["issue_active_pct"], ncu_capture=f"profiles/ncu_train_{tag}_traffic.json")
 json.dump(b, open(os.path.join(P, f"bench_{tag}.json"), "w"))
 for src, dst in (("stage_profile_t148.txt", f"stage_profile_{tag}_t148.txt"), ("stage_profile_t1.txt", f"stage_profile_{tag}_t1.txt"),
-                 (f"launches_{tag}.csv", f"launches_{tag}.csv"), ("e2e_band.json", f"e2e_band_{tag}.json"), ("bench_n2.json", f"bench_{tag}_n2.json")):
+                 ("stage_profile_t1_c8.txt", f"stage_profile_{tag}_t1_c8.txt"),
+                 (f"launches_{tag}.csv", f"launches_{tag}.csv"), ("e2e_band.json", f"e2e_band_{tag}.json"),
+                 ("e2e_band_long.json", f"e2e_band_long_{tag}.json"), (f"bench_ref_{tag}.json", f"bench_ref_{tag}.json"),
+                 (f"bench_{tag}_n2.json", f"bench_{tag}_n2.json"), (f"bench_{tag}_n4.json", f"bench_{tag}_n4.json"),
+                 (f"bench_{tag}_n8.json", f"bench_{tag}_n8.json")):
     if os.path.exists(os.path.join(G, src)):
         shutil.copy(os.path.join(G, src), os.path.join(P, dst))
+crep = os.path.join(G, f"prof_{tag}_cluster8.ncu-rep")
+if os.path.exists(crep):                      # the 8-CTA-cluster build, one trial
+    craw = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", crep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
+    with open(os.path.join(P, f"ncu_train_{tag}_raw_cluster8.txt"), "w") as f:
+        f.write(f"# ncu -i prof_{tag}_cluster8.ncu-rep --page raw --csv (selected metrics); raae_cn::raae_train_kernel, 1 trial as an 8-CTA cluster, 5 train batches\n")
+        for i, h in enumerate(craw[0]):
+            if h in keys or h in ("launch__cluster_dim_x", "launch__cluster_scheduling_policy", "launch__cluster_max_active"):
+                f.write(f"{h:95s} {craw[1][i]:16s} {craw[2][i]}\n")
+    with open(os.path.join(P, f"ncu_train_{tag}_lines_cluster8.txt"), "w") as f:
+        f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), crep, "30"], capture_output=True, text=True).stdout)
+with open(os.path.join(P, f"sass_{tag}.txt"), "w") as f:
+    f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_summary.py")], capture_output=True, text=True).stdout)
 with open(os.path.join(P, f"parity_{tag}.md"), "w") as f:
     f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "parity_table.py"), G], capture_output=True, text=True).stdout)
 print(json.dumps({"ms_per_step": b["ms_per_step"], "value": b["value"], "e2e": b["e2e"]["value"], "frac": b["roofline"]["frac"],
