@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import Engine
+from .engine import Engine, auto_ctas_per_trial
 from .trainer import build_modules
 
 
@@ -60,6 +60,7 @@ class DataParallelTrainer:
         self.exchange = exchange
         self.cfg = dict(cfg)
         self.cfg.setdefault("epoch_stop_smooth", 500)
+        self.cfg["ctas_per_trial"] = auto_ctas_per_trial(self.cfg, V, device)     # per-GPU batch 512: a 4-CTA cluster per replica
         if presharded:
             self.per, lo, hi = len(spec_train) // V, 0, (len(spec_train) // V) * V
         else:

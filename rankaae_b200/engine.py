@@ -109,6 +109,24 @@ def make_config(cfg, n_trials, max_rows=None):
         tensor_cores=int(g("tensor_cores", int(os.environ.get("RAAE_TENSOR_CORES", str(DEFAULT_TENSOR_CORES))))))
 
 
+def auto_ctas_per_trial(cfg, n_trials, device=0):
+    """Cluster size for `n_trials` resident trials when the config does not fix `ctas_per_trial`: the largest of 8 / 4 / 2
+    whose clusters (one per trial) still fit the GPU in ONE wave (raae_max_clusters: 15 / 33 / 74 on a B200) and that has a
+    128-row tile of the batch for every CTA; 1 (one CTA per trial, the ensemble path) otherwise."""
+    g = cfg.get if hasattr(cfg, "get") else (lambda k, d=None: getattr(cfg, k, d))
+    fixed = g("ctas_per_trial", None)
+    if fixed is None:
+        fixed = os.environ.get("RAAE_CTAS_PER_TRIAL")
+    if fixed is not None:
+        return int(fixed)
+    tiles = (int(g("batch_size", 1024)) + 127) // 128
+    dev = torch.device(device).index if not isinstance(device, int) else device
+    for c in (8, 4, 2):
+        if tiles >= c and n_trials <= L.max_clusters(c, dev or 0):
+            return c
+    return 1
+
+
 class Engine:
     """One handle per GPU: `n_trials` independent trials resident on `device`."""
 

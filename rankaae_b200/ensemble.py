@@ -53,7 +53,7 @@ def run_ensemble(work_dir, train_config, data_file, trials, verbose=False, devic
     """Trains this rank's share of `trials` trials concurrently.  Returns [(metrics, time_used)] in the order of
     shard_trials(trials, world, rank) — the same tuples the reference's run_training returns (train_sc.py:102)."""
     from .dataloader import load_splits, to_device_pinned
-    from .engine import Engine
+    from .engine import Engine, auto_ctas_per_trial
 
     p = train_config
     mine = shard_trials(trials, world, rank)
@@ -72,6 +72,8 @@ def run_ensemble(work_dir, train_config, data_file, trials, verbose=False, devic
         return []
     cfg = dict(p.to_dict())
     cfg.setdefault("epoch_stop_smooth", 500)
+    # few trials per GPU (e.g. 64 trials over 8 GPUs): a thread-block cluster per trial, as large as still fits in one wave
+    cfg["ctas_per_trial"] = auto_ctas_per_trial(cfg, (trials + world - 1) // world, device)
     eng = Engine(cfg, n_trials=len(mine), device=device, max_rows=max(int(p.batch_size), sv.shape[0]),
                  seeds=[base_seed + t for t in mine])
     st, at, sv, av = (to_device_pinned(a, eng.device) for a in (st, at, sv, av))

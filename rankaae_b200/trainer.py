@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .dataloader import get_datasets
-from .engine import Engine
+from .engine import Engine, auto_ctas_per_trial
 from .model import DiscriminatorFC
 from .parameter import AE_CLS_DICT, OPTIM_DICT, Parameters
 
@@ -113,6 +113,7 @@ class Trainer:
         self.epochs_per_call = epochs_per_call
         cfg = dict(config_parameters.to_dict())
         cfg.setdefault("epoch_stop_smooth", self.epoch_stop_smooth)
+        cfg["ctas_per_trial"] = auto_ctas_per_trial(cfg, 1, device)      # one trial: a thread-block cluster (8 CTAs at batch 1024)
         n_val = val_data[0].shape[0]
         self.engine = Engine(cfg, n_trials=1, device=device, max_rows=max(int(self.batch_size), n_val), seeds=[seed])
         self.engine.load_modules(0, encoder, decoder, discriminator)

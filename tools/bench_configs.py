@@ -128,8 +128,8 @@ def dp_single_trial(dev, rank, world, steps=40, n_rows=1_000_000, ctas=4):
                 dp._exchange_update(o)
 
     for exchange in ("peer", "nccl"):
-        dp = DataParallelTrainer(dict(DP_CFG, ctas_per_trial=ctas), spec, aux, sv, av, dev, rank, 1 if world == 1 else world,
-                                 seed=1, exchange=exchange, presharded=True)
+        dp = DataParallelTrainer(dict(DP_CFG, ctas_per_trial=ctas), spec, aux, sv, av, dev, rank, world, seed=1, exchange=exchange,
+                                 presharded=True)
         perm = dp.make_perm()
         train_some(dp, 0, perm, 8)
         ms, _ = _timed(lambda: train_some(dp, 1, perm, steps), dev, world)
@@ -225,7 +225,7 @@ def reference_api(cfg, n_rows, dev_index, epochs=40, trials=148):
     csv = os.path.join(work, "data.csv")
     write_csv(csv, spec, aux)
     n_train = int(n_rows * 0.7)
-    c1 = dict(cfg, max_epoch=epochs, trials=1, timeout=1, verbose=False, data_file="data.csv", ctas_per_trial=8)
+    c1 = dict(cfg, max_epoch=epochs, trials=1, timeout=1, verbose=False, data_file="data.csv")   # cluster size chosen by Trainer
     with open(os.path.join(work, "fix_config.yaml"), "w") as f:
         yaml.safe_dump(c1, f)
     out = {}
@@ -239,7 +239,7 @@ def reference_api(cfg, n_rows, dev_index, epochs=40, trials=148):
     tr.train()
     torch.cuda.synchronize()
     t2 = time.time()
-    out["trainer"] = {"api": "Trainer.from_data(csv).train()", "epochs": epochs, "load_s": t1 - t0, "train_s": t2 - t1,
+    out["trainer"] = {"api": "Trainer.from_data(csv).train()", "epochs": epochs, "ctas_per_trial": int(tr.engine.ccfg.ctas_per_trial), "load_s": t1 - t0, "train_s": t2 - t1,
                       "samples_per_sec_incl_load": epochs * n_train / (t2 - t0), "samples_per_sec_train": epochs * n_train / (t2 - t1),
                       "final_pt": os.path.exists(os.path.join(job, "final.pt"))}
     tr.engine.close()
