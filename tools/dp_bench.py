@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import aae_oracle as O                                     # noqa: E402  (synthetic data generator only)
+from rankaae_b200.synthetic import synthetic_dataset                   # noqa: E402
 from rankaae_b200 import _lib as L                                     # noqa: E402
 from rankaae_b200.dp import DataParallelTrainer                        # noqa: E402
 
@@ -75,7 +75,7 @@ def main():
     bs = CFG["batch_size"]
     V = args.replicas
     n_train = bs * args.steps * world * V
-    spec, aux = O.synthetic_dataset(n_train + 1050, O.Config.from_dict(CFG), seed=3, dtype=np.float32)
+    spec, aux = synthetic_dataset(n_train + 1050, CFG["n_aux"], CFG["dim_in"], seed=3, dtype=np.float32)
     res = {"workload": f"config #4 shape: 256-point spectra, 6 descriptors, per-rank batch {bs}, {args.steps} batches per rank, "
                        f"{world} rank(s) x {V} replica(s) per GPU (global batch {bs * world * V}), 5 phases per batch", "n_gpus": world,
            "replicas_per_gpu": V}

@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import aae_oracle as O                                     # noqa: E402  (synthetic data generator only)
+from rankaae_b200.synthetic import synthetic_dataset                   # noqa: E402
 from rankaae_b200.engine import Engine                                 # noqa: E402
 from rankaae_b200.ensemble import gather_results, shard_trials         # noqa: E402
 from rankaae_b200.trainer import init_trial_state                      # noqa: E402
@@ -60,7 +60,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     t_wall0 = time.time()
-    spec, aux = O.synthetic_dataset(N_ROWS, O.Config.from_dict(BASE), seed=5, dtype=np.float32)
+    spec, aux = synthetic_dataset(N_ROWS, BASE["n_aux"], BASE["dim_in"], seed=5, dtype=np.float32)
     mine = shard_trials(args.trials, world, rank)
     per_trial = [sweep_point(t) for t in mine]
     eng = Engine(BASE, n_trials=len(mine), device=dev, max_rows=N_VAL, seeds=mine, per_trial_cfg=per_trial)
