@@ -544,9 +544,9 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
 #pragma unroll
     for (int j = 0; j < 8; ++j) accW1[i][j] = 0.f;
   float accW0[kZ] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // (ch, q) partials of dW0[ch][:]
-  float dW2p = 0.f, da1p = 0.f, db1p = 0.f;          // (ch, q) partials
+  float dW2p[4] = {0.f, 0.f, 0.f, 0.f}, da1p[4] = {0.f, 0.f, 0.f, 0.f}, db1p[4] = {0.f, 0.f, 0.f, 0.f};   // (ty, c4) partials
   float da0p[4] = {0.f, 0.f, 0.f, 0.f}, db0p[4] = {0.f, 0.f, 0.f, 0.f};   // (ty, c4) partials
-  float db2p = 0.f;                                   // lane 0 of every warp
+  float db2p = 0.f;                                   // threads 0..127: one row of every tile each
   double lossp = 0.0;
   const int tiles_real = (c.Breal + kTM - 1) / kTM, tiles_fake = (c.B + kTM - 1) / kTM;
   for (int t = 0; t < tiles_real + tiles_fake; ++t) {
@@ -555,6 +555,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
     if (((fake ? t - tiles_real : t) % c.csize) != c.crank) continue;
     const int nrows = fake ? c.B : c.Breal;
     const int row0 = (fake ? t - tiles_real : t) * kTM, nv = min(kTM, nrows - row0);
+    RAAE_PROBE_INIT();
     const MaskSrc mk0 = fake ? mk_fake0 : mk_real0;        // register copies
     const MaskSrc mk1 = fake ? mk_fake1 : mk_real1;
     const float label = fake ? 0.f : 1.f;
@@ -576,28 +577,38 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
       Zt[i] = v;
     }
     __syncthreads();
-    // ---- layer 0: this thread's weight row W0[ch][:] stays in registers, the input row is two broadcast loads ----
+    RAAE_PROBE(23);     // input rows + noise
+    // ---- layer 0: thread (ty, c4) owns channels c4..c4+3 of rows ty, ty + 16, ...: its four weight rows stay in registers,
+    //      the input row is two broadcast loads, one mask draw covers the four channels, float4 stores ----
     {
-      float w0r[kZ];
+      float w0r[4][kZ];
 #pragma unroll
-      for (int k = 0; k < kZ; ++k) w0r[k] = W0s[ch * 9 + k];
-      const float b0c = b0s[ch], a0c = a0s[ch];
-#pragma unroll 4
-      for (int i = 0; i < kTM / 4; ++i) {
-        const int r = q + 4 * i;
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < kZ; ++k) w0r[j][k] = W0s[(c4 + j) * 9 + k];
+      const float4 b0v = *reinterpret_cast<const float4*>(b0s + c4), a0v = *reinterpret_cast<const float4*>(a0s + c4);
+      const float bb[4] = {b0v.x, b0v.y, b0v.z, b0v.w}, aa[4] = {a0v.x, a0v.y, a0v.z, a0v.w};
+#pragma unroll 2
+      for (int i = 0; i < kTM / 16; ++i) {
+        const int r = ty + 16 * i;
         const float4 z0 = *reinterpret_cast<const float4*>(Zt + r * kZ);
         const float4 z1 = *reinterpret_cast<const float4*>(Zt + r * kZ + 4);
-        float u = b0c;
-        u = fmaf(z0.x, w0r[0], u); u = fmaf(z0.y, w0r[1], u); u = fmaf(z0.z, w0r[2], u); u = fmaf(z0.w, w0r[3], u);
-        u = fmaf(z1.x, w0r[4], u); u = fmaf(z1.y, w0r[5], u); u = fmaf(z1.z, w0r[6], u); u = fmaf(z1.w, w0r[7], u);
-        float h = 0.f;
-        if (r < nv) h = mask_keep(mk0, row0 + r, ch) ? prelu_f(u, a0c) * mk0.scale : 0.f;
-        else u = 0.f;
-        U1[r * kLD + ch] = u;
-        H1[r * kLD + ch] = h;
+        const uint32_t kb = r < nv ? mask_keep4(mk0, row0 + r, c4) : 0u;
+        float u[4], h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = bb[j];
+          a = fmaf(z0.x, w0r[j][0], a); a = fmaf(z0.y, w0r[j][1], a); a = fmaf(z0.z, w0r[j][2], a); a = fmaf(z0.w, w0r[j][3], a);
+          a = fmaf(z1.x, w0r[j][4], a); a = fmaf(z1.y, w0r[j][5], a); a = fmaf(z1.z, w0r[j][6], a); a = fmaf(z1.w, w0r[j][7], a);
+          u[j] = r < nv ? a : 0.f;
+          h[j] = (kb >> j & 1u) ? prelu_f(a, aa[j]) * mk0.scale : 0.f;
+        }
+        *reinterpret_cast<float4*>(U1 + r * kLD + c4) = make_float4(u[0], u[1], u[2], u[3]);
+        *reinterpret_cast<float4*>(H1 + r * kLD + c4) = make_float4(h[0], h[1], h[2], h[3]);
       }
     }
     __syncthreads();
+    RAAE_PROBE(24);     // layer 0
     // ---- layer 1 ----
     {
       float acc[8][4];
@@ -612,49 +623,80 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
         for (int j = 0; j < 4; ++j) U2[(ty + 16 * i) * kLD + tx + 16 * j] = acc[i][j] + b1s[tx + 16 * j];
     }
     __syncthreads();
-    for (int i = 0; i < kTM / 4; ++i) {
-      int r = q + 4 * i;
-      float h = 0.f;
-      if (r < nv) h = mask_keep(mk1, row0 + r, ch) ? prelu_f(U2[r * kLD + ch], a1s[ch]) * mk1.scale : 0.f;
-      H2[r * kLD + ch] = h;
-    }
-    __syncthreads();
-    // ---- logits, BCE-with-logits (mean over the rows of this half), dL/dlogit ----
-    for (int r = warp; r < kTM; r += kThreads / 32) {
-      float s = H2[r * kLD + lane] * w2s[lane] + H2[r * kLD + lane + 32] * w2s[lane + 32];
-#pragma unroll
-      for (int of = 16; of > 0; of >>= 1) s += __shfl_xor_sync(0xffffffffu, s, of);
-      if (lane == 0) {
-        float dl = 0.f;
-        if (r < nv) {
-          float x = s + b2;
-          float li = fmaxf(x, 0.f) - x * label + log1pf(expf(-fabsf(x)));
-          lossp += (double)li * inv_rows;              // inv_rows: one float64 division per tile, not per row
-          dl = (sigmoid_f(x) - label) / (float)nrows;
-        }
-        sm->dlogit[r] = dl;
-        db2p += dl;                                    // lane 0 of every warp: partial sum of dL/dlogit (reduced at the end)
+    {
+      const float4 a1v = *reinterpret_cast<const float4*>(a1s + c4);
+#pragma unroll 4
+      for (int i = 0; i < kTM / 16; ++i) {
+        const int r = ty + 16 * i;
+        const uint32_t kb = r < nv ? mask_keep4(mk1, row0 + r, c4) : 0u;
+        const float4 u = *reinterpret_cast<const float4*>(U2 + r * kLD + c4);
+        float4 h;
+        h.x = (kb & 1u) ? prelu_f(u.x, a1v.x) * mk1.scale : 0.f;
+        h.y = (kb & 2u) ? prelu_f(u.y, a1v.y) * mk1.scale : 0.f;
+        h.z = (kb & 4u) ? prelu_f(u.z, a1v.z) * mk1.scale : 0.f;
+        h.w = (kb & 8u) ? prelu_f(u.w, a1v.w) * mk1.scale : 0.f;
+        *reinterpret_cast<float4*>(H2 + r * kLD + c4) = h;
       }
     }
     __syncthreads();
+    RAAE_PROBE(25);     // layer 1 GEMM + H2
+    // ---- logits, BCE-with-logits (mean over the rows of this half), dL/dlogit ----
+    // the dot products by warps (shuffle reduction), then the scalar loss arithmetic of the 128 rows by 128 threads at once
+    // (it was a serial chain of 16 rows on lane 0 of every warp)
+    {
+      const float w2a = w2s[lane], w2b = w2s[lane + 32];
+#pragma unroll 4
+      for (int r = warp; r < kTM; r += kThreads / 32) {
+        float s = H2[r * kLD + lane] * w2a + H2[r * kLD + lane + 32] * w2b;
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) s += __shfl_xor_sync(0xffffffffu, s, of);
+        if (lane == 0) sm->logit[r] = s + b2;
+      }
+    }
+    __syncthreads();
+    if (tid < kTM) {
+      float dl = 0.f;
+      if (tid < nv) {
+        const float x = sm->logit[tid];
+        const float li = fmaxf(x, 0.f) - x * label + log1pf(expf(-fabsf(x)));
+        lossp += (double)li * inv_rows;                // inv_rows: one float64 division per tile, not per row
+        dl = (sigmoid_f(x) - label) / (float)nrows;
+      }
+      sm->dlogit[tid] = dl;
+      db2p += dl;                                      // per-thread partial sum of dL/dlogit (reduced at the end)
+    }
+    __syncthreads();
+    RAAE_PROBE(26);     // logits + BCE
     if (backward) {
       // ---- layer 2 and the PReLU/dropout of layer 1 ----
-      for (int i = 0; i < kTM / 4; ++i) {
-        int r = q + 4 * i;
-        float du = 0.f;
-        if (r < nv) {
-          float dl = sm->dlogit[r];
-          dW2p = fmaf(dl, H2[r * kLD + ch], dW2p);
-          float g = mask_keep(mk1, row0 + r, ch) ? dl * w2s[ch] * mk1.scale : 0.f;
-          float u = U2[r * kLD + ch];
-          bool pos = u > 0.f;
-          du = pos ? g : a1s[ch] * g;
-          da1p += pos ? 0.f : u * g;
-          db1p += du;
+      {
+        const float4 a1v = *reinterpret_cast<const float4*>(a1s + c4), w2v = *reinterpret_cast<const float4*>(w2s + c4);
+#pragma unroll 2
+        for (int i = 0; i < kTM / 16; ++i) {
+          const int r = ty + 16 * i;
+          float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < nv) {
+            const float dl = sm->dlogit[r];
+            const float4 h = *reinterpret_cast<const float4*>(H2 + r * kLD + c4);
+            const float4 u = *reinterpret_cast<const float4*>(U2 + r * kLD + c4);
+            const uint32_t kb = mask_keep4(mk1, row0 + r, c4);
+#define RAAE_DU2(comp, idx, bit)                                                         \
+            {                                                                            \
+              dW2p[idx] = fmaf(dl, h.comp, dW2p[idx]);                                   \
+              const float g = (kb & bit) ? dl * w2v.comp * mk1.scale : 0.f;              \
+              const bool pos = u.comp > 0.f;                                             \
+              du.comp = pos ? g : a1v.comp * g;                                          \
+              da1p[idx] += pos ? 0.f : u.comp * g;                                       \
+              db1p[idx] += du.comp;                                                      \
+            }
+            RAAE_DU2(x, 0, 1u) RAAE_DU2(y, 1, 2u) RAAE_DU2(z, 2, 4u) RAAE_DU2(w, 3, 8u)
+#undef RAAE_DU2
+          }
+          *reinterpret_cast<float4*>(U2 + r * kLD + c4) = du;
         }
-        U2[r * kLD + ch] = du;
       }
       __syncthreads();
+      RAAE_PROBE(16);   // du2 pass
       // ---- layer 1: dW1 += du2^T h1, dh1 = du2 @ W1 ----
       {
         const int qq = tid >> 6, tt = tid & 63;
@@ -687,6 +729,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
         }
       }
       __syncthreads();
+      RAAE_PROBE(17);   // dW1 + dh1 GEMMs + epilogue
       // ---- layer 0: dW0 += du1^T z;  fake rows: dz = -alpha * du1 @ W0 (gradient reversal) ----
       // dW0[ch][k] over rows q, q + 4, ...: one du1 load and one broadcast input row per 8 FMAs
 #pragma unroll 4
@@ -724,6 +767,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
         }
       }
       __syncthreads();
+      RAAE_PROBE(22);   // dW0 + dz
     }
   }
   {
@@ -764,7 +808,6 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
 #pragma unroll
       for (int k = 0; k < kZ; ++k) part[(q * kH + ch) * kZ + k] = accW0[k];
     }
-    sm->red[q][ch] = dW2p; sm->red[4 + q][ch] = da1p; sm->red[8 + q][ch] = db1p;
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -772,16 +815,23 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
       int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
       if (k < ns) gW0[n * ns + k] = part[(0 * kH + n) * kZ + k] + part[(1 * kH + n) * kZ + k] + part[(2 * kH + n) * kZ + k] + part[(3 * kH + n) * kZ + k];
     }
-    if (q == 0) {
-      gW2[ch] = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
-      ga1[ch] = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
-      gb1[ch] = sm->red[8][ch] + sm->red[9][ch] + sm->red[10][ch] + sm->red[11][ch];
-    }
     {
-      const float tot = block_sum(lane == 0 ? db2p : 0.f, sm->redw);
+      const float tot = block_sum(db2p, sm->redw);
       if (tid == 0) gb2[0] = tot;
     }
     __syncthreads();
+    // (ty, c4) partials of dW2 / da1 / db1 -> column sums over the 16 row groups
+    {
+      float* const dst3[3] = {gW2, ga1, gb1};
+      const float* const src3[3] = {dW2p, da1p, db1p};
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        sm->red[ty][c4 + 0] = src3[v][0]; sm->red[ty][c4 + 1] = src3[v][1]; sm->red[ty][c4 + 2] = src3[v][2]; sm->red[ty][c4 + 3] = src3[v][3];
+        __syncthreads();
+        if (tid < kH) { float sacc = 0.f; for (int i = 0; i < 16; ++i) sacc += sm->red[i][tid]; dst3[v][tid] = sacc; }
+        __syncthreads();
+      }
+    }
     sm->red[ty][c4 + 0] = da0p[0]; sm->red[ty][c4 + 1] = da0p[1]; sm->red[ty][c4 + 2] = da0p[2]; sm->red[ty][c4 + 3] = da0p[3];
     __syncthreads();
     if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; ga0[tid] = s; }
