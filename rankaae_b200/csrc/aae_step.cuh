@@ -2396,7 +2396,7 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
   StageTimer timer_(&sm->prof[kStBwdEncLast]);
   const raae_net_layout& nl = NL(c, kE);
   const int L = nl.n_linear, l = L - 1, ns = nl.out_dim[l];
-  const int tid = threadIdx.x, ch = tid & 63, q = tid >> 6;
+  const int tid = threadIdx.x;
   const float* zE = c.sc + c.p->sl.zE;
   const float* dz = c.sc + c.p->sl.dz;
   float* Ws = arena;                   // [kZ][kLD]
@@ -2447,11 +2447,18 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
     Ws[n * kLD + k] = n < ns ? netp(c, kE)[nl.w_off[l] + n * kH + k] : 0.f;
   }
   __syncthreads();
-  float accW8[kZ];
-  float wcol[kZ];                      // W[n][ch], n < 8
+  // thread (ty, c4) owns channels c4..c4+3 of rows ty, ty + 16, ...: its 8 x 4 block of W stays in registers, a row of the
+  // latent gradient is two broadcast loads, one mask draw covers the four channels, float4 loads / stores
+  const int ty = tid >> 4, c4 = (tid & 15) * 4;
+  float accW[kZ][4], wcol[kZ][4];
 #pragma unroll
-  for (int n = 0; n < kZ; ++n) { accW8[n] = 0.f; wcol[n] = Ws[n * kLD + ch]; }
-  float accB = 0.f, sgp = 0.f, sgxp = 0.f;
+  for (int n = 0; n < kZ; ++n) {
+    const float4 w = *reinterpret_cast<const float4*>(Ws + n * kLD + c4);
+    wcol[n][0] = w.x; wcol[n][1] = w.y; wcol[n][2] = w.z; wcol[n][3] = w.w;
+    accW[n][0] = accW[n][1] = accW[n][2] = accW[n][3] = 0.f;
+  }
+  float accB = 0.f;                                   // threads < 64: latent n = tid & 7, rows (tid >> 3) + 8 j of every tile
+  float sgp4[4] = {0.f, 0.f, 0.f, 0.f}, sgxp4[4] = {0.f, 0.f, 0.f, 0.f};
   const int ntiles = (c.B + kTM - 1) / kTM;
   for (int t = c.crank; t < ntiles; t += c.csize) {
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
@@ -2476,48 +2483,73 @@ __device__ __noinline__ void bwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
       *reinterpret_cast<float4*>(D5 + r * kZ + k0) = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
-    // dW[n][ch] over rows q, q + 4, ...: one activation load and one broadcast row of D5 per 8 FMAs
-    // g_prev[r][ch] = sum_n D5[r][n] W[n][ch] with this thread's weight column held in registers
-    for (int i = 0; i < kTM / 4; ++i) {
-      const int r = q + 4 * i;
+    // dW[n][c4 + j] += D5[r][n] a[r][c4 + j];  g_prev[r][c4 + j] = sum_n D5[r][n] W[n][c4 + j]
+#pragma unroll 2
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
       const float4 d0 = *reinterpret_cast<const float4*>(D5 + r * kZ);
       const float4 d1 = *reinterpret_cast<const float4*>(D5 + r * kZ + 4);
       const float dr[kZ] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-      const float av = At[r * kLD + ch];
-      float gg = 0.f;
+      const float4 a4 = *reinterpret_cast<const float4*>(At + r * kLD + c4);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+      float gg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int n = 0; n < kZ; ++n) {
-        accW8[n] = fmaf(dr[n], av, accW8[n]);
-        gg = fmaf(dr[n], wcol[n], gg);
-      }
-      if (ch < kZ) accB += D5[r * kZ + ch];
+      for (int n = 0; n < kZ; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          accW[n][j] = fmaf(dr[n], av[j], accW[n][j]);
+          gg[j] = fmaf(dr[n], wcol[n][j], gg[j]);
+        }
       if (r < nv) {
-        bool keep = mask_keep(in.mask, row0 + r, ch);
-        float gm = keep ? gg * in.mask.scale : 0.f;
-        sgp += gm;
-        sgxp = fmaf(gg, av, sgxp);
-        g_out[(size_t)(row0 + r) * kH + ch] = gm;
+        const uint32_t kb = mask_keep4(in.mask, row0 + r, c4);
+        float gm[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          gm[j] = (kb >> j & 1u) ? gg[j] * in.mask.scale : 0.f;
+          sgp4[j] += gm[j];
+          sgxp4[j] = fmaf(gg[j], av[j], sgxp4[j]);
+        }
+        *reinterpret_cast<float4*>(g_out + (size_t)(row0 + r) * kH + c4) = make_float4(gm[0], gm[1], gm[2], gm[3]);
       }
+    }
+    if (tid < 64) {
+      const int n = tid & 7, g = tid >> 3;
+#pragma unroll 4
+      for (int j = 0; j < kTM / 8; ++j) accB += D5[(g + 8 * j) * kZ + n];
     }
     __syncthreads();
   }
-  // reduce the four row groups: dW partials [4][8][64] and bias partials in the At / D5 area (free now)
-  float* part = At;                      // [4][kZ][64]
+  // reduce the 16 row groups: dW partials [16][8][64] in the At area (free now), the BN-backward sums and the bias partials
+  float* part = At;                      // [16][kZ][64] = 8192 floats <= kTile
 #pragma unroll
-  for (int n = 0; n < kZ; ++n) part[(q * kZ + n) * kH + ch] = accW8[n];
-  sm->red[q][ch] = sgp;
-  sm->red[4 + q][ch] = sgxp;
-  if (ch < kZ) sm->red[8 + q][ch] = accB;
+  for (int n = 0; n < kZ; ++n)
+    *reinterpret_cast<float4*>(part + (ty * kZ + n) * kH + c4) = make_float4(accW[n][0], accW[n][1], accW[n][2], accW[n][3]);
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
-    int oo = tid + kThreads * e, n = oo >> 6, k = oo & 63;
-    if (n < ns) gradW[n * kH + k] = part[(0 * kZ + n) * kH + k] + part[(1 * kZ + n) * kH + k] + part[(2 * kZ + n) * kH + k] + part[(3 * kZ + n) * kH + k];
+    const int oo = tid + kThreads * e, n = oo >> 6, k = oo & 63;
+    if (n < ns) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) sacc += part[(g * kZ + n) * kH + k];
+      gradW[n * kH + k] = sacc;
+    }
   }
-  if (tid < ns) gradW[ns * kH + tid] = sm->red[8][tid] + sm->red[9][tid] + sm->red[10][tid] + sm->red[11][tid];   // [W | b] contiguous
-  if (q == 0) {
-    sg_dst[ch] = sm->red[0][ch] + sm->red[1][ch] + sm->red[2][ch] + sm->red[3][ch];
-    sgx_dst[ch] = sm->red[4][ch] + sm->red[5][ch] + sm->red[6][ch] + sm->red[7][ch];
+  sm->red[ty][c4 + 0] = sgp4[0]; sm->red[ty][c4 + 1] = sgp4[1]; sm->red[ty][c4 + 2] = sgp4[2]; sm->red[ty][c4 + 3] = sgp4[3];
+  __syncthreads();
+  if (tid < kH) { float sacc = 0.f; for (int i = 0; i < 16; ++i) sacc += sm->red[i][tid]; sg_dst[tid] = sacc; }
+  __syncthreads();
+  sm->red[ty][c4 + 0] = sgxp4[0]; sm->red[ty][c4 + 1] = sgxp4[1]; sm->red[ty][c4 + 2] = sgxp4[2]; sm->red[ty][c4 + 3] = sgxp4[3];
+  __syncthreads();
+  if (tid < kH) { float sacc = 0.f; for (int i = 0; i < 16; ++i) sacc += sm->red[i][tid]; sgx_dst[tid] = sacc; }
+  __syncthreads();
+  if (tid < 64) sm->red[0][tid] = accB;               // [8 row groups][8 latents]
+  __syncthreads();
+  if (tid < ns) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) sacc += sm->red[0][g * 8 + tid];
+    gradW[ns * kH + tid] = sacc;                      // [W | b] contiguous
   }
   __syncthreads();
   if (c.csize > 1) { cl::sync(); cluster_gather_sg(c, sm); }
