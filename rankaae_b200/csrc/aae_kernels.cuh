@@ -120,12 +120,11 @@ __device__ __noinline__ void build_batch(const Ctx& c_ref, const int32_t* __rest
 }
 
 // One iteration of the batch loop body, trainer.py:112-204 (gradient-reversal branch).
-__device__ __forceinline__ void train_step(Ctx& c, int phase_mask, bool run_p0 = true) {
+__device__ __forceinline__ void train_step(const Ctx& c, int phase_mask, bool run_p0 = true) {
   const KParams& p = *c.p;
   RAAE_SMEM();
   const int tid = threadIdx.x, ns = p.cfg.nstyle;
   const int LE = p.lay.net[kE].n_linear;
-  c.train = 1;
   if (tid == 0) {
     sm->alpha = alpha_schedule(c);
     for (int i = 0; i < 8; ++i) sm->loss_acc[i] = 0.0;
@@ -295,31 +294,37 @@ raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ Run
 #else
   const int trial = a.trial0 + blockIdx.x;
 #endif
-  Ctx c;
-  init_ctx(c, p, a, trial);
+  Ctx& c = sm->ctx;                      // one copy per CTA in shared memory: thread 0 writes, a barrier publishes
+  const int bs = p.cfg.batch_size;
+  if (threadIdx.x == 0) {
+    init_ctx(c, p, a, trial);
+    if (a.debug) {
+      c.B = a.dbg.rows;
+      c.epoch = a.dbg.epoch;
+      c.apply = a.dbg.apply_updates;
+      c.step_id = 0;
+    } else if (a.split) {
+      c.B = min(bs, p.n_train - a.step0 * bs);
+      c.step_id = (uint32_t)(a.epoch * a.n_steps + a.step0);
+      c.apply = 0;
+    }
+  }
   if (threadIdx.x < 32) sm->prof[threadIdx.x] = 0;
   const long long t_start = clock64();
+  __syncthreads();
   tc_setup(p, sm);
   if (a.debug) {
-    c.B = a.dbg.rows;
-    c.epoch = a.dbg.epoch;
-    c.apply = a.dbg.apply_updates;
-    c.step_id = 0;
     build_batch(c, nullptr);
     train_step(c, a.dbg.phase_mask);
     tc_teardown(p, sm);
     return;
   }
-  const int bs = p.cfg.batch_size;
   const int32_t* perm = a.perm + (size_t)trial * p.n_train;
   if (a.split) {
     // one batch, selected phases, gradients exported instead of applied (data-parallel mode: the host all-reduces
     // them and raae_adam_kernel applies the update).  The batch and the P0 forward belong to the launch that runs P1.
     const bool first = (a.phase_mask & (1 << kAdv)) != 0;
     if (first && a.step0 == 0 && threadIdx.x == 0 && c.crank == 0) { c.st[p.lay.misc_off + 5] = 0.f; c.st[p.lay.misc_off + 6] = 0.f; }
-    c.B = min(bs, p.n_train - a.step0 * bs);
-    c.step_id = (uint32_t)(a.epoch * a.n_steps + a.step0);
-    c.apply = 0;
     if (first) build_batch(c, perm + a.step0 * bs);
     train_step(c, a.phase_mask, first);
     tc_teardown(p, sm);
@@ -327,8 +332,11 @@ raae_train_kernel(const __grid_constant__ KParams p, const __grid_constant__ Run
   }
   if (threadIdx.x == 0 && c.crank == 0) { c.st[p.lay.misc_off + 5] = 0.f; c.st[p.lay.misc_off + 6] = 0.f; }
   for (int s = 0; s < a.n_steps; ++s) {
-    c.B = min(bs, p.n_train - s * bs);
-    c.step_id = (uint32_t)(a.epoch * a.n_steps + s);
+    if (threadIdx.x == 0) {              // every reader of the previous step's values is behind the barrier that ended it
+      c.B = min(bs, p.n_train - s * bs);
+      c.step_id = (uint32_t)(a.epoch * a.n_steps + s);
+    }
+    __syncthreads();
     build_batch(c, perm + s * bs);
     train_step(c, 0x1f);
   }
@@ -477,16 +485,19 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
 #else
   const int trial = a.trial0 + blockIdx.x;
 #endif
-  Ctx c;
-  init_ctx(c, p, a, trial);
+  Ctx& c = sm->ctx;                      // one copy per CTA in shared memory: thread 0 writes, a barrier publishes
   const int tid = threadIdx.x, ns = p.cfg.nstyle, K = p.cfg.n_aux;
   const int LE = p.lay.net[kE].n_linear;
-  c.train = 0;
-  c.apply = 0;
-  c.B = p.n_val;
-  c.x = p.spec_val;
-  c.xld = p.cfg.dim_in;
-  c.step_id = 0x40000000u + (uint32_t)a.epoch;
+  if (tid == 0) {
+    init_ctx(c, p, a, trial);
+    c.train = 0;
+    c.apply = 0;
+    c.B = p.n_val;
+    c.x = p.spec_val;
+    c.xld = p.cfg.dim_in;
+    c.step_id = 0x40000000u + (uint32_t)a.epoch;
+  }
+  __syncthreads();
   raae_val_io io = a.val;
   if (io.per_trial) {                    // raae_evaluate_trials: one output block per trial
     const size_t tb = (size_t)(trial - a.trial0);

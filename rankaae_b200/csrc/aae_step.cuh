@@ -11,6 +11,34 @@
 
 namespace raae {
 
+// Per-trial context of the running kernel.  ONE copy per CTA in shared memory (SmemFixed::ctx): thread 0 writes it, a
+// barrier publishes it, and every stage function starts with a register copy of it (`const Ctx c = c_ref`).  It used to
+// live in the kernel's local-memory frame, where the copy at every stage entry missed the (28 KB, streamed-through) L1.
+struct Ctx {
+  const KParams* p;
+  const RunArgs* a;
+  float* st;          // trial state block
+  float* sc;          // trial scratch block
+  const double* hp;   // trial hyper-parameters
+  int B;              // rows of the current batch
+  int Breal;          // rows of z_real (cfg batch_size; trainer.py:121)
+  const float* x;     // input spectra rows of the current batch / validation set
+  int xld;
+  uint32_t seed, step_id;
+  int train;          // BN batch statistics + dropout + noise
+  int apply;          // apply optimizer updates
+  int epoch;
+  int trial;
+  float drop_scale[2];     // [0] encoder / decoder, [1] discriminator: 1 / (1 - p), read once per kernel from the hp row
+  uint32_t drop_thresh[2]; // round(p * 65536); 0 = no dropout
+#if RAAE_CLUSTER
+  int crank, csize;        // rank of this CTA in the trial's thread-block cluster / cluster size (ctas_per_trial)
+#else
+  // one CTA per trial (this translation unit): every cluster branch folds away at compile time
+  static constexpr int crank = 0, csize = 1;
+#endif
+};
+
 struct SmemFixed {
   float mean[2][RAAE_MAX_LAYERS][kH];   // per net (E, D) / layer: BN mean used by the current forward
   float inv[2][RAAE_MAX_LAYERS][kH];    // 1/sqrt(var + eps)
@@ -44,6 +72,7 @@ struct SmemFixed {
   double xchgd[2][40];
   float sgp[kH], sgxp[kH];              // this CTA's partial sums behind sg / sgx
   double ktot[4 * kZ];                  // Kendall totals per descriptor: sum |p| over p > 0, -(sum |p| over p < 0), counts
+  Ctx ctx;                              // the kernel's context (see Ctx)
 };
 
 enum StageId { kStBatch = 0, kStFwdWide, kStFwdHidden, kStFwdLatent, kStFwdEncLast, kStBwdWide, kStBwdHidden, kStBwdLatent,
@@ -74,31 +103,6 @@ struct StageTimer {
 #define RAAE_PROBE_INIT() do { } while (0)
 #define RAAE_PROBE(slot) do { } while (0)
 #endif
-
-struct Ctx {
-  const KParams* p;
-  const RunArgs* a;
-  float* st;          // trial state block
-  float* sc;          // trial scratch block
-  const double* hp;   // trial hyper-parameters
-  int B;              // rows of the current batch
-  int Breal;          // rows of z_real (cfg batch_size; trainer.py:121)
-  const float* x;     // input spectra rows of the current batch / validation set
-  int xld;
-  uint32_t seed, step_id;
-  int train;          // BN batch statistics + dropout + noise
-  int apply;          // apply optimizer updates
-  int epoch;
-  int trial;
-  float drop_scale[2];     // [0] encoder / decoder, [1] discriminator: 1 / (1 - p), read once per kernel from the hp row
-  uint32_t drop_thresh[2]; // round(p * 65536); 0 = no dropout
-#if RAAE_CLUSTER
-  int crank, csize;        // rank of this CTA in the trial's thread-block cluster / cluster size (ctas_per_trial)
-#else
-  // one CTA per trial (this translation unit): every cluster branch folds away at compile time
-  static constexpr int crank = 0, csize = 1;
-#endif
-};
 
 // Shared memory is always reached through the `extern __shared__` symbol (never through a pointer stored
 // in a struct) so that the compiler emits LDS/STS with 32-bit addresses instead of generic LD/ST.
