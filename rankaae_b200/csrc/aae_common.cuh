@@ -169,6 +169,43 @@ __device__ __forceinline__ uint32_t mask_keep4(const MaskSrc& m, int row, int c)
          ((w1 & 0xffffu) >= m.thresh ? 4u : 0u) | ((w1 >> 16) >= m.thresh ? 8u : 0u);
 }
 
+// Keep bits of the kTM / 16 row groups a staging thread owns (rows r0 + 16 i of the tile that starts at row0, channels
+// c..c+3): bits [4 i, 4 i + 4).  Rows >= nv read as dropped.  Same draws as mask_keep4; the source of the mask is decided
+// ONCE (one uniform branch) and the hashed path is straight-line code - sixteen independent mixer chains the scheduler can
+// interleave - whereas a mask_keep4 call per row group left a branch diamond per group in the unrolled staging loops and
+// serialised them (two warps per scheduler cannot hide a dependent chain of ~25 integer operations per group).
+__device__ __forceinline__ uint32_t mask_keep4_rows(const MaskSrc& m, int row0, int r0, int c, int nv) {
+  uint32_t bits = 0u;
+  if (m.ptr) {
+    uint32_t w[kTM / 16];
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = r0 + 16 * i;
+      w[i] = r < nv ? *reinterpret_cast<const uint32_t*>(m.ptr + (size_t)(row0 + r) * kH + c) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i)
+      bits |= (((w[i] & 0xffu) ? 1u : 0u) | ((w[i] & 0xff00u) ? 2u : 0u) | ((w[i] & 0xff0000u) ? 4u : 0u) |
+               ((w[i] & 0xff000000u) ? 8u : 0u)) << (4 * i);
+    return bits;
+  }
+  if (m.thresh == 0u) {
+    bits = 0xffffffffu;
+  } else {
+    const uint32_t pair0 = (uint32_t)((row0 + r0) * kH + c) >> 1;
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const uint32_t pair = pair0 + (uint32_t)(i * 16 * kH / 2);
+      const uint32_t w0 = mask_word(m.key, pair), w1 = mask_word(m.key, pair + 1u);
+      bits |= (((w0 & 0xffffu) >= m.thresh ? 1u : 0u) | ((w0 >> 16) >= m.thresh ? 2u : 0u) |
+               ((w1 & 0xffffu) >= m.thresh ? 4u : 0u) | ((w1 >> 16) >= m.thresh ? 8u : 0u)) << (4 * i);
+    }
+  }
+  // rows r0 + 16 i >= nv: groups i >= ceil((nv - r0) / 16)
+  const int nvalid = nv > r0 ? (nv - r0 + 15) >> 4 : 0;
+  return nvalid >= kTM / 16 ? bits : (bits & ((1u << (4 * nvalid)) - 1u));
+}
+
 // ------------------------------------------------------------------------------------------
 // scalar math restated from SURVEY.md Appendix A
 // ------------------------------------------------------------------------------------------

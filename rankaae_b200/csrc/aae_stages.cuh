@@ -428,22 +428,23 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
         if (n0 + kH < N) { prefetch_w_rows64((ci & 1) ? Wc : Wc2, kLD, Wg, n0 + kH, N); cp_async_commit(); }
         mma_nn<kH>(Y + n0, kLDW, Wcur, kLD, acc, ty, tx);
       }
+      // branch-free body (rows >= nv of dv and of the activation tile are zero, their keep bits clear); guarded store
+      const uint32_t kbits = mask_keep4_rows(in.mask, row0, ty, c4, nv);
+      float* const g_dst = c.sc + c.p->sl.g[0] + (size_t)row0 * kH + c4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        int r = ty + 16 * i;
-        if (r < nv) {
-          uint32_t kb = mask_keep4(in.mask, row0 + r, c4);
-          float4 a = *reinterpret_cast<const float4*>(At + r * kLD + c4);
-          float4 gm;
-          gm.x = (kb & 1u) ? acc[i][0] * in.mask.scale : 0.f;
-          gm.y = (kb & 2u) ? acc[i][1] * in.mask.scale : 0.f;
-          gm.z = (kb & 4u) ? acc[i][2] * in.mask.scale : 0.f;
-          gm.w = (kb & 8u) ? acc[i][3] * in.mask.scale : 0.f;
-          sg4[0] += gm.x; sg4[1] += gm.y; sg4[2] += gm.z; sg4[3] += gm.w;
-          sgx4[0] = fmaf(acc[i][0], a.x, sgx4[0]); sgx4[1] = fmaf(acc[i][1], a.y, sgx4[1]);
-          sgx4[2] = fmaf(acc[i][2], a.z, sgx4[2]); sgx4[3] = fmaf(acc[i][3], a.w, sgx4[3]);
-          *reinterpret_cast<float4*>(c.sc + c.p->sl.g[0] + (size_t)(row0 + r) * kH + c4) = gm;
-        }
+        const int r = ty + 16 * i;
+        const uint32_t kb = kbits >> (4 * i);
+        const float4 a = *reinterpret_cast<const float4*>(At + r * kLD + c4);
+        float4 gm;
+        gm.x = (kb & 1u) ? acc[i][0] * in.mask.scale : 0.f;
+        gm.y = (kb & 2u) ? acc[i][1] * in.mask.scale : 0.f;
+        gm.z = (kb & 4u) ? acc[i][2] * in.mask.scale : 0.f;
+        gm.w = (kb & 8u) ? acc[i][3] * in.mask.scale : 0.f;
+        sg4[0] += gm.x; sg4[1] += gm.y; sg4[2] += gm.z; sg4[3] += gm.w;
+        sgx4[0] = fmaf(acc[i][0], a.x, sgx4[0]); sgx4[1] = fmaf(acc[i][1], a.y, sgx4[1]);
+        sgx4[2] = fmaf(acc[i][2], a.z, sgx4[2]); sgx4[3] = fmaf(acc[i][3], a.w, sgx4[3]);
+        if (r < nv) *reinterpret_cast<float4*>(g_dst + (size_t)r * kH) = gm;
       }
       if (RAAE_PROFILE && !RAAE_PROF_FWD && tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) sm->prof[21] += clock64() - q4;
     }
@@ -560,6 +561,11 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
     const MaskSrc mk1 = fake ? mk_fake1 : mk_real1;
     const float label = fake ? 0.f : 1.f;
     const double inv_rows = 1.0 / (double)nrows;
+    // dropout keep bits of this thread's (row group, 4 channels) blocks of both hidden layers: drawn once per tile
+    // (straight-line mixer chains), used by the forward and by the backward passes
+    uint32_t kbits0 = mask_keep4_rows(mk0, row0, ty, c4, nv);
+    uint32_t kbits1 = mask_keep4_rows(mk1, row0, ty, c4, nv);
+    asm volatile("" : "+r"(kbits0), "+r"(kbits1));     // opaque: the bit tests are re-derived where used, not kept in registers
     // ---- input rows (+ input noise, model.py:659-660) ----
     for (int i = tid; i < kTM * kZ; i += kThreads) {
       int r = i >> 3, k = i & 7;
@@ -593,7 +599,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
         const int r = ty + 16 * i;
         const float4 z0 = *reinterpret_cast<const float4*>(Zt + r * kZ);
         const float4 z1 = *reinterpret_cast<const float4*>(Zt + r * kZ + 4);
-        const uint32_t kb = r < nv ? mask_keep4(mk0, row0 + r, c4) : 0u;
+        const uint32_t kb = kbits0 >> (4 * i);
         float u[4], h[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -628,7 +634,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
 #pragma unroll 4
       for (int i = 0; i < kTM / 16; ++i) {
         const int r = ty + 16 * i;
-        const uint32_t kb = r < nv ? mask_keep4(mk1, row0 + r, c4) : 0u;
+        const uint32_t kb = kbits1 >> (4 * i);
         const float4 u = *reinterpret_cast<const float4*>(U2 + r * kLD + c4);
         float4 h;
         h.x = (kb & 1u) ? prelu_f(u.x, a1v.x) * mk1.scale : 0.f;
@@ -679,7 +685,8 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
             const float dl = sm->dlogit[r];
             const float4 h = *reinterpret_cast<const float4*>(H2 + r * kLD + c4);
             const float4 u = *reinterpret_cast<const float4*>(U2 + r * kLD + c4);
-            const uint32_t kb = mask_keep4(mk1, row0 + r, c4);
+            uint32_t kb = kbits1 >> (4 * i);
+            asm volatile("" : "+r"(kb));
 #define RAAE_DU2(comp, idx, bit)                                                         \
             {                                                                            \
               dW2p[idx] = fmaf(dl, h.comp, dW2p[idx]);                                   \
@@ -712,7 +719,8 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
           int r = ty + 16 * i;
           float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
           if (r < nv) {
-            uint32_t kb = mask_keep4(mk0, row0 + r, c4);
+            uint32_t kb = kbits0 >> (4 * i);
+            asm volatile("" : "+r"(kb));
             float4 u = *reinterpret_cast<const float4*>(U1 + r * kLD + c4);
 #define RAAE_DIS(comp, idx, bit)                                             \
             {                                                                \
