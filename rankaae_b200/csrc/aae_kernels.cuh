@@ -68,35 +68,57 @@ __device__ __noinline__ void build_batch(const Ctx& c_ref, const int32_t* __rest
   const int q_per_row = images ? nch64 * 16 : (dim >> 2);                 // float4 quads per row (padded to whole 64-col chunks)
   const int rows_all = csize > 1 ? cl::own_tiles(c.B, crank, csize) * kTM
                      : images ? ((c.B + kTM - 1) / kTM) * kTM : c.B;      // whole tiles: rows >= B are zero-filled
-  for (int i = tid; i < rows_all * q_per_row; i += kThreads) {
-    const int sl = i / q_per_row, c4 = (i - sl * q_per_row) * 4;
-    const int r = csize == 1 ? sl : cl::slot_row(sl, crank, csize);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < c.B && c4 < dim) {
-      const size_t srow = dbg ? (size_t)r : (size_t)idx[r];
-      v = *reinterpret_cast<const float4*>(xsrc + srow * dim + c4);
-      if (sigma != 0.f) {
-        uint32_t e = (uint32_t)(r * kMaxDim + c4);
-        float n0, n1, n2, n3;
-        normal_pair(key, e >> 1, n0, n1);
-        normal_pair(key, (e >> 1) + 1u, n2, n3);
-        v.x += sigma * n0; v.y += sigma * n1; v.z += sigma * n2; v.w += sigma * n3;
-      }
-      *reinterpret_cast<float4*>(xn + (size_t)r * xld + c4) = v;
+  // Four quads per thread and pass: the row indices, then the four gathered loads, are all in flight before the first use
+  // (one quad per pass exposed two dependent memory round trips - index, then row - 256 times per thread and batch).
+  constexpr int U = 4;
+  const int total = rows_all * q_per_row;
+  const int qshift = (q_per_row & (q_per_row - 1)) == 0 ? 31 - __clz(q_per_row) : -1;      // power of two: shift instead of divide
+  for (int i0 = tid; i0 < total; i0 += kThreads * U) {
+    int rr_[U], cc_[U];
+    bool ok_[U];
+    size_t srow_[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * kThreads;
+      const int sl = qshift >= 0 ? (i >> qshift) : i / q_per_row;
+      cc_[u] = (i - sl * q_per_row) * 4;
+      rr_[u] = csize == 1 ? sl : cl::slot_row(sl, crank, csize);
+      ok_[u] = i < total && rr_[u] < c.B && cc_[u] < dim;
+      srow_[u] = ok_[u] ? (dbg ? (size_t)rr_[u] : (size_t)idx[rr_[u]]) : 0;
     }
-    if (images) {
-      const int T = r >> 7, rr = r & 127;
-      if (r < c.B && c4 < dim) {
-        const float4 xr = *reinterpret_cast<const float4*>(sm->bias + c4);
-        v.x -= xr.x; v.y -= xr.y; v.z -= xr.z; v.w -= xr.w;
+    float4 v_[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      v_[u] = ok_[u] ? *reinterpret_cast<const float4*>(xsrc + srow_[u] * dim + cc_[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * kThreads, r = rr_[u], c4 = cc_[u];
+      if (i >= total) break;
+      float4 v = v_[u];
+      if (ok_[u]) {
+        if (sigma != 0.f) {
+          uint32_t e = (uint32_t)(r * kMaxDim + c4);
+          float n0, n1, n2, n3;
+          normal_pair(key, e >> 1, n0, n1);
+          normal_pair(key, (e >> 1) + 1u, n2, n3);
+          v.x += sigma * n0; v.y += sigma * n1; v.z += sigma * n2; v.w += sigma * n3;
+        }
+        *reinterpret_cast<float4*>(xn + (size_t)r * xld + c4) = v;
       }
-      // raw fp32 in the operand layout: the consumers split it into rounded hi / lo planes in shared memory, so the
-      // batch crosses HBM once per consumer
-      float* bk = xk + (size_t)(T * nch64 + (c4 >> 6)) * 8192;
-      *reinterpret_cast<float4*>(reinterpret_cast<char*>(bk) + tc::sw128_chunk_off(rr, c4 & 63, tc::kABlockBytes)) = v;
-      if (c4 < nch128 * 128) {
-        float* bm = xm + (size_t)(T * nch128 + (c4 >> 7)) * 16384;
-        *reinterpret_cast<float4*>(reinterpret_cast<char*>(bm) + tc::sw128_32b_chunk_off(rr, c4 & 127, tc::kABlockBytes)) = v;
+      if (images) {
+        const int T = r >> 7, rr = r & 127;
+        if (ok_[u]) {
+          const float4 xr = *reinterpret_cast<const float4*>(sm->bias + c4);
+          v.x -= xr.x; v.y -= xr.y; v.z -= xr.z; v.w -= xr.w;
+        }
+        // raw fp32 in the operand layout: the consumers split it into rounded hi / lo planes in shared memory, so the
+        // batch crosses HBM once per consumer
+        float* bk = xk + (size_t)(T * nch64 + (c4 >> 6)) * 8192;
+        *reinterpret_cast<float4*>(reinterpret_cast<char*>(bk) + tc::sw128_chunk_off(rr, c4 & 63, tc::kABlockBytes)) = v;
+        if (c4 < nch128 * 128) {
+          float* bm = xm + (size_t)(T * nch128 + (c4 >> 7)) * 16384;
+          *reinterpret_cast<float4*>(reinterpret_cast<char*>(bm) + tc::sw128_32b_chunk_off(rr, c4 & 127, tc::kABlockBytes)) = v;
+        }
       }
     }
   }

@@ -406,9 +406,12 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
     if (want_bwd) {
       // db, dW += dv^T a, g = (dv @ W) * dropout
       {
-        float s = dbp;
-        for (int r = 0; r < kTM; ++r) s += Y[r * kLDW + tid];
-        dbp = s;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // four independent chains instead of 128 dependent additions
+#pragma unroll 4
+        for (int r = 0; r < kTM; r += 4) {
+          s0 += Y[r * kLDW + tid]; s1 += Y[(r + 1) * kLDW + tid]; s2 += Y[(r + 2) * kLDW + tid]; s3 += Y[(r + 3) * kLDW + tid];
+        }
+        dbp += (s0 + s1) + (s2 + s3);
       }
       const long long q3 = RAAE_PROFILE ? clock64() : 0ll;
       mma_tn8(Y, kLDW, 8 * (tid >> 3), At, kLD, 8 * (tid & 7), 0, kTM, accW);

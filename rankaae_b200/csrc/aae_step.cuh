@@ -1346,18 +1346,23 @@ __device__ __noinline__ void fwd_enc_last(const Ctx& c_ref, const LayerIn& in_re
     const int row0 = t * kTM, nv = min(kTM, c.B - row0);
     build_act_tile(At, in.src, row0, nv, sm->mean[in.snet][in.slayer], sm->inv[in.snet][in.slayer], in.slope, in.mask);
     __syncthreads();
-    for (int o = tid; o < kTM * kZ; o += kThreads) {
-      int r = o >> 3, n = o & 7;
-      if (r < nv) {
-        float acc = sm->bias[n];
+    {
+      // thread (row r = tid / 2, latents n0 = 4 (tid & 1) .. + 3): one pass over the activation row feeds four independent
+      // accumulation chains (the chain order over k is the one of a single accumulator per output, as before); float4 store
+      const int r = tid >> 1, n0 = (tid & 1) * 4;
+      float acc[4] = {sm->bias[n0], sm->bias[n0 + 1], sm->bias[n0 + 2], sm->bias[n0 + 3]};
 #pragma unroll 4
-        for (int k = 0; k < kH; k += 4) {
-          float4 a = *reinterpret_cast<const float4*>(At + r * kLD + k);
-          float4 w = *reinterpret_cast<const float4*>(Ws + n * kLD + k);
-          acc = fmaf(a.x, w.x, acc); acc = fmaf(a.y, w.y, acc); acc = fmaf(a.z, w.z, acc); acc = fmaf(a.w, w.w, acc);
+      for (int k = 0; k < kH; k += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(At + r * kLD + k);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(Ws + (n0 + j) * kLD + k);
+          acc[j] = fmaf(a.x, w.x, acc[j]); acc[j] = fmaf(a.y, w.y, acc[j]); acc[j] = fmaf(a.z, w.z, acc[j]); acc[j] = fmaf(a.w, w.w, acc[j]);
         }
-        zE[(size_t)(row0 + r) * kZ + n] = n < ns ? acc : 0.f;
       }
+      if (r < nv)
+        *reinterpret_cast<float4*>(zE + (size_t)(row0 + r) * kZ + n0) =
+            make_float4(n0 < ns ? acc[0] : 0.f, n0 + 1 < ns ? acc[1] : 0.f, n0 + 2 < ns ? acc[2] : 0.f, n0 + 3 < ns ? acc[3] : 0.f);
     }
     __syncthreads();
   }

@@ -3,7 +3,7 @@
 // Operands are staged in shared memory in the canonical K-major SWIZZLE_128B layout and described to the tensor
 // core by 64-bit matrix descriptors; the FP32 accumulator (128 lanes x 64 columns) lives in tensor memory (TMEM)
 // and is read back with tcgen05.ld.  FP32 accuracy is kept with the 3 x TF32 error-compensated split
-//   a b ~= a_hi b_hi + a_lo b_hi + a_hi b_lo,     x_hi = x with the 13 low mantissa bits cleared, x_lo = x - x_hi
+//   a b ~= a_hi b_hi + a_lo b_hi + a_hi b_lo,     x_hi = x rounded to TF32 (nearest), x_lo = x - x_hi
 // (single-pass TF32 fails parity on these networks: SURVEY.md Appendix D-6).
 //
 // Bit layouts follow cute/arch/mma_sm100_desc.hpp (UMMA::SmemDescriptor / UMMA::InstrDescriptor) of the CUTLASS
@@ -133,9 +133,14 @@ __device__ __forceinline__ uint32_t sw128_chunk_off(int row, int k, int block_by
 __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
+// The low half is handed to the tensor core as the exact FP32 residual x - hi (so hi + lo == x bit for bit) and the hardware
+// truncates it to TF32 itself: |x - hi| <= 2^-11 |x|, the truncation drops at most 2^-10 of that, and because hi was ROUNDED
+// the residual - and with it the truncation error - has a random sign (truncating x itself is what adds up coherently).
+// Two integer instructions per element less than rounding the residual as well; the dropped term stays at the level of the
+// lo x lo product the 3 x TF32 scheme omits anyway (2^-22 |x|).
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
   hi = tf32_rna(x);
-  lo = tf32_rna(x - hi);
+  lo = x - hi;
 }
 __device__ __forceinline__ void split_store(float* hi_base, float* lo_base, uint32_t off_bytes, float4 v) {
   float4 h, l;
