@@ -399,6 +399,7 @@ __device__ __forceinline__ void bitonic_sort(float* key, int* idx, int npad) {
 __device__ __noinline__ void latent_metrics(const Ctx& c_ref) {
   const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
   RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStBatch]);      // the validation kernel builds no batch: slot 0 is free there
   const KParams& p = *c.p;
   const int n = c.B, ns = p.cfg.nstyle, tid = threadIdx.x;
   const int lE = p.lay.net[kE].n_linear - 1;
@@ -510,6 +511,10 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
   Ctx& c = sm->ctx;                      // one copy per CTA in shared memory: thread 0 writes, a barrier publishes
   const int tid = threadIdx.x, ns = p.cfg.nstyle, K = p.cfg.n_aux;
   const int LE = p.lay.net[kE].n_linear;
+#ifdef RAAE_PROFILE_VAL
+  const long long t_start_val = clock64();
+  if (tid < 32) sm->prof[tid] = 0;
+#endif
   if (tid == 0) {
     init_ctx(c, p, a, trial);
     c.train = 0;
@@ -606,6 +611,15 @@ raae_val_kernel(const __grid_constant__ KParams p, const __grid_constant__ RunAr
       plateau_step(c, combined);
     }
   }
+#ifdef RAAE_PROFILE_VAL
+  // profiling builds only: stage cycles of the validation block in a SECOND [n_trials][32] block behind the train kernel's
+  // (tools/stage_profile.py allocates both); slot 0 = latent_metrics, slot 15 = whole kernel
+  if (a.prof && tid == 0 && c.crank == 0) {
+    long long* vp = a.prof + ((size_t)p.cfg.n_trials + trial) * 32;
+    for (int i = 0; i < 15; ++i) vp[i] += sm->prof[i];
+    vp[15] += clock64() - t_start_val;
+  }
+#endif
   tc_teardown(p, sm);
 }
 

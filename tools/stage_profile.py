@@ -29,11 +29,22 @@ for t in range(T):
 eng.bind_dataset(*synthetic_arrays())
 eng.train_epochs(0, 2)
 torch.cuda.synchronize()
-prof = torch.zeros(T, 32, dtype=torch.int64, device="cuda:0")
+VAL = bool(os.environ.get("RAAE_PROFILE_VAL"))      # build with RAAE_NVCC_EXTRA="-DRAAE_PROFILE_VAL=1": second block = validation kernel
+prof = torch.zeros(2 * T if VAL else T, 32, dtype=torch.int64, device="cuda:0")
 L.check(eng.lib.raae_set_profile_buffer(eng.handle, prof.data_ptr()))
 eng.train_epochs(2, E)
 torch.cuda.synchronize()
-p = prof.cpu().numpy().astype(np.float64) / (E * 5)          # cycles per train step
+p_all = prof.cpu().numpy().astype(np.float64)
+p = p_all[:T] / (E * 5)          # cycles per train step
+if VAL:
+    pv = p_all[T:] / E           # cycles per validation block
+    vnames = list(names)
+    vnames[0] = "latent_metrics"
+    print(f"validation kernel: {pv[:, 15].mean()/1e6:.3f} Mcycles per epoch per trial")
+    for i, n in enumerate(vnames[:15]):
+        if pv[:, i].mean() > 0:
+            print(f"  val {n:22s} {pv[:, i].mean()/1e3:10.1f} kcyc  {100*pv[:, i].mean()/pv[:, 15].mean():5.1f}%")
+    print(f"  val {'(unaccounted)':22s} {(pv[:, 15].mean() - pv[:, :15].sum(1).mean())/1e3:10.1f} kcyc")
 tot = p[:, 15].mean()
 print(f"trials {T}: {tot/1e6:.3f} Mcycles per step per trial (mean over trials), calls per step in brackets")
 calls = [1, 6, 34, 4, 6, 4, 21, 3, 4, 2, 1, 1, 1, 1, 1, 1]
