@@ -77,8 +77,9 @@ typedef struct raae_config {
   int32_t tensor_cores;        /* contractions on tcgen05 (kind::tf32, 3 x TF32 round-to-nearest split, TMEM accumulators): bit 0
                                   hidden-block forward, bit 1 hidden-block backward, bit 2 input block of the encoder on the batch
                                   (forward + weight gradient from operand images in scratch, streamed with bulk copies; also the
-                                  re-encoding pass of the MI phase), bit 4 decoder output forward; bit 3 is unused; 0 = everything as
-                                  FP32 FMA */
+                                  re-encoding pass of the MI phase), bit 4 decoder output forward, bit 5 decoder output backward (input
+                                  gradient and weight gradient, the loss-gradient tile parked in tensor memory); bit 3 is unused;
+                                  0 = everything as FP32 FMA */
   int32_t reserved[2];
 } raae_config;
 

@@ -18,8 +18,17 @@ enum LastMode { kLastRecon = 0, kLastSmooth = 1, kLastStoreV = 2, kLastFromDv = 
 //   kLastEval  : plain-MSE reconstruction and smoothness losses only (validation, trainer.py:223-239)
 // Losses land in sm->loss_acc[kRecon] / [kSmooth].
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int o) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+// TCB: the backward contractions (g = dv W, dW = dv^T a) run on tcgen05 as well (config tensor_cores bit 5).  The 128 x 256
+// gradient tile cannot share the 227 KB of shared memory with its hi / lo operand planes, so it is parked in TENSOR MEMORY
+// (the 256 accumulator columns of the forward product, free once v has been copied out) and re-read slab by slab:
+//   g  (TMEM columns 256..319) += dv[:, 64 s ..] W[64 s .., :]   per 64-column slab, dv slab staged K-major hi / lo, W^T slab by bulk copy
+//   dW (TMEM columns 320..447, kept over the whole batch)        per 128-column half, dv half staged MN-major as ONE plane at a
+//                                                                 time (hi: x a_hi, x a_lo; then lo: x a_hi), a staged MN-major hi / lo
+// All staging goes through one 64 KB buffer, so the six passes of a tile are serial; they still cost less than half of the
+// FP32-FMA contractions they replace.
+template <bool TCB>
+__device__ __noinline__ void dec_last_t(const Ctx& c_ref, int mode, int inst, int o) {
+  const Ctx c = c_ref;                 // register copy of the kernel context (shared memory)
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[mode == kLastStoreV ? kStDecLastStoreV : mode == kLastFromDv ? kStDecLastFromDv : kStDecLastLoss]);
   const raae_net_layout& nl = NL(c, kD);
@@ -62,11 +71,42 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
     }
     tc::fence_async_all();
   }
+  // ---- tcgen05 backward (TCB): buffers, barriers, W^T image ----
+  float* const Xb = Y;                      // 16384 floats: K-major hi | lo of a 64-column slab of dv, or ONE MN-major plane of a 128-column half
+  float* const Phi = Y + 16384;             // activations a, MN-major (B operand of dW): [2 blocks][128 rows][32] hi ...
+  float* const Plo = Phi + tc::kATileFloats; // ... and lo
+  float* const Wtb = Wc;                    // [hi 4096 | lo 4096] W^T slab (B operand of g); Wc + the row buffers = 35 KB, 1 KB aligned
+  float* const wt = c.sc + c.p->sl.wk;      // its image in global scratch: the encoder's input-weight image is rebuilt by every stage that uses it
+  uint64_t* const wtfull = reinterpret_cast<uint64_t*>(&sm->pipe_bar[5]);   // W^T slab landed
+  uint64_t* const bdone = reinterpret_cast<uint64_t*>(&sm->pipe_bar[6]);    // MMA batch of the backward completed
+  uint32_t n_wt = 0u, n_bd = 0u;            // completed phases seen
+  const bool leader = tc::warp_uniform_id() == 0;
+  const int erow = 32 * (warp & 3) + lane, eh = warp >> 2;                  // TMEM ownership: lane (row), column half
+  const uint32_t trow = (uint32_t)(32 * (warp & 3)) << 16;
+  if (TCB) {
+    if (tid == 0) { tc::mbar_init(wtfull, 1); tc::mbar_init(bdone, 1); }
+    // element (row k, column c) of slab c >> 6 = W[c][k]: K-major hi / lo image of W^T, one [hi 4096 | lo 4096] block per 64 output columns
+    for (int i = tid; i < nchN * kH * 16; i += kThreads) {
+      const int cc = i >> 4, k4 = (i & 15) * 4;
+      const float4 w = cc < N ? *reinterpret_cast<const float4*>(Wg + (size_t)cc * kH + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+      float* blk = wt + (size_t)(cc >> 6) * 8192;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float h, lo;
+        tc::tf32_split(wv[j], h, lo);
+        const uint32_t off = tc::sw128_chunk_off(k4 + j, (cc & 63) & ~3, tc::kBBlockBytes) + (uint32_t)((cc & 3) * 4);
+        *reinterpret_cast<float*>(reinterpret_cast<char*>(blk) + off) = h;
+        *reinterpret_cast<float*>(reinterpret_cast<char*>(blk + 4096) + off) = lo;
+      }
+    }
+    tc::fence_async_all();
+  }
   __syncthreads();
   uint32_t n_acc = 0u;                      // completed phases of accfull seen
-  float accW[8][8];
+  float accW[TCB ? 1 : 8][8];               // FP32-FMA path: this thread's 8 x 8 block of dW over the whole batch
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < (TCB ? 1 : 8); ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) accW[i][j] = 0.f;
   float dbp = 0.f;
@@ -413,11 +453,121 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
         }
         dbp += (s0 + s1) + (s2 + s3);
       }
+      float acc[8][4];
+      long long q4 = 0ll;
+      if constexpr (TCB) {
+        // ---- dv: shared memory -> TMEM columns [0, 256): thread = row (TMEM lane), column half eh ----
+        if (leader && tc::elect_one()) {                 // first W^T slab: lands behind the copy and the first staging pass
+          tc::mbar_expect_tx(wtfull, 32768u);
+          tc::bulk_g2s(Wtb, wt, 32768u, wtfull);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int col0 = 128 * eh + 32 * q4;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(Y + erow * kLDW + col0 + j);
+            v[j] = t4.x; v[j + 1] = t4.y; v[j + 2] = t4.z; v[j + 3] = t4.w;
+          }
+          tc::tmem_st32(d_tmem + trow + (uint32_t)col0, v);
+        }
+        tc::tmem_wait_st();
+        tc::fence_before_sync();
+        __syncthreads();                                 // every row of dv is in TMEM: the Y area becomes the operand buffers
+        tc::fence_after_sync();
+        // a -> MN-major hi / lo (this thread's (ty, c4) chunks); rows >= nv of the activation tile are zero
+        {
+          const uint32_t offM = tc::sw128_32b_chunk_off(ty, c4, tc::kABlockBytes);
+#pragma unroll
+          for (int i = 0; i < kTM / 16; ++i)
+            tc::split_store(Phi, Plo, offM + (uint32_t)(i * 16 * 128), *reinterpret_cast<const float4*>(At + (ty + 16 * i) * kLD + c4));
+        }
+        // ---- g += dv[:, 64 s ..] W[64 s .., :]: slab staged K-major hi / lo from TMEM (row erow, columns 64 s + 32 eh ..) ----
+        for (int s2 = 0; s2 < nchN; ++s2) {
+          {
+            float v[32];
+            tc::tmem_ld32(d_tmem + trow + (uint32_t)(64 * s2 + 32 * eh), v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              tc::split_store(Xb, Xb + tc::kATileFloats, tc::sw128_chunk_off(erow, 32 * eh + j, tc::kABlockBytes),
+                              make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          }
+          tc::fence_async_smem();
+          tc::fence_before_sync();
+          __syncthreads();
+          if (leader && tc::elect_one()) {
+            tc::mbar_wait(wtfull, n_wt & 1u);
+            tc::fence_after_sync();
+            tc::issue_gemm_3xtf32_acc(d_tmem + 256u, Xb, Xb + tc::kATileFloats, Wtb, Wtb + 4096, s2 > 0 ? 1u : 0u);
+            tc::mma_commit(bdone);
+          }
+          ++n_wt;
+          tc::mbar_wait(bdone, n_bd & 1u);
+          ++n_bd;
+          if (s2 + 1 < nchN && leader && tc::elect_one()) {   // the slab buffer is free again
+            tc::mbar_expect_tx(wtfull, 32768u);
+            tc::bulk_g2s(Wtb, wt + (size_t)(s2 + 1) * 8192, 32768u, wtfull);
+          }
+        }
+        // ---- dW[128 h ..][:] += dv[:, 128 h ..]^T a: the half staged MN-major, its rounded hi plane first (x a_hi, x a_lo),
+        //      then the residual plane (x a_hi); thread (erow, eh) owns columns 128 h + 64 eh .. + 63 (blocks 2 eh, 2 eh + 1) ----
+        for (int h2 = 0; h2 < (nchN + 1) / 2; ++h2) {
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+            for (int b2 = 0; b2 < 2; ++b2) {
+              float v[32];
+              tc::tmem_ld32(d_tmem + trow + (uint32_t)(128 * h2 + 64 * eh + 32 * b2), v);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 hi4, lo4;
+                tc::tf32_split(v[j], hi4.x, lo4.x);
+                tc::tf32_split(v[j + 1], hi4.y, lo4.y);
+                tc::tf32_split(v[j + 2], hi4.z, lo4.z);
+                tc::tf32_split(v[j + 3], hi4.w, lo4.w);
+                *reinterpret_cast<float4*>(reinterpret_cast<char*>(Xb) + tc::sw128_32b_chunk_off(erow, 64 * eh + 32 * b2 + j, tc::kABlockBytes)) =
+                    pass == 0 ? hi4 : lo4;
+              }
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            __syncthreads();
+            if (leader && tc::elect_one()) {
+              tc::fence_after_sync();
+              const uint32_t dW_t = d_tmem + 320u + (uint32_t)(64 * h2);
+              if (pass == 0) {
+                tc::issue_gemm_tn128_pass(dW_t, Xb, tc::kABlockBytes, Phi, tc::kABlockBytes, it > 0 ? 1u : 0u);
+                tc::issue_gemm_tn128_pass(dW_t, Xb, tc::kABlockBytes, Plo, tc::kABlockBytes, 1u);
+              } else {
+                tc::issue_gemm_tn128_pass(dW_t, Xb, tc::kABlockBytes, Phi, tc::kABlockBytes, 1u);
+              }
+              tc::mma_commit(bdone);
+            }
+            tc::mbar_wait(bdone, n_bd & 1u);
+            ++n_bd;
+          }
+        }
+        // ---- g: accumulator -> shared memory (the staging buffer is free) in the (ty, c4) ownership of the epilogue ----
+        {
+          float v[32];
+          tc::fence_after_sync();
+          tc::tmem_ld32(d_tmem + trow + (uint32_t)(256 + 32 * eh), v);
+          tc::fence_before_sync();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(Xb + erow * kLD + 32 * eh + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 g4 = *reinterpret_cast<const float4*>(Xb + (ty + 16 * i) * kLD + c4);
+          acc[i][0] = g4.x; acc[i][1] = g4.y; acc[i][2] = g4.z; acc[i][3] = g4.w;
+        }
+      } else {
       const long long q3 = RAAE_PROFILE ? clock64() : 0ll;
       mma_tn8(Y, kLDW, 8 * (tid >> 3), At, kLD, 8 * (tid & 7), 0, kTM, accW);
-      const long long q4 = RAAE_PROFILE ? clock64() : 0ll;
+      q4 = RAAE_PROFILE ? clock64() : 0ll;
       if (RAAE_PROFILE && !RAAE_PROF_FWD && tid == 0 && (mode == kLastRecon || mode == kLastSmooth)) { sm->prof[19] += q3 - q2; sm->prof[20] += q4 - q3; }
-      float acc[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -430,6 +580,7 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
         __syncthreads();
         if (n0 + kH < N) { prefetch_w_rows64((ci & 1) ? Wc : Wc2, kLD, Wg, n0 + kH, N); cp_async_commit(); }
         mma_nn<kH>(Y + n0, kLDW, Wcur, kLD, acc, ty, tx);
+      }
       }
       // branch-free body (rows >= nv of dv and of the activation tile are zero, their keep bits clear); guarded store
       const uint32_t kbits = mask_keep4_rows(in.mask, row0, ty, c4, nv);
@@ -473,12 +624,30 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
     if (tid < kH) { float s = 0.f; for (int i = 0; i < 16; ++i) s += sm->red[i][tid]; sgx_dst[tid] = s; }
     float* gradW = Y;            // dense [N][64]
     float* gradb = Y + N * kH;   // [N], right behind dW: [W | b] is one run of the parameter vector
-    const int m0 = 8 * (tid >> 3), n0 = 8 * (tid & 7);
+    if constexpr (TCB) {
+      // TMEM columns 320 + 64 h ..: D[lane = output column 128 h + lane][k] (identity row map); a CTA without rows contributes zeros
+      const bool any_tile = has_tiles(c, ntiles);
+      tc::fence_after_sync();
+      for (int h2 = 0; h2 < (nchN + 1) / 2; ++h2) {
+        float v[32];
+        tc::tmem_ld32(d_tmem + trow + (uint32_t)(320 + 64 * h2 + 32 * eh), v);
+        const int cc = 128 * h2 + erow;
+        if (cc < N) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(gradW + cc * kH + 32 * eh + j) =
+                any_tile ? make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      tc::fence_before_sync();
+    } else {
+      const int m0 = 8 * (tid >> 3), n0 = 8 * (tid & 7);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (m0 + i < N) gradW[(m0 + i) * kH + n0 + j] = accW[i][j];
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (m0 + i < N) gradW[(m0 + i) * kH + n0 + j] = accW[i][j];
+    }
     if (tid < N) gradb[tid] = dbp;
     __syncthreads();
     if (c.csize > 1) { cl::sync(); cluster_gather_sg(c, sm); }
@@ -486,6 +655,12 @@ __device__ __noinline__ void dec_last(const Ctx& c_ref, int mode, int inst, int 
     stage_sync(c);
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void dec_last(const Ctx& c, int mode, int inst, int o) {
+  const bool bwd = mode == kLastRecon || mode == kLastSmooth || mode == kLastFromDv;
+  if (bwd && (c.p->cfg.tensor_cores & 32)) dec_last_t<true>(c, mode, inst, o);
+  else dec_last_t<false>(c, mode, inst, o);
 }
 
 // ------------------------------------------------------------------------------------------

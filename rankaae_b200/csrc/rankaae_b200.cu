@@ -44,8 +44,8 @@ int validate_config(const raae_config& c) {
   if (c.max_rows < c.batch_size) return fail(-1, "max_rows must be >= batch_size");
   if (c.ctas_per_trial != 1 && c.ctas_per_trial != 2 && c.ctas_per_trial != 4 && c.ctas_per_trial != RAAE_MAX_CTAS)
     return fail(-1, "ctas_per_trial must be 1, 2, 4 or 8 (thread-block cluster size per trial)");
-  if (c.tensor_cores & ~0x17)
-    return fail(-1, "tensor_cores: bits 0 (hidden forward), 1 (hidden backward), 2 (input block from operand images), 4 (decoder output forward) are implemented");
+  if (c.tensor_cores & ~0x37)
+    return fail(-1, "tensor_cores: bits 0 (hidden forward), 1 (hidden backward), 2 (input block from operand images), 4 (decoder output forward), 5 (decoder output backward) are implemented");
   return 0;
 }
 

@@ -13,9 +13,9 @@ from . import _lib as L
 ADAMW_DEFAULT_WD = 1e-2
 # contractions on tcgen05 (3 x TF32 round-to-nearest split, fp32-grade: the parity suite passes in every mode): bit 0
 # hidden-block forward, bit 1 hidden-block backward, bit 2 encoder input block from the batch / MI-phase operand images,
-# bit 4 decoder output forward; `tensor_cores: 0` in the config (or RAAE_TENSOR_CORES=0)
-# selects the all-FP32-FMA path
-DEFAULT_TENSOR_CORES = 23
+# bit 4 decoder output forward, bit 5 decoder output backward (the gradient tile parked in tensor memory); `tensor_cores: 0`
+# in the config (or RAAE_TENSOR_CORES=0) selects the all-FP32-FMA path
+DEFAULT_TENSOR_CORES = 55
 
 
 def optimizer_hparams(cfg):

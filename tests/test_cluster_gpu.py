@@ -69,7 +69,7 @@ def test_cluster_golden_parity_and_validation(ctas):
         eng.close()
 
 
-@pytest.mark.parametrize("tensor_cores", [23, 0], ids=["tcgen05", "fp32fma"])
+@pytest.mark.parametrize("tensor_cores", [55, 0], ids=["tcgen05", "fp32fma"])
 @pytest.mark.parametrize("ctas", CLUSTERS)
 def test_cluster_fullsize_phase_parity(ctas, tensor_cores):
     """BASELINE configs[1] batches: 1024 rows (one tile per CTA at 8 CTAs) and the ragged 804 (the last CTA of 8 owns no

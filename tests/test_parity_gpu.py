@@ -136,7 +136,7 @@ EXAMPLE = dict(
     use_flex_spec_target=True, weight_decay=0.01, kendall_activation=True, epoch_stop_smooth=1500)
 
 
-@pytest.fixture(scope="module", params=[23, 7, 0], ids=["tcgen05", "tcgen05-hidden+input", "fp32fma"])
+@pytest.fixture(scope="module", params=[55, 23, 7, 0], ids=["tcgen05", "tcgen05-fma-dec-bwd", "tcgen05-hidden+input", "fp32fma"])
 def example_engine(request, torch_cuda):
     """Both contraction back ends: tcgen05 3xTF32 (default) and the all-FP32-FMA path."""
     eng = _engine(dict(EXAMPLE, tensor_cores=request.param), max_rows=1056)
