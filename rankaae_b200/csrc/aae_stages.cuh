@@ -511,42 +511,50 @@ __device__ __noinline__ void dec_last_t(const Ctx& c_ref, int mode, int inst, in
           }
         }
         // ---- dW[128 h ..][:] += dv[:, 128 h ..]^T a: the half staged MN-major, its rounded hi plane first (x a_hi, x a_lo),
-        //      then the residual plane (x a_hi); thread (erow, eh) owns columns 128 h + 64 eh .. + 63 (blocks 2 eh, 2 eh + 1) ----
+        //      then the residual plane (x a_hi); thread (erow, eh) owns columns 128 h + 64 eh .. + 63 (blocks 2 eh, 2 eh + 1).
+        //      The half is read from TMEM once; the residual plane is formed in registers while the MMAs of the hi plane run ----
         for (int h2 = 0; h2 < (nchN + 1) / 2; ++h2) {
+          float v0[32], v1[32];
+          tc::tmem_ld32(d_tmem + trow + (uint32_t)(128 * h2 + 64 * eh), v0);
+          tc::tmem_ld32(d_tmem + trow + (uint32_t)(128 * h2 + 64 * eh + 32), v1);
+          const uint32_t dW_t = d_tmem + 320u + (uint32_t)(64 * h2);
+          char* const xb0 = reinterpret_cast<char*>(Xb);
 #pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-            for (int b2 = 0; b2 < 2; ++b2) {
-              float v[32];
-              tc::tmem_ld32(d_tmem + trow + (uint32_t)(128 * h2 + 64 * eh + 32 * b2), v);
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 hi4, lo4;
-                tc::tf32_split(v[j], hi4.x, lo4.x);
-                tc::tf32_split(v[j + 1], hi4.y, lo4.y);
-                tc::tf32_split(v[j + 2], hi4.z, lo4.z);
-                tc::tf32_split(v[j + 3], hi4.w, lo4.w);
-                *reinterpret_cast<float4*>(reinterpret_cast<char*>(Xb) + tc::sw128_32b_chunk_off(erow, 64 * eh + 32 * b2 + j, tc::kABlockBytes)) =
-                    pass == 0 ? hi4 : lo4;
-              }
-            }
-            tc::fence_async_smem();
-            tc::fence_before_sync();
-            __syncthreads();
-            if (leader && tc::elect_one()) {
-              tc::fence_after_sync();
-              const uint32_t dW_t = d_tmem + 320u + (uint32_t)(64 * h2);
-              if (pass == 0) {
-                tc::issue_gemm_tn128_pass(dW_t, Xb, tc::kABlockBytes, Phi, tc::kABlockBytes, it > 0 ? 1u : 0u);
-                tc::issue_gemm_tn128_pass(dW_t, Xb, tc::kABlockBytes, Plo, tc::kABlockBytes, 1u);
-              } else {
-                tc::issue_gemm_tn128_pass(dW_t, Xb, tc::kABlockBytes, Phi, tc::kABlockBytes, 1u);
-              }
-              tc::mma_commit(bdone);
-            }
-            tc::mbar_wait(bdone, n_bd & 1u);
-            ++n_bd;
+          for (int j = 0; j < 32; j += 4) {
+            float4 h0, h1;
+            h0.x = tc::tf32_rna(v0[j]); h0.y = tc::tf32_rna(v0[j + 1]); h0.z = tc::tf32_rna(v0[j + 2]); h0.w = tc::tf32_rna(v0[j + 3]);
+            h1.x = tc::tf32_rna(v1[j]); h1.y = tc::tf32_rna(v1[j + 1]); h1.z = tc::tf32_rna(v1[j + 2]); h1.w = tc::tf32_rna(v1[j + 3]);
+            *reinterpret_cast<float4*>(xb0 + tc::sw128_32b_chunk_off(erow, 64 * eh + j, tc::kABlockBytes)) = h0;
+            *reinterpret_cast<float4*>(xb0 + tc::sw128_32b_chunk_off(erow, 64 * eh + 32 + j, tc::kABlockBytes)) = h1;
+            v0[j] -= h0.x; v0[j + 1] -= h0.y; v0[j + 2] -= h0.z; v0[j + 3] -= h0.w;       // exact residuals
+            v1[j] -= h1.x; v1[j + 1] -= h1.y; v1[j + 2] -= h1.z; v1[j + 3] -= h1.w;
           }
+          tc::fence_async_smem();
+          tc::fence_before_sync();
+          __syncthreads();
+          if (leader && tc::elect_one()) {
+            tc::fence_after_sync();
+            tc::issue_gemm_tn128_pass(dW_t, Xb, tc::kABlockBytes, Phi, tc::kABlockBytes, it > 0 ? 1u : 0u);
+            tc::issue_gemm_tn128_pass(dW_t, Xb, tc::kABlockBytes, Plo, tc::kABlockBytes, 1u);
+            tc::mma_commit(bdone);
+          }
+          tc::mbar_wait(bdone, n_bd & 1u);
+          ++n_bd;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            *reinterpret_cast<float4*>(xb0 + tc::sw128_32b_chunk_off(erow, 64 * eh + j, tc::kABlockBytes)) = make_float4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+            *reinterpret_cast<float4*>(xb0 + tc::sw128_32b_chunk_off(erow, 64 * eh + 32 + j, tc::kABlockBytes)) = make_float4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
+          }
+          tc::fence_async_smem();
+          tc::fence_before_sync();
+          __syncthreads();
+          if (leader && tc::elect_one()) {
+            tc::fence_after_sync();
+            tc::issue_gemm_tn128_pass(dW_t, Xb, tc::kABlockBytes, Phi, tc::kABlockBytes, 1u);
+            tc::mma_commit(bdone);
+          }
+          tc::mbar_wait(bdone, n_bd & 1u);
+          ++n_bd;
         }
         // ---- g: accumulator -> shared memory (the staging buffer is free) in the (ty, c4) ownership of the epilogue ----
         {

@@ -1,10 +1,10 @@
 #!/bin/bash
 # Quick iteration run on one B200 (under gpurun): GPU parity tests, a short bench of the ensemble kernel and of the single
-# trial, and the in-kernel stage timers.  usage: tools/quick_check.sh TAG [pytest-args]
+# trial, and the in-kernel stage timers.  usage: tools/quick_check.sh TAG [pytest -k expression]
 TAG=${1:-q}
 O=gpurun_out
 mkdir -p $O
-python -m pytest tests -m gpu -x -q ${2:-} > $O/pytest_$TAG.log 2>&1; echo "pytest rc $?" ; tail -3 $O/pytest_$TAG.log
+python -m pytest tests -m gpu -x -q ${2:+-k "$2"} > $O/pytest_$TAG.log 2>&1; echo "pytest rc $?" ; tail -3 $O/pytest_$TAG.log
 python bench.py --steps 6 --warmup 3 --no-cpu --no-configs --no-peak > $O/bench_$TAG.json 2> $O/bench_$TAG.err; echo "bench rc $?"
 python - <<PY
 import json
