@@ -213,18 +213,20 @@ __device__ __forceinline__ float prelu_f(float u, float a) { return u > 0.f ? u 
 
 // nn.Softplus(beta=2, threshold=20): model.py:535.  softplus(x) = max(x, 0) + log1p(exp(-|x|)) keeps the
 // argument of the logarithm in (1, 2], where the hardware exp/log pair is accurate to ~1e-7 absolute.
+// Branch-free: beyond the threshold (2 v > 20) exp(-2 v) < 2.1e-9 vanishes against 1 in float32, so the same expression
+// returns 0.5 * (2 v + 0) = v exactly, which is what the thresholded module returns.  (Written as `bv > 20 ? v : ...` it
+// compiled into a branch diamond per element that serialised the eight elements of a row-pass iteration.)
 __device__ __forceinline__ float softplus2_f(float v) {
   float bv = 2.f * v;
-  return bv > 20.f ? v : 0.5f * (fmaxf(bv, 0.f) + __logf(1.f + __expf(-fabsf(bv))));
+  return 0.5f * (fmaxf(bv, 0.f) + __logf(1.f + __expf(-fabsf(bv))));
 }
 __device__ __forceinline__ float sigmoid_f(float x) {
   float e = __expf(-fabsf(x));
   float s = __fdividef(1.f, 1.f + e);
   return x >= 0.f ? s : e * s;
 }
-__device__ __forceinline__ float softplus2_grad_f(float v) {
-  float bv = 2.f * v;
-  return bv > 20.f ? 1.f : sigmoid_f(bv);
+__device__ __forceinline__ float softplus2_grad_f(float v) {       // sigmoid(2 v); == 1.f beyond the threshold (1 + 2.1e-9 == 1)
+  return sigmoid_f(2.f * v);
 }
 
 // 17-tap Gaussian (sigma 3) exactly as torch builds it in float32 (model.py:186-206)

@@ -112,7 +112,7 @@ __device__ __noinline__ void dec_last_t(const Ctx& c_ref, int mode, int inst, in
   float dbp = 0.f;
   float sg4[4] = {0.f, 0.f, 0.f, 0.f}, sgx4[4] = {0.f, 0.f, 0.f, 0.f};
   double loss_a = 0.0, loss_b = 0.0;        // a: reconstruction, b: smoothness
-  const float nB = (float)c.B, nN = (float)N;
+  const float nB = (float)c.B, nN = (float)N, inv_nN = 1.f / (float)N;
   const double inv_B = 1.0 / (double)c.B, inv_BN = 1.0 / ((double)c.B * (double)N);
   // prefix sums of the (symmetric) taps: P[j] = w[0] + ... + w[j]; the replicate-padding overhang of the adjoint folds
   // into the end points with these weights (see the smoothness branch below)
@@ -317,11 +317,13 @@ __device__ __noinline__ void dec_last_t(const Ctx& c_ref, int mode, int inst, in
             if ((MODE == kLastRecon) && flex) {
 #pragma unroll
               for (int of = 16; of > 0; of >>= 1) { sy += __shfl_xor_sync(0xffffffffu, sy, of); sx += __shfl_xor_sync(0xffffffffu, sx, of); }
-              float m_out = sy / nN, m_in = sx / nN;
-              float rr = fabsf(m_out) / fabsf(m_in);
+              // reciprocal-multiply divisions (2 ulp): an IEEE division carries a slow-path branch, and four of them per row
+              // cut the unrolled row body into pieces
+              float m_out = sy * inv_nN, m_in = sx * inv_nN;
+              float rr = __fdividef(fabsf(m_out), fabsf(m_in));
               cc = fminf(fmaxf(rr, 0.7f), 1.3f);
               float sgn = m_out > 0.f ? 1.f : (m_out < 0.f ? -1.f : 0.f);
-              dr = (0.2f / nB) * (rr - 1.f) * sgn / (fabsf(m_in) * nN);
+              dr = __fdividef((0.2f / nB) * (rr - 1.f) * sgn, fabsf(m_in) * nN);
               if (lane == 0) loss_a += 0.1 * (double)((rr - 1.f) * (rr - 1.f)) * inv_B;
             }
             float sq = 0.f;
@@ -399,11 +401,11 @@ __device__ __noinline__ void dec_last_t(const Ctx& c_ref, int mode, int inst, in
                     for (int k = 0; k < 17; ++k) kt = fmaf(kGauss17[k], win[e + k], kt);
                     // overhang of the replicate padding: sum_{i<8} (K^T e)[i] = sum_{m<8} e[m] P[7-m] folds into y[0],
                     // and by symmetry sum_{q<8} e[N-1-q] P[7-q] into y[N-1]
-                    if (j == 0) {
+                    if (e == 0 && col0 == 0) {           // j == 0 (e is a compile-time index: one test per row, not eight)
 #pragma unroll
                       for (int m = 0; m < 8; ++m) kt = fmaf(tapP[7 - m], ezp[16 + m], kt);
                     }
-                    if (j == N - 1) {
+                    if (FULL ? (e == 7 && col0 == kMaxDim - 8) : (j == N - 1)) {
 #pragma unroll
                       for (int q2 = 0; q2 < 8; ++q2) kt = fmaf(tapP[7 - q2], ezp[16 + N - 1 - q2], kt);
                     }
