@@ -229,6 +229,27 @@ __device__ __forceinline__ float softplus2_grad_f(float v) {       // sigmoid(2 
   return sigmoid_f(2.f * v);
 }
 
+// One AdamW element update (torch.optim.AdamW: decoupled decay, exp_avg, exp_avg_sq, bias-corrected step), shared by the fused
+// stages and the stand-alone optimizer kernels so that every path produces the same bits.  Square root and the two
+// divisions are the hardware approximations (<= 2 ulp each, i.e. <= 1e-9 of the parameter per step at the usual
+// lr / |p| ratios; flush-to-zero only matters where eps = 1e-8 dominates the denominator anyway): the IEEE versions carry
+// slow-path calls, which put a branch diamond around every element of the unrolled update loop and serialised it.
+__device__ __forceinline__ float sqrt_approx_f(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void adamw_update(float& p, float& m, float& v, float g, float decay, float w1, float b2, float w2, float ss,
+                                             float bc2s) {
+  // explicit roundings (fmaf / __fmul_rn): left to the compiler, `v b2 + (w2 g) g` contracts one way in one call site and the
+  // other way in another, and the split-phase path would drift from the fused one by an ulp per step
+  const float pp = __fmul_rn(p, decay);
+  m = fmaf(g - m, w1, m);
+  v = fmaf(__fmul_rn(w2, g), g, __fmul_rn(v, b2));
+  const float denom = __fdividef(sqrt_approx_f(v), bc2s) + kAdamEps;
+  p = fmaf(-ss, __fdividef(m, denom), pp);
+}
+
 // 17-tap Gaussian (sigma 3) exactly as torch builds it in float32 (model.py:186-206)
 __device__ __constant__ float kGauss17[17] = {
     0.0038155282381922007f, 0.008779441937804222f, 0.018076900392770767f, 0.03330628201365471f,

@@ -640,12 +640,9 @@ __device__ __forceinline__ void adam_element(const KParams& p, float* st, const 
   float* P = st + p.lay.net[net].param_off + rel;
   float* M = st + ol.m_off + i;
   float* V = st + ol.v_off + i;
-  float pp = *P * a.decay;
-  float m = *M;
-  m = m + (gi - m) * a.w1;
-  float v = *V * a.b2 + (a.w2 * gi) * gi;
-  float denom = sqrtf(v) / a.bc2s + kAdamEps;
-  *P = pp - a.ss * (m / denom);
+  float pp = *P, m = *M, v = *V;
+  adamw_update(pp, m, v, gi, a.decay, a.w1, a.b2, a.w2, a.ss, a.bc2s);
+  *P = pp;
   *M = m;
   *V = v;
 }
@@ -780,11 +777,9 @@ __global__ void raae_adam_peer_kernel(const __grid_constant__ KParams p, int o, 
         if (v0 + u < V) {
           float* st = p.state + (size_t)(v0 + u) * p.lay.state_floats;
           const AdamScalars a = same[u] ? a0 : adam_scalars(st, p.hp + (size_t)(v0 + u) * RAAE_HP_COUNT, ol, o);
-          const float pp = P4[u] * a.decay;
-          const float m = M4[u] + (g - M4[u]) * a.w1;
-          const float vv = V4[u] * a.b2 + (a.w2 * g) * g;
-          const float denom = sqrtf(vv) / a.bc2s + kAdamEps;
-          st[po] = pp - a.ss * (m / denom);
+          float pp = P4[u], m = M4[u], vv = V4[u];
+          adamw_update(pp, m, vv, g, a.decay, a.w1, a.b2, a.w2, a.ss, a.bc2s);
+          st[po] = pp;
           st[mo] = m;
           st[vo] = vv;
         }

@@ -459,12 +459,8 @@ __device__ __noinline__ void adam_apply_cluster(const Ctx& c_ref, const SmemFixe
         const float gi = gv[k];
         if (dbg) dbg[ol.net_off[net] + poff + i] = gi;
         if (c.apply) {
-          float pp = pv[k] * decay;
-          float m = mv[k];
-          m = m + (gi - m) * w1;
-          float v = vv[k] * b2 + (w2 * gi) * gi;
-          float denom = sqrtf(v) / bc2s + kAdamEps;
-          pp = pp - ss * (m / denom);
+          float pp = pv[k], m = mv[k], v = vv[k];
+          adamw_update(pp, m, v, gi, decay, w1, b2, w2, ss, bc2s);
           P[i] = pp; M[i] = m; V[i] = v;
         }
       }
@@ -493,22 +489,15 @@ __device__ __forceinline__ void adam_apply(const Ctx& c, const SmemFixed* sm, in
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int i = base + k * kThreads;
-      if (i < n) { pv[k] = P[i]; mv[k] = M[i]; vv[k] = V[i]; gv[k] = g[i]; }
-      else { pv[k] = 0.f; mv[k] = 0.f; vv[k] = 0.f; gv[k] = 0.f; }
+      const bool ok = i < n;                  // predicated loads, no branch per element
+      pv[k] = ok ? P[i] : 0.f; mv[k] = ok ? M[i] : 0.f; vv[k] = ok ? V[i] : 0.f; gv[k] = ok ? g[i] : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int i = base + k * kThreads;
-      if (i < n) {
-        const float gi = gv[k];
-        float pp = pv[k] * decay;
-        float m = mv[k];
-        m = m + (gi - m) * w1;
-        float v = vv[k] * b2 + (w2 * gi) * gi;
-        float denom = sqrtf(v) / bc2s + kAdamEps;
-        pp = pp - ss * (m / denom);
-        P[i] = pp; M[i] = m; V[i] = v;
-      }
+      float pp = pv[k], m = mv[k], v = vv[k];          // branch-free arithmetic, guarded stores: the eight elements interleave
+      adamw_update(pp, m, v, gv[k], decay, w1, b2, w2, ss, bc2s);
+      if (i < n) { P[i] = pp; M[i] = m; V[i] = v; }
     }
   }
 }
