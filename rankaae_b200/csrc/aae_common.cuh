@@ -113,13 +113,20 @@ __device__ __forceinline__ uint32_t stream_key(uint32_t seed, uint32_t step_id, 
   return mix32(seed ^ mix32(step_id * 256u + kind));
 }
 
+// hardware square root (<= 1 ulp, no slow path - and so no branch - around it)
+__device__ __forceinline__ float sqrt_approx_f(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // standard normal for element idx of a stream (Box-Muller on two hashed uniforms per pair)
 __device__ __forceinline__ float normal_at(uint32_t key, uint32_t idx) {
   uint32_t pair = idx >> 1;
   uint32_t h1 = hash2(key, 2u * pair), h2 = hash2(key, 2u * pair + 1u);
   float u1 = ((h1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
   float u2 = ((h2 >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  float r = sqrtf(-2.0f * __logf(u1));
+  float r = sqrt_approx_f(-2.0f * __logf(u1));
   float s, c;
   __sincosf(6.28318530717958647692f * u2, &s, &c);
   return (idx & 1u) ? r * s : r * c;
@@ -130,7 +137,7 @@ __device__ __forceinline__ void normal_pair(uint32_t key, uint32_t pair, float& 
   uint32_t h1 = hash2(key, 2u * pair), h2 = hash2(key, 2u * pair + 1u);
   float u1 = ((h1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
   float u2 = ((h2 >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  float r = sqrtf(-2.0f * __logf(u1));
+  float r = sqrt_approx_f(-2.0f * __logf(u1));
   float s, c;
   __sincosf(6.28318530717958647692f * u2, &s, &c);
   n0 = r * c;
@@ -234,11 +241,6 @@ __device__ __forceinline__ float softplus2_grad_f(float v) {       // sigmoid(2 
 // divisions are the hardware approximations (<= 2 ulp each, i.e. <= 1e-9 of the parameter per step at the usual
 // lr / |p| ratios; flush-to-zero only matters where eps = 1e-8 dominates the denominator anyway): the IEEE versions carry
 // slow-path calls, which put a branch diamond around every element of the unrolled update loop and serialised it.
-__device__ __forceinline__ float sqrt_approx_f(float x) {
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
 __device__ __forceinline__ void adamw_update(float& p, float& m, float& v, float g, float decay, float w1, float b2, float w2, float ss,
                                              float bc2s) {
   // explicit roundings (fmaf / __fmul_rn): left to the compiler, `v b2 + (w2 g) g` contracts one way in one call site and the
