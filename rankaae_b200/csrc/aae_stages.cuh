@@ -869,7 +869,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
         for (int i = 0; i < kTM / 16; ++i) {
           const int r = ty + 16 * i;
           float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < nv) {
+          {                                    // branch-free: rows >= nv carry dlogit = 0, h = u = 0 and clear keep bits
             const float dl = sm->dlogit[r];
             const float4 h = *reinterpret_cast<const float4*>(H2 + r * kLD + c4);
             const float4 u = *reinterpret_cast<const float4*>(U2 + r * kLD + c4);
@@ -906,7 +906,7 @@ __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, co
         for (int i = 0; i < 8; ++i) {
           int r = ty + 16 * i;
           float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < nv) {
+          {                                    // branch-free: rows >= nv have clear keep bits and u = 0
             uint32_t kb = kbits0 >> (4 * i);
             asm volatile("" : "+r"(kb));
             float4 u = *reinterpret_cast<const float4*>(U1 + r * kLD + c4);

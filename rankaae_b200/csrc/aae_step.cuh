@@ -2329,17 +2329,15 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = ty + 16 * i;
-          if (r < nv && k0 + c4 < K) {
-            float4 v = vv[i];
-            if (act == 1) {
-              v.x = acc[i][0] * softplus2_grad_f(v.x); v.y = acc[i][1] * softplus2_grad_f(v.y);
-              v.z = acc[i][2] * softplus2_grad_f(v.z); v.w = acc[i][3] * softplus2_grad_f(v.w);
-            } else {
-              v.x = v.x > 0.f ? acc[i][0] : 0.f; v.y = v.y > 0.f ? acc[i][1] : 0.f;
-              v.z = v.z > 0.f ? acc[i][2] : 0.f; v.w = v.w > 0.f ? acc[i][3] : 0.f;
-            }
-            *reinterpret_cast<float4*>(dx_out + (size_t)(row0 + r) * dx_ld + k0 + c4) = v;
+          float4 v = vv[i];                    // branch-free arithmetic (the activation is warp-uniform), guarded store
+          if (act == 1) {
+            v.x = acc[i][0] * softplus2_grad_f(v.x); v.y = acc[i][1] * softplus2_grad_f(v.y);
+            v.z = acc[i][2] * softplus2_grad_f(v.z); v.w = acc[i][3] * softplus2_grad_f(v.w);
+          } else {
+            v.x = v.x > 0.f ? acc[i][0] : 0.f; v.y = v.y > 0.f ? acc[i][1] : 0.f;
+            v.z = v.z > 0.f ? acc[i][2] : 0.f; v.w = v.w > 0.f ? acc[i][3] : 0.f;
           }
+          if (r < nv && k0 + c4 < K) *reinterpret_cast<float4*>(dx_out + (size_t)(row0 + r) * dx_ld + k0 + c4) = v;
         }
       }
       __syncthreads();                         // the chunk buffers are reloaded by the next tile
