@@ -437,32 +437,36 @@ __device__ __noinline__ void adam_apply_cluster(const Ctx& c_ref, const SmemFixe
   float* M = c.st + ol.m_off + ol.net_off[net] + poff;
   float* V = c.st + ol.v_off + ol.net_off[net] + poff;
   const float decay = sm->ad[0], w1 = sm->ad[1], b2 = sm->ad[2], w2 = sm->ad[3], ss = sm->ad[4], bc2s = sm->ad[5];
+  const bool apply = c.apply != 0;
   for (int base = i0 + threadIdx.x; base < i1; base += kThreads * 4) {
-    float pv[4], mv[4], vv[4], gv[4];
+    // branch-free: every DSMEM load of the four elements is in flight before the first sum (out-of-range elements read
+    // element i0 and are never stored), the parameter / moment loads are predicated, the stores guarded
+    float pv[4], mv[4], vv[4], gv[4], part[4][RAAE_MAX_CTAS];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = base + k * kThreads;
-      gv[k] = 0.f; pv[k] = 0.f; mv[k] = 0.f; vv[k] = 0.f;
-      if (i < i1) {
-        float sgrad = 0.f;
+      const int is = i < i1 ? i : i0;
 #pragma unroll
-        for (int r = 0; r < RAAE_MAX_CTAS; ++r)
-          if (r < C) sgrad += cl::ld_f32(gbase[r] + 4u * (uint32_t)i);
-        gv[k] = sgrad;
-        if (c.apply) { pv[k] = P[i]; mv[k] = M[i]; vv[k] = V[i]; }
-      }
+      for (int r = 0; r < RAAE_MAX_CTAS; ++r) part[k][r] = cl::ld_f32(gbase[r] + 4u * (uint32_t)is);   // gbase[r >= C] repeats rank C - 1
+      const bool ok = apply && i < i1;
+      pv[k] = ok ? P[i] : 0.f; mv[k] = ok ? M[i] : 0.f; vv[k] = ok ? V[i] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float sgrad = 0.f;
+#pragma unroll
+      for (int r = 0; r < RAAE_MAX_CTAS; ++r) sgrad += r < C ? part[k][r] : 0.f;       // rank order
+      gv[k] = sgrad;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = base + k * kThreads;
+      const float gi = gv[k];
+      float pp = pv[k], m = mv[k], v = vv[k];
+      adamw_update(pp, m, v, gi, decay, w1, b2, w2, ss, bc2s);
       if (i < i1) {
-        const float gi = gv[k];
         if (dbg) dbg[ol.net_off[net] + poff + i] = gi;
-        if (c.apply) {
-          float pp = pv[k], m = mv[k], v = vv[k];
-          adamw_update(pp, m, v, gi, decay, w1, b2, w2, ss, bc2s);
-          P[i] = pp; M[i] = m; V[i] = v;
-        }
+        if (apply) { P[i] = pp; M[i] = m; V[i] = v; }
       }
     }
   }
