@@ -163,8 +163,7 @@ __device__ __forceinline__ void cluster_allreduce_f(const Ctx& c, SmemFixed* sm,
     for (int r = 0; r < RAAE_MAX_CTAS; ++r) s += v[r];
     vec[tid] = s;
   }
-  __syncthreads();
-  if (tid == 0) sm->xpar = par ^ 1u;
+  if (tid == 0) sm->xpar = par ^ 1u;     // every thread read `par` before the cluster barrier; published by the barrier below
   __syncthreads();
 }
 __device__ __forceinline__ void cluster_allreduce_d(const Ctx& c, SmemFixed* sm, double* vec, int n) {   // n <= 40
@@ -184,7 +183,6 @@ __device__ __forceinline__ void cluster_allreduce_d(const Ctx& c, SmemFixed* sm,
     for (int r = 0; r < RAAE_MAX_CTAS; ++r) s += v[r];
     vec[tid] = s;
   }
-  __syncthreads();
   if (tid == 0) sm->xpar = par ^ 1u;
   __syncthreads();
 }
@@ -524,8 +522,10 @@ struct LayerIn {
 };
 
 // finalize BN statistics of channel c from the shifted sums; updates running buffers in train mode
+// rm_old / rv_old: the running buffers of the channel as loaded at the START of the stage (bn_running_load) - loaded here,
+// at its end, the read-modify-write exposed a DRAM round trip in front of every stage's closing barrier
 __device__ __forceinline__ void bn_finalize(const Ctx& c, SmemFixed* sm, int net, int l, int ch, float shift, float s1,
-                                            float s2, int nrows, bool running = true) {
+                                            float s2, int nrows, bool running, float rm_old, float rv_old) {
   const raae_net_layout& nl = NL(c, net);
   float n = (float)nrows;
   float d = s1 / n;
@@ -540,14 +540,24 @@ __device__ __forceinline__ void bn_finalize(const Ctx& c, SmemFixed* sm, int net
   float* rm = c.st + nl.rm_off[l];
   float* rv = c.st + nl.rv_off[l];
   float unb = nrows > 1 ? var * (n / (n - 1.f)) : var;
-  rm[ch] = (1.f - kBnMomentum) * rm[ch] + kBnMomentum * mean;
-  rv[ch] = (1.f - kBnMomentum) * rv[ch] + kBnMomentum * unb;
+  rm[ch] = (1.f - kBnMomentum) * rm_old + kBnMomentum * mean;
+  rv[ch] = (1.f - kBnMomentum) * rv_old + kBnMomentum * unb;
+}
+// the running mean / variance of channel threadIdx.x of layer l (threads < 64 of the CTA that advances them, train mode)
+__device__ __forceinline__ void bn_running_load(const Ctx& c, int net, int l, float& rm_old, float& rv_old) {
+  rm_old = 0.f; rv_old = 0.f;
+  if (c.train && threadIdx.x < kH && c.crank == 0) {
+    const raae_net_layout& nl = NL(c, net);
+    rm_old = c.st[nl.rm_off[l] + threadIdx.x];
+    rv_old = c.st[nl.rv_off[l] + threadIdx.x];
+  }
 }
 
 // Cluster merge of BatchNorm batch statistics (all threads; the values of threads tid < kH count): every CTA contributes the
 // mean and the centred sum of squares (M2) of ITS rows; exact parallel-variance merge in rank order, identical in every CTA;
 // rank 0 advances the running buffers.
-__device__ __forceinline__ void bn_merge_cluster(const Ctx& c, SmemFixed* sm, int net, int l, float mean_l, float m2_l) {
+__device__ __forceinline__ void bn_merge_cluster(const Ctx& c, SmemFixed* sm, int net, int l, float mean_l, float m2_l, float rm_old,
+                                                 float rv_old) {
   const int tid = threadIdx.x;
   __syncthreads();
   const uint32_t par = sm->xpar;
@@ -570,23 +580,23 @@ __device__ __forceinline__ void bn_merge_cluster(const Ctx& c, SmemFixed* sm, in
     float m2 = 0.f;
 #pragma unroll
     for (int r = 0; r < RAAE_MAX_CTAS; ++r) { const float d = mr[r] - mean; m2 += qr[r] + nr[r] * d * d; }
-    bn_finalize(c, sm, net, l, tid, mean, 0.f, m2, c.B, c.crank == 0);
+    bn_finalize(c, sm, net, l, tid, mean, 0.f, m2, c.B, c.crank == 0, rm_old, rv_old);
   }
-  __syncthreads();
-  if (tid == 0) sm->xpar = par ^ 1u;
+  if (tid == 0) sm->xpar = par ^ 1u;     // every thread read `par` before the cluster barrier; published by the caller's barrier
   __syncthreads();
 }
 // end of a forward stage in train mode (all threads): shifted single-pass sums of this CTA's rows (threads tid < kH) ->
 // sm->mean / inv of the layer (+ running buffers)
-__device__ __forceinline__ void bn_stats_finish(const Ctx& c, SmemFixed* sm, int net, int l, float shift, float s1, float s2) {
+__device__ __forceinline__ void bn_stats_finish(const Ctx& c, SmemFixed* sm, int net, int l, float shift, float s1, float s2,
+                                                float rm_old, float rv_old) {
   if (c.csize == 1) {
-    if (threadIdx.x < kH) bn_finalize(c, sm, net, l, threadIdx.x, shift, s1, s2, c.B);
+    if (threadIdx.x < kH) bn_finalize(c, sm, net, l, threadIdx.x, shift, s1, s2, c.B, true, rm_old, rv_old);
     return;
   }
   const float nl = (float)cl::own_rows(c.B, c.crank, c.csize);
   float mean_l = 0.f, m2_l = 0.f;
   if (nl > 0.f) { const float d = s1 / nl; mean_l = shift + d; m2_l = fmaxf(s2 - s1 * d, 0.f); }
-  bn_merge_cluster(c, sm, net, l, mean_l, m2_l);
+  bn_merge_cluster(c, sm, net, l, mean_l, m2_l, rm_old, rv_old);
 }
 
 __device__ __noinline__ void fwd_hidden_edge(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
@@ -594,6 +604,8 @@ __device__ __noinline__ void fwd_hidden_edge(const Ctx& c_ref, int net, int l, c
   const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[in.kind == kInWide ? kStFwdWide : in.kind == kInHidden ? kStFwdHidden : kStFwdLatent]);
+  float rm_old, rv_old;                // running BatchNorm buffers of this layer, loaded a whole stage ahead of their update
+  bn_running_load(c, net, l, rm_old, rv_old);
   const raae_net_layout& nl = NL(c, net);
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, ch = tid & 63, q = tid >> 6;
   const int K = nl.in_dim[l];
@@ -723,7 +735,7 @@ __device__ __noinline__ void fwd_hidden_edge(const Ctx& c_ref, int net, int l, c
 #pragma unroll
       for (int i = 0; i < 16; ++i) a2 += sm->red[i][tid];
     }
-    bn_stats_finish(c, sm, net, l, tid < kH ? sm->shift[tid] : 0.f, a1, a2);
+    bn_stats_finish(c, sm, net, l, tid < kH ? sm->shift[tid] : 0.f, a1, a2, rm_old, rv_old);
   }
   __syncthreads();
 }
@@ -735,6 +747,8 @@ __device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, cons
   const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStFwdHidden]);
+  float rm_old, rv_old;                // running BatchNorm buffers of this layer, loaded a whole stage ahead of their update
+  bn_running_load(c, net, l, rm_old, rv_old);
   const raae_net_layout& nl = NL(c, net);
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4;
   const float* Wg = netp(c, net) + nl.w_off[l];
@@ -836,7 +850,7 @@ __device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, cons
 #pragma unroll
       for (int i = 0; i < 16; ++i) a2 += sm->red[i][tid];
     }
-    bn_stats_finish(c, sm, net, l, tid < kH ? sm->shift[tid] : 0.f, a1, a2);
+    bn_stats_finish(c, sm, net, l, tid < kH ? sm->shift[tid] : 0.f, a1, a2, rm_old, rv_old);
   }
   __syncthreads();
 }
@@ -851,6 +865,8 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
   const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStFwdHidden]);
+  float rm_old, rv_old;                // running BatchNorm buffers of this layer, loaded a whole stage ahead of their update
+  bn_running_load(c, net, l, rm_old, rv_old);
   const raae_net_layout& nl = NL(c, net);
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4, warp = tid >> 5, lane = tid & 31;
   const float* Wg = netp(c, net) + nl.w_off[l];
@@ -1013,7 +1029,7 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
       a2 = sm->red[4][tid] + sm->red[5][tid] + sm->red[6][tid] + sm->red[7][tid];
     }
     RAAE_FPROBE(20);                     // column reductions
-    bn_stats_finish(c, sm, net, l, tid < kH ? sm->shift[tid] : 0.f, a1, a2);
+    bn_stats_finish(c, sm, net, l, tid < kH ? sm->shift[tid] : 0.f, a1, a2, rm_old, rv_old);
     RAAE_FPROBE(21);                     // statistics (cluster: exchange + merge)
   }
   __syncthreads();
@@ -1031,6 +1047,8 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, cons
   const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStFwdWide]);
+  float rm_old, rv_old;                // running BatchNorm buffers of this layer, loaded a whole stage ahead of their update
+  bn_running_load(c, net, l, rm_old, rv_old);
   const raae_net_layout& nl = NL(c, net);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = nl.in_dim[l], nch = c.p->sl.nch64;
@@ -1252,8 +1270,8 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, cons
         for (int w = 0; w < 4; ++w) { const float d = sm->red[w][tid] - mean; m2 += sm->red[4 + w][tid] + sm->redw[w] * d * d; }
       }
     }
-    if (csize == 1) { if (tid < kH) bn_finalize(c, sm, net, l, tid, mean, 0.f, m2, B); }
-    else bn_merge_cluster(c, sm, net, l, mean, m2);
+    if (csize == 1) { if (tid < kH) bn_finalize(c, sm, net, l, tid, mean, 0.f, m2, B, true, rm_old, rv_old); }
+    else bn_merge_cluster(c, sm, net, l, mean, m2, rm_old, rv_old);
   }
   __syncthreads();
 }
