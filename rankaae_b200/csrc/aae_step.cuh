@@ -1178,20 +1178,33 @@ __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, cons
         tc::mbar_wait(&full[b], (uint32_t)((cit >> 1) & 1));
         float4* src = reinterpret_cast<float4*>(Araw + b * 8192);   // rounded in place: becomes the hi plane
         float4* dst = reinterpret_cast<float4*>(Alo + b * 8192);
+        // 2048 quads over 224 threads: nine unguarded quads per thread (all nine loads in flight, straight-line split and
+        // stores - a guard around the two stores of every quad compiled into a branch diamond per quad), the last 32 quads
+        // by the first converter warp
+        {
+          float4 x[9];
 #pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-          float4 x[5];
+          for (int k = 0; k < 9; ++k) x[k] = src[ctid + 224 * k];
 #pragma unroll
-          for (int k = 0; k < 5; ++k) { const int q = ctid + 224 * (5 * hb + k); x[k] = q < 2048 ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f); }
-#pragma unroll
-          for (int k = 0; k < 5; ++k) {
-            const int q = ctid + 224 * (5 * hb + k);
+          for (int k = 0; k < 9; ++k) {
             float4 hi, lo;
             tc::tf32_split(x[k].x, hi.x, lo.x);
             tc::tf32_split(x[k].y, hi.y, lo.y);
             tc::tf32_split(x[k].z, hi.z, lo.z);
             tc::tf32_split(x[k].w, hi.w, lo.w);
-            if (q < 2048) { src[q] = hi; dst[q] = lo; }
+            src[ctid + 224 * k] = hi;
+            dst[ctid + 224 * k] = lo;
+          }
+          if (ctid < 2048 - 9 * 224) {            // warp-uniform: the first converter warp
+            const int q = 9 * 224 + ctid;
+            const float4 xv = src[q];
+            float4 hi, lo;
+            tc::tf32_split(xv.x, hi.x, lo.x);
+            tc::tf32_split(xv.y, hi.y, lo.y);
+            tc::tf32_split(xv.z, hi.z, lo.z);
+            tc::tf32_split(xv.w, hi.w, lo.w);
+            src[q] = hi;
+            dst[q] = lo;
           }
         }
         tc::fence_async_smem();
