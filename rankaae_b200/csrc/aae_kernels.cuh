@@ -15,7 +15,7 @@ __device__ inline float alpha_schedule(const Ctx& c) {
 // spec_in += randn_like(spec_in) * spec_noise (trainer.py:112) for the rows idx[0..B) of the training
 // split; descriptors of the same rows; z_sample of the MI phase.
 __device__ __noinline__ void build_batch(const Ctx& c_ref, const int32_t* __restrict__ idx) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   const KParams& p = *c.p;
   const int tid = threadIdx.x, dim = p.cfg.dim_in, xld = p.sl.xld, K = p.cfg.n_aux, ns = p.cfg.nstyle;
   float* xn = c.sc + p.sl.xn;
@@ -397,7 +397,7 @@ __device__ __forceinline__ void bitonic_sort(float* key, int* idx, int npad) {
 // scipy.stats.shapiro(z_k).statistic per style (Royston weights supplied by the host)
 // and max |Spearman| over style pairs (trainer.py:286-293).  Results: sm->zs[2][0] = min W, zs[2][1] = coupling.
 __device__ __noinline__ void latent_metrics(const Ctx& c_ref) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStBatch]);      // the validation kernel builds no batch: slot 0 is free there
   const KParams& p = *c.p;

@@ -681,7 +681,7 @@ __device__ __forceinline__ void dec_last(const Ctx& c, int mode, int inst, int o
 // sc.dz = -alpha * dL/dstyles for the fake rows.
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void dis_stage(const Ctx& c_ref, int backward, int o, const float* z_real_ptr, uint32_t key_zreal) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStDis]);
   const raae_net_layout& nl = NL(c, kS);
@@ -1099,7 +1099,7 @@ __device__ __forceinline__ void kendall_row(const float* __restrict__ Ss, const 
 }
 
 __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __restrict__ aux, int want_grad) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStKendall]);
   const raae_net_layout& el = NL(c, kE);
@@ -1227,7 +1227,7 @@ __device__ __noinline__ void kendall_stage(const Ctx& c_ref, const float* __rest
 
 // MSE between the re-encoded latent and z_sample (mutual_info_loss functions.py:174-192)
 __device__ __noinline__ void mi_mse_stage(const Ctx& c_ref, int want_grad) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStMiMse]);
   const raae_net_layout& el = NL(c, kE);

@@ -600,7 +600,7 @@ __device__ __forceinline__ void bn_stats_finish(const Ctx& c, SmemFixed* sm, int
 }
 
 __device__ __noinline__ void fwd_hidden_edge(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[in.kind == kInWide ? kStFwdWide : in.kind == kInHidden ? kStFwdHidden : kStFwdLatent]);
@@ -743,7 +743,7 @@ __device__ __noinline__ void fwd_hidden_edge(const Ctx& c_ref, int net, int l, c
 // forward of a hidden block whose input is another hidden block's panel (K = 64): the raw pre-activation tile of
 // tile t+1 is prefetched with cp.async while tile t runs its contraction and epilogue.
 __device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStFwdHidden]);
@@ -861,7 +861,7 @@ __device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, cons
 // The epilogue works in the TMEM layout (thread = row, 32 consecutive columns): bias, store, and the shifted
 // single-pass BatchNorm sums as per-thread partials that are reduced over the rows once per layer.
 __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStFwdHidden]);
@@ -1044,7 +1044,7 @@ __device__ __noinline__ void fwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
 // merged exactly at the end.  HBM traffic: the batch once (the hi/lo split never leaves the SM).
 __device__ __noinline__ void fwd_wide_img(const Ctx& c_ref, int net, int l, const float* __restrict__ xk, const float* __restrict__ xref,
                                           float* __restrict__ u_out) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStFwdWide]);
   float rm_old, rv_old;                // running BatchNorm buffers of this layer, loaded a whole stage ahead of their update
@@ -1348,7 +1348,7 @@ __device__ __forceinline__ void latent_colstats(const Ctx& c, SmemFixed* sm, con
 // last encoder Linear (64 -> nstyle) + BatchNorm1d(nstyle).  zE receives the PRE-BN output; the BN
 // statistics go to sm->mean/inv[kE][L-1][0..nstyle).
 __device__ __noinline__ void fwd_enc_last(const Ctx& c_ref, const LayerIn& in_ref) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStFwdEncLast]);
@@ -1485,7 +1485,7 @@ __device__ __forceinline__ void decoder_forward_hidden(const Ctx& c, const Layer
 //   in.kind == kInLatent : input latent rows;                        dz_out (optional) [rows][kZ]
 __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, const float* __restrict__ u_l,
                                              const float* __restrict__ g_in, float* g_out, int o) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[in.kind == kInWide ? kStBwdWide : in.kind == kInHidden ? kStBwdHidden : kStBwdLatent]);
@@ -1758,7 +1758,7 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, c
 // g / u / u_prev tiles of tile t+1 are prefetched with cp.async while tile t runs its two contractions.
 __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, const float* __restrict__ u_l,
                                           const float* __restrict__ g_in, float* __restrict__ g_out, int o) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStBwdHidden]);
@@ -1928,7 +1928,7 @@ __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, cons
 // before the first use, so a tile exposes one memory latency.
 __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, const float* __restrict__ u_l,
                                              const float* __restrict__ g_in, float* __restrict__ g_out, int o) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStBwdHidden]);
@@ -2190,7 +2190,7 @@ __device__ __noinline__ void bwd_hidden64_tc(const Ctx& c_ref, int net, int l, c
 __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, const float* __restrict__ u_l,
                                           const float* __restrict__ g_in, int o, const float* __restrict__ xm,
                                           const float* __restrict__ xref, float* dx_out, int dx_ld, int act) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStBwdWide]);
   const raae_net_layout& nl = NL(c, net);
@@ -2421,7 +2421,7 @@ __device__ __noinline__ void bwd_wide_img(const Ctx& c_ref, int net, int l, cons
 // last encoder layer backward: BN(nstyle) -> Linear(64, nstyle); input gradient for hidden layer L-2
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void bwd_enc_last(const Ctx& c_ref, const LayerIn& in_ref, float* __restrict__ g_out, int o) {
-  const Ctx c = c_ref;                 // register copy: the caller's object lives in local memory
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
   const LayerIn in = in_ref;
   RAAE_SMEM();
   StageTimer timer_(&sm->prof[kStBwdEncLast]);
