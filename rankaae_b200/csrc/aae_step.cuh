@@ -740,6 +740,140 @@ __device__ __noinline__ void fwd_hidden_edge(const Ctx& c_ref, int net, int l, c
   __syncthreads();
 }
 
+// forward of a hidden block whose input is the latent (K = nstyle <= 8: decoder layer 0).  Thread (ty, c4) owns channels
+// c4..c4+3 of rows ty, ty + 16, ...: its four weight rows stay in registers, a latent row is two broadcast loads, the outputs
+// go straight into the epilogue's registers (no bounce through a [128][64] tile, one barrier less per tile), and the next
+// tile's latent rows (one float4 per thread) are loaded while this one is contracted.
+__device__ __noinline__ void fwd_latent(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
+  const LayerIn in = in_ref;
+  RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStFwdLatent]);
+  float rm_old, rv_old;                // running BatchNorm buffers of this layer, loaded a whole stage ahead of their update
+  bn_running_load(c, net, l, rm_old, rv_old);
+  const raae_net_layout& nl = NL(c, net);
+  const int tid = threadIdx.x, ty = tid >> 4, c4 = (tid & 15) * 4;
+  const int K = nl.in_dim[l];
+  const float* Wg = netp(c, net) + nl.w_off[l];
+  float* Ws = arena;                          // [64][9]
+  float* Zt = arena + 1024;                   // [kTM][kZ]
+  const float* zmean = in.slayer >= 0 ? sm->mean[in.snet][in.slayer] : nullptr;
+  const float* zinv = in.slayer >= 0 ? sm->inv[in.snet][in.slayer] : nullptr;
+  const int ntiles = (c.B + kTM - 1) / kTM;
+  const int zr = tid >> 1, zk0 = (tid & 1) * 4;      // this thread's float4 of a latent tile: row tid / 2, columns 4 (tid & 1) ..
+  auto load_z = [&](int t) {
+    const int row0 = t * kTM;
+    return (t < ntiles && row0 + zr < c.B) ? *reinterpret_cast<const float4*>(in.src + (size_t)(row0 + zr) * kZ + zk0)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 zraw = load_z(c.crank);
+  __syncthreads();
+  for (int o = tid; o < kH * 9; o += kThreads) {
+    int n = o / 9, k = o - n * 9;
+    Ws[o] = k < K ? Wg[n * K + k] : 0.f;
+  }
+  if (tid < kH) {
+    sm->bias[tid] = netp(c, net)[nl.b_off[l] + tid];
+    sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
+    if (!c.train) {
+      sm->mean[net][l][tid] = c.st[nl.rm_off[l] + tid];
+      sm->inv[net][l][tid] = 1.f / sqrtf(c.st[nl.rv_off[l] + tid] + kBnEps);
+    }
+  }
+  __syncthreads();
+  float wr[4][kZ];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < kZ; ++k) wr[j][k] = Ws[(c4 + j) * 9 + k];
+  const float4 b4 = *reinterpret_cast<const float4*>(sm->bias + c4);
+  const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+  const float4 a_sl = *reinterpret_cast<const float4*>(sm->slope + c4);
+  float4 s1v = make_float4(0.f, 0.f, 0.f, 0.f), s2v = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = c.crank; t < ntiles; t += c.csize) {
+    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    {
+      // latent tile (normalised with the BatchNorm of the encoder output where it applies; zero beyond nstyle / nv)
+      float o[4] = {zraw.x, zraw.y, zraw.z, zraw.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = zk0 + e;
+        if (zr < nv && k < K) { if (zmean) o[e] = (o[e] - zmean[k]) * zinv[k]; }
+        else o[e] = 0.f;
+      }
+      *reinterpret_cast<float4*>(Zt + zr * kZ + zk0) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+    zraw = load_z(t + c.csize);                  // in flight during the contraction and the epilogue
+    float4 uo[kTM / 16];
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      const float4 z0 = *reinterpret_cast<const float4*>(Zt + r * kZ);
+      const float4 z1 = *reinterpret_cast<const float4*>(Zt + r * kZ + 4);
+      float a[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float acc = bb[j];
+        acc = fmaf(z0.x, wr[j][0], acc); acc = fmaf(z0.y, wr[j][1], acc); acc = fmaf(z0.z, wr[j][2], acc); acc = fmaf(z0.w, wr[j][3], acc);
+        acc = fmaf(z1.x, wr[j][4], acc); acc = fmaf(z1.y, wr[j][5], acc); acc = fmaf(z1.z, wr[j][6], acc); acc = fmaf(z1.w, wr[j][7], acc);
+        a[j] = acc;
+      }
+      uo[i] = make_float4(a[0], a[1], a[2], a[3]);
+    }
+    if (c.train && t == c.crank) {
+      float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < kTM / 16; ++i)
+        if (ty + 16 * i < nv) {
+          sp.x += prelu_f(uo[i].x, a_sl.x); sp.y += prelu_f(uo[i].y, a_sl.y);
+          sp.z += prelu_f(uo[i].z, a_sl.z); sp.w += prelu_f(uo[i].w, a_sl.w);
+        }
+      *reinterpret_cast<float4*>(&sm->red[ty][c4]) = sp;
+      __syncthreads();
+      if (tid < kH) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sacc += sm->red[i][tid];
+        sm->shift[tid] = sacc / (float)nv;
+      }
+      __syncthreads();
+    }
+    const float4 sh = c.train ? *reinterpret_cast<const float4*>(sm->shift + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      if (r < nv) {
+        *reinterpret_cast<float4*>(u_out + (size_t)(row0 + r) * kH + c4) = uo[i];
+        float d;
+        d = prelu_f(uo[i].x, a_sl.x) - sh.x; s1v.x += d; s2v.x = fmaf(d, d, s2v.x);
+        d = prelu_f(uo[i].y, a_sl.y) - sh.y; s1v.y += d; s2v.y = fmaf(d, d, s2v.y);
+        d = prelu_f(uo[i].z, a_sl.z) - sh.z; s1v.z += d; s2v.z = fmaf(d, d, s2v.z);
+        d = prelu_f(uo[i].w, a_sl.w) - sh.w; s1v.w += d; s2v.w = fmaf(d, d, s2v.w);
+      }
+    }
+    __syncthreads();                             // the latent tile is rewritten by the next iteration
+  }
+  if (c.train) {
+    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s1v;
+    __syncthreads();
+    float a1 = 0.f, a2 = 0.f;
+    if (tid < kH) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a1 += sm->red[i][tid];
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&sm->red[ty][c4]) = s2v;
+    __syncthreads();
+    if (tid < kH) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a2 += sm->red[i][tid];
+    }
+    bn_stats_finish(c, sm, net, l, tid < kH ? sm->shift[tid] : 0.f, a1, a2, rm_old, rv_old);
+  }
+  __syncthreads();
+}
+
 // forward of a hidden block whose input is another hidden block's panel (K = 64): the raw pre-activation tile of
 // tile t+1 is prefetched with cp.async while tile t runs its contraction and epilogue.
 __device__ __noinline__ void fwd_hidden64(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, float* __restrict__ u_out) {
@@ -1420,6 +1554,8 @@ __device__ __forceinline__ void fwd_hidden(const Ctx& c, int net, int l, const L
   } else if (in.kind == kInWide && (c.p->cfg.tensor_cores & 4) && in.img) {
     fwd_wide_img(c, net, l, c.sc + (in.img == 2 ? c.p->sl.yk : c.p->sl.xk),
                  c.sc + (in.img == 2 ? c.p->sl.yref : c.p->sl.xref) + c.crank * kMaxDim, u_out);
+  } else if (in.kind == kInLatent) {
+    fwd_latent(c, net, l, in, u_out);
   } else {
     fwd_hidden_edge(c, net, l, in, u_out);
   }
