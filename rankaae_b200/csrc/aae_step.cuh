@@ -1890,6 +1890,169 @@ __device__ __noinline__ void bwd_hidden_edge(const Ctx& c_ref, int net, int l, c
   stage_sync(c);
 }
 
+// backward of a hidden block whose input is the latent (decoder layer 0, K = nstyle <= 8).  All 16 global loads of a tile
+// (g, u) are in flight before the first use; du stays in registers in the (ty, c4) ownership for the weight gradient
+// (dW[c4 + j][k] += du z, the latent row as two broadcast loads: no shared-memory round trip, 8 x 4 accumulators per thread)
+// and goes to shared memory only for dz = du W, which needs whole rows (two threads per row, combined by a shuffle).
+__device__ __noinline__ void bwd_latent(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, const float* __restrict__ u_l,
+                                        const float* __restrict__ g_in, float* g_out, int o) {
+  const Ctx c = c_ref;                 // register copy of the kernel context (SmemFixed::ctx, shared memory)
+  const LayerIn in = in_ref;
+  RAAE_SMEM();
+  StageTimer timer_(&sm->prof[kStBwdLatent]);
+  const raae_net_layout& nl = NL(c, net);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, c4 = tx * 4;
+  const int K = nl.in_dim[l];
+  const float* Wg = netp(c, net) + nl.w_off[l];
+  float* Dt = arena;                          // [kTM][kLD] du
+  float* Zt = arena + kTile;                  // [kTM][kZ] latent rows
+  float* Ws = Zt + kTM * kZ;                  // [64][9]
+  float* gradW = Ws + kH * 9 + 16;            // dense [64][K] + [64] db + [64] dslope (reused after the tile loop)
+  float* part = gradW + kH * kZ + 2 * kH;     // [16 row groups][64][8] partials of dW
+  const bool want_out = g_out != nullptr;
+  const float* zmean = in.slayer >= 0 ? sm->mean[in.snet][in.slayer] : nullptr;
+  const float* zinv = in.slayer >= 0 ? sm->inv[in.snet][in.slayer] : nullptr;
+  const int ntiles = (c.B + kTM - 1) / kTM;
+  __syncthreads();
+  if (tid < kH) {
+    float nB = (float)c.B;
+    sm->cg[tid] = sm->sg[tid] / nB;
+    sm->cgx[tid] = sm->sgx[tid] / nB;
+    sm->slope[tid] = netp(c, net)[nl.a_off[l] + tid];
+  }
+  for (int i = tid; i < kH * 9; i += kThreads) {
+    int n = i / 9, k = i - n * 9;
+    Ws[i] = k < K ? Wg[n * K + k] : 0.f;
+  }
+  __syncthreads();
+  const float4 mu = *reinterpret_cast<const float4*>(sm->mean[net][l] + c4);
+  const float4 is = *reinterpret_cast<const float4*>(sm->inv[net][l] + c4);
+  const float4 sl = *reinterpret_cast<const float4*>(sm->slope + c4);
+  const float4 cg = *reinterpret_cast<const float4*>(sm->cg + c4);
+  const float4 cgx = *reinterpret_cast<const float4*>(sm->cgx + c4);
+  float db4[4] = {0.f, 0.f, 0.f, 0.f}, ds4[4] = {0.f, 0.f, 0.f, 0.f};
+  float accW[4][kZ];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < kZ; ++k) accW[j][k] = 0.f;
+  const int zr = tid >> 1, zk0 = (tid & 1) * 4;      // this thread's float4 of a latent tile
+  for (int t = c.crank; t < ntiles; t += c.csize) {
+    const int row0 = t * kTM, nv = min(kTM, c.B - row0);
+    float4 gg[kTM / 16], uu[kTM / 16];
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      const bool ok = r < nv;
+      const size_t go = (size_t)(row0 + (ok ? r : 0)) * kH + c4;
+      gg[i] = ok ? *reinterpret_cast<const float4*>(g_in + go) : make_float4(0.f, 0.f, 0.f, 0.f);
+      uu[i] = ok ? *reinterpret_cast<const float4*>(u_l + go) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    {
+      // latent tile (normalised with the BatchNorm of the encoder output where it applies; zero beyond nstyle / nv)
+      const float4 v = zr < nv ? *reinterpret_cast<const float4*>(in.src + (size_t)(row0 + zr) * kZ + zk0) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float ov[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = zk0 + e;
+        if (zr < nv && k < K) { if (zmean) ov[e] = (ov[e] - zmean[k]) * zinv[k]; }
+        else ov[e] = 0.f;
+      }
+      *reinterpret_cast<float4*>(Zt + zr * kZ + zk0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    }
+    // du = PReLU'(u) BN'(g) (zero for rows >= nv), kept in registers and written to shared memory for dz
+    float4 dur[kTM / 16];
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const bool valid = ty + 16 * i < nv;
+      const float4 g = gg[i], u = uu[i];
+      float4 du;
+#define RAAE_DU(comp, idx)                                                          \
+      {                                                                             \
+        float xh = (prelu_f(u.comp, sl.comp) - mu.comp) * is.comp;                  \
+        float dh = (g.comp - cg.comp - xh * cgx.comp) * is.comp;                    \
+        bool pos = u.comp > 0.f;                                                    \
+        float d = pos ? dh : sl.comp * dh;                                          \
+        d = valid ? d : 0.f;                                                        \
+        du.comp = d;                                                                \
+        ds4[idx] += (pos || !valid) ? 0.f : u.comp * dh;                            \
+        db4[idx] += d;                                                              \
+      }
+      RAAE_DU(x, 0) RAAE_DU(y, 1) RAAE_DU(z, 2) RAAE_DU(w, 3)
+#undef RAAE_DU
+      dur[i] = du;
+      if (want_out) *reinterpret_cast<float4*>(Dt + (ty + 16 * i) * kLD + c4) = du;
+    }
+    __syncthreads();
+    // dW[c4 + j][k] += du[r][c4 + j] z[r][k]
+#pragma unroll
+    for (int i = 0; i < kTM / 16; ++i) {
+      const int r = ty + 16 * i;
+      const float4 z0 = *reinterpret_cast<const float4*>(Zt + r * kZ);
+      const float4 z1 = *reinterpret_cast<const float4*>(Zt + r * kZ + 4);
+      const float zz[kZ] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+      const float dd[4] = {dur[i].x, dur[i].y, dur[i].z, dur[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < kZ; ++k) accW[j][k] = fmaf(dd[j], zz[k], accW[j][k]);
+    }
+    if (want_out) {
+      // dz[r][k] = sum_n du[r][n] W[n][k]: two threads per row (32 channels each), partial sums combined by shuffle
+      const int r = tid >> 1, half = tid & 1;
+      float s8[kZ];
+#pragma unroll
+      for (int k = 0; k < kZ; ++k) s8[k] = 0.f;
+#pragma unroll 2
+      for (int n4 = 0; n4 < 32; n4 += 4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(Dt + r * kLD + 32 * half + n4);
+        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float* wrow = Ws + (32 * half + n4 + e) * 9;
+#pragma unroll
+          for (int k = 0; k < kZ; ++k) s8[k] = fmaf(dv[e], wrow[k], s8[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kZ; ++k) s8[k] += __shfl_xor_sync(0xffffffffu, s8[k], 1);
+      if (half == 0 && r < nv) {
+        *reinterpret_cast<float4*>(g_out + (size_t)(row0 + r) * kZ) = make_float4(s8[0], s8[1], s8[2], s8[3]);
+        *reinterpret_cast<float4*>(g_out + (size_t)(row0 + r) * kZ + 4) = make_float4(s8[4], s8[5], s8[6], s8[7]);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- reductions over the 16 row groups (fixed order), gradient export, AdamW ----
+  float* gb = gradW + kH * K;    // [64] db | [64] dslope, right behind dW: [W | b | a] is one run of the parameter vector
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    *reinterpret_cast<float4*>(part + ((ty * kH) + c4 + j) * kZ) = make_float4(accW[j][0], accW[j][1], accW[j][2], accW[j][3]);
+    *reinterpret_cast<float4*>(part + ((ty * kH) + c4 + j) * kZ + 4) = make_float4(accW[j][4], accW[j][5], accW[j][6], accW[j][7]);
+  }
+  sm->red[ty][c4 + 0] = db4[0]; sm->red[ty][c4 + 1] = db4[1]; sm->red[ty][c4 + 2] = db4[2]; sm->red[ty][c4 + 3] = db4[3];
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int oo = tid + kThreads * e, n = oo >> 3, k = oo & 7;
+    if (k < K) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) sacc += part[((g * kH) + n) * kZ + k];
+      gradW[n * K + k] = sacc;
+    }
+  }
+  if (tid < kH) { float sacc = 0.f; for (int i = 0; i < 16; ++i) sacc += sm->red[i][tid]; gb[tid] = sacc; }
+  __syncthreads();
+  sm->red[ty][c4 + 0] = ds4[0]; sm->red[ty][c4 + 1] = ds4[1]; sm->red[ty][c4 + 2] = ds4[2]; sm->red[ty][c4 + 3] = ds4[3];
+  __syncthreads();
+  if (tid < kH) { float sacc = 0.f; for (int i = 0; i < 16; ++i) sacc += sm->red[i][tid]; gb[kH + tid] = sacc; }
+  __syncthreads();
+  if (c.csize > 1) cl::sync();                 // every CTA's partial gradients are in place
+  adam_apply(c, sm, o, net, nl.w_off[l], kH * K + 2 * kH, gradW);
+  stage_sync(c);
+}
+
 // backward of a hidden block whose input is another hidden block's panel (K = 64), software-pipelined: the raw
 // g / u / u_prev tiles of tile t+1 are prefetched with cp.async while tile t runs its two contractions.
 __device__ __noinline__ void bwd_hidden64(const Ctx& c_ref, int net, int l, const LayerIn& in_ref, const float* __restrict__ u_l,
@@ -2735,6 +2898,8 @@ __device__ __forceinline__ void bwd_hidden(const Ctx& c, int net, int l, const L
     bwd_wide_img(c, net, l, u_l, g_in, o, c.sc + c.p->sl.xm, c.sc + c.p->sl.xref + c.crank * kMaxDim, nullptr, 0, 0);
   } else if (in.kind == kInWide && in.img == 2 && g_out != nullptr && (c.p->cfg.tensor_cores & 4)) {
     bwd_wide_img(c, net, l, u_l, g_in, o, c.sc + c.p->sl.ym, c.sc + c.p->sl.yref + c.crank * kMaxDim, g_out, in.ld, in.act);
+  } else if (in.kind == kInLatent) {
+    bwd_latent(c, net, l, in, u_l, g_in, g_out, o);
   } else {
     bwd_hidden_edge(c, net, l, in, u_l, g_in, g_out, o);
   }
