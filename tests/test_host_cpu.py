@@ -129,6 +129,14 @@ def test_config_errors_are_reported(built_lib):
             L.query_layout(make_config(dict(base, **bad), n_trials=1))
     with pytest.raises(NotImplementedError):
         make_config(dict(base, gradient_reversal=False), n_trials=1)
+    # contraction groups: bits 0, 1, 2, 4, 5 exist (55 = all of them, the default); bit 3 and anything above bit 5 do not
+    from rankaae_b200.engine import DEFAULT_TENSOR_CORES
+    assert DEFAULT_TENSOR_CORES == 55
+    for ok in (0, 7, 23, 55):
+        L.query_layout(make_config(dict(base, tensor_cores=ok), n_trials=1))
+    for bad in (8, 64, 63):
+        with pytest.raises(L.RaaeError, match="tensor_cores"):
+            L.query_layout(make_config(dict(base, tensor_cores=bad), n_trials=1))
 
 
 def test_no_cpu_fallback(built_lib):
