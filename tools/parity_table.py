@@ -1,16 +1,17 @@
 #!/usr/bin/env python
-"""Builds profiles/parity_r01.md from the gpurun_out/parity_*.json reports written by the last `pytest -m gpu` run.
-usage: python tools/parity_table.py [gpurun_out] > profiles/parity_r01.md"""
+"""Builds profiles/parity_rNN.md from the gpurun_out/parity_*.json reports written by the last `pytest -m gpu` run.
+usage: python tools/parity_table.py [gpurun_out] > profiles/parity_r02.md"""
 import glob
 import json
 import os
 import sys
 
 src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out"
-print("# Parity results on B200, round 1 (from gpurun_out/parity_*.json of the final `pytest -m gpu` run)\n")
+print("# Parity results on B200 (from gpurun_out/parity_*.json of the final `pytest -m gpu` run of the round)\n")
 print("Teacher-forced, same float32-representable state and explicit draws on both sides; oracle in float64.")
-print("`tc23` = default (hidden blocks, encoder input block and decoder output forward on tcgen05, 3xTF32 round-to-nearest")
-print("split), `tc7` = hidden + input blocks only, `tc0` = all-FP32-FMA path.  `f32 yardstick` = error of the SAME oracle code run")
+print("`tc55` = default (hidden blocks, encoder input block, decoder output forward AND backward on tcgen05, 3xTF32 split with a")
+print("rounded high half), `tc23` = the same with the decoder output backward as FP32 FMA, `tc7` = hidden + input blocks only,")
+print("`tc0` = all-FP32-FMA path.  `f32 yardstick` = error of the SAME oracle code run")
 print("in float32 against its float64 run (what the reference's own precision costs on that case); the test band is")
 print("max(2e-3, 3 x yardstick) for gradients.\n")
 print("| suite | case | phase | rows | abs loss err | worst per-network grad rel-L2 | f32 yardstick (worst net) | BN buffer err |")
