@@ -429,8 +429,9 @@ def run_ours(args):
                 "launch_ms": train_ms,
                 "note": "per launch = 5 train batches x T trials; contractions of the hidden blocks, of the encoder input "
                         "block (forward + weight gradient, operand images streamed with bulk copies) and of the decoder "
-                        "output forward run on tcgen05 (kind::tf32, 3xTF32 round-to-nearest split, TMEM accumulators); "
-                        "the decoder output backward, the discriminator, the latent-width layers and all element-wise / "
+                        "output layer (forward and backward, the loss-gradient tile parked in tensor memory) run on tcgen05 "
+                        "(kind::tf32, 3xTF32 split with a rounded high half, TMEM accumulators); "
+                        "the discriminator, the latent-width layers and all element-wise / "
                         "loss stages run on CUDA cores; the kernel is latency-bound at 8 warps/SM, not at either roof "
                         "(profiles/ncu_train_r02.md); achieved = ALGORITHMIC flops (each product once; the 3xTF32 split "
                         "executes 3x that on the tensor pipe: executed_tflops) / launch time; frac is against the dense TF32 "
